@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- genotypes scored per second on B200, the metric of BASELINE.json.
+
+Workload (config.workload): BASELINE.json configs[2], the synthetic genome-wide PRS of
+1,000,000 variants x 500,000 samples, variant-sharded.  It does not fit one GPU (1 TB of int8
+GT), so every rank holds the per-GPU shard of the 8-GPU run -- 125,000 variants x 500,000
+samples = 125 GB of raw BCF GT bytes resident in HBM -- and N ranks score N such shards (weak
+scaling; N = 8 is the whole problem).  One step = one pass of the scoring path over the rank's
+shard (count -> decide -> accumulate for every score row) followed by the cross-rank combine
+of the per-sample partial sums.
+
+value    : genotypes/s, whole job, inputs resident in HBM when the timed region starts.
+e2e      : same metric through npc_score_block with HOST buffers: pinned staging -> H2D ->
+           kernels -> D2H of the scores, every step, on a bounded slice of the same cohort.
+roofline : algorithmic HBM bytes (2 B per genotype + row metadata + sums traffic) / measured time
+           of the scoring kernels, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline : the CPU oracle (a C port of the reference algorithm; the Nim reference cannot be
+           built in this image) on a bounded sample of the same cohort.
+--impl reference : that oracle with all host threads, as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x6E696D70
+N_SAMPLES = 500_000
+V_PER_GPU = 125_000
+MISS_RATE = 0.005
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
+    ap.add_argument("--variants", type=int, default=V_PER_GPU, help="variants per GPU (shard)")
+    ap.add_argument("--block-rows", type=int, default=0, help="score rows per npc_score_block_device call (0 = auto)")
+    ap.add_argument("--e2e-variants", type=int, default=4096)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---- synthetic score rows / cohort parameters -------------------------------------
+
+def cohort_params(v0, V):
+    """Per-variant parameters as a pure function of the variant index: af ~ U(0.01, 0.5),
+    beta ~ N(0, 0.05^2) rounded to 4 decimals, eaf = af rounded, ref == ea for 27% of rows."""
+    rng = np.random.default_rng([SEED, v0])
+    af = rng.uniform(0.01, 0.5, size=V)
+    beta = np.round(rng.normal(0.0, 0.05, size=V), 4)
+    ref_is_ea = (rng.random(V) < 0.27).astype(np.int32)
+    af_thr = (af * 65536).astype(np.uint32)
+    miss_thr = np.full(V, int(MISS_RATE * (1 << 24)), dtype=np.uint32)
+    alt = np.ones(V, dtype=np.int32)
+    return af, beta, ref_is_ea, af_thr, miss_thr, alt
+
+
+def make_rows(dtype, V, af, beta, ref_is_ea):
+    rows = np.zeros(V, dtype=dtype)
+    rows["gt_row"] = np.arange(V)
+    rows["ref_is_ea"] = ref_is_ea
+    rows["eaidx"] = np.where(ref_is_ea == 1, 0, 1)
+    rows["beta"] = beta
+    rows["eaf"] = np.round(af, 4)
+    rows["kind"] = 0
+    return rows
+
+
+# ---- clocks -------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons of one GPU, sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU oracle legs ------------------------------------------------------------------------------
+
+def cpu_oracle_rate(n, seconds, threads):
+    """Time the oracle (tests/orc.py -> oracle/nimpress_oracle.c) on a bounded sample of the same
+    cohort: first a calibration batch, then enough variants for about `seconds` of work."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    stride = -(-2 * n // 128) * 128
+
+    def run(V):
+        af, beta, ref_is_ea, af_thr, miss_thr, alt = cohort_params(0, V)
+        gt = np.zeros((V, stride), dtype=np.int8)
+        orc.synth_fill(gt, n, 0, SEED, af_thr, miss_thr, alt)
+        rows = make_rows(orc.ROW_DTYPE, V, af, beta, ref_is_ea)
+        t0 = time.perf_counter()
+        out = orc.score_matrix(gt, n, 2, rows, threads=threads)
+        dt = time.perf_counter() - t0
+        assert out["nloci"] == V
+        return dt
+
+    v_cal = max(threads * 4, 16)
+    dt = run(v_cal)
+    V = int(min(max(v_cal, seconds / max(dt, 1e-6) * v_cal), 40_000, (24 << 30) // stride))
+    V = max(V - V % threads, threads)
+    dt = run(V)
+    return n * V / dt, V, dt
+
+
+def reference_arm(args):
+    """--impl reference: the CPU implementation of the path (the oracle port; the Nim reference
+    cannot be compiled here) with all host threads, on bounded samples of this workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.samples
+    rates, sample_v, ms = [], 0, []
+    per_step = max(args.cpu_seconds / max(args.steps + args.warmup, 1), 2.0)
+    for i in range(args.warmup + args.steps):
+        r, V, dt = cpu_oracle_rate(n, per_step, threads)
+        if i >= args.warmup:
+            rates.append(r); sample_v = V; ms.append(dt * 1e3)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "genotypes scored/sec (variants x samples)", "value": value,
+        "unit": "genotypes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config3 shard: {n} samples, bounded sample of {sample_v} variants per step",
+                   "samples": n, "variants_per_step": sample_v},
+        "cpu_baseline": {"value": value, "unit": "genotypes/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_v} variants x {n} samples per step, rows split over {threads} threads, "
+                                   "AF-mismatch binomTest (warning only) not run"},
+        "e2e": {"value": value, "unit": "genotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---- B200 arm -------------------------------------------------------------------------------------
+
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import nimpress_b200 as nb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, V = args.samples, args.variants
+    stride = -(-2 * n // 128) * 128
+    block_rows = args.block_rows or max(1, min(V, (48 << 20) // stride))      # ~48 MB tiles: second pass from L2
+    v0 = rank * V                                                             # this rank's slice of the variant axis
+    af, beta, ref_is_ea, af_thr, miss_thr, alt = cohort_params(v0, V)
+    rows = make_rows(nb.ROW_DTYPE, V, af, beta, ref_is_ea)
+
+    eng = nb.Engine(n, max_rows_per_block=max(block_rows, 1), n_slots=0, device=local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_policy()                                                          # nimpress defaults
+    gt = torch.empty((V, stride), dtype=torch.uint8, device=dev)
+    t_af = torch.from_numpy(af_thr.view(np.int32)).to(dev)
+    t_ms = torch.from_numpy(miss_thr.view(np.int32)).to(dev)
+    t_alt = torch.from_numpy(alt).to(dev)
+    eng.synth_fill_device(gt, stride, v0, V, SEED, t_af, t_ms, t_alt)
+    # block-relative row tables, resident on the device (inputs are in HBM before the clock starts)
+    rows_rel = rows.copy()
+    rows_rel["gt_row"] = np.arange(V) % block_rows
+    d_rows = torch.from_numpy(rows_rel.view(np.uint8).reshape(V, -1)).to(dev)
+    torch.cuda.synchronize()
+
+    gather = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    sums_ptr, nloci_ptr = eng.partial_device_ptr()
+
+    class _Wrap:   # expose the library-owned partial sums to torch.distributed without a copy
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+    t_sums = torch.as_tensor(_Wrap(sums_ptr, (n,), "<f8"), device=dev)
+    t_nloci = torch.as_tensor(_Wrap(nloci_ptr, (1,), "<i8"), device=dev)
+
+    def step():
+        eng.reset()
+        for r0 in range(0, V, block_rows):
+            nr = min(block_rows, V - r0)
+            eng.score_block_device(gt[r0], stride, nr, d_rows[r0], n_rows=nr)
+        if world > 1:                                  # combine: gather partials, add in rank order
+            dist.all_gather(gather, t_sums)
+            total = gather[0].clone()
+            for g in gather[1:]:
+                total += g
+            nl = t_nloci.clone()
+            dist.all_reduce(nl)
+            return total, nl
+        return t_sums, t_nloci
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        total, nl = step()
+        ev[i + 1].record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches - l0
+    ms_total = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    genotypes_step = float(n) * V * world
+    value = genotypes_step / (ms_step * 1e-3)
+    assert int(nl.item()) == V * world, (int(nl.item()), V * world)
+
+    # roofline of the scoring kernels of one rank: algorithmic bytes
+    n_blocks = -(-V // block_rows)
+    alg_bytes = 2.0 * n * V + 32.0 * V + 16.0 * n * n_blocks
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "count+decide+accumulate sequence over one shard (all launches of a step)",
+                "algorithmic_bytes_per_step": alg_bytes}
+
+    # end to end through the staged C-ABI call with host buffers
+    e2e = None
+    if not args.no_e2e:
+        Ve = min(args.e2e_variants, V)
+        eb = max(1, min(Ve, (256 << 20) // stride))
+        e_eng = nb.Engine(n, max_rows_per_block=eb, n_slots=3, device=local)
+        e_eng.set_policy()
+        slots = {}
+        host_rows = rows[:Ve].copy()
+        host_rows["gt_row"] = np.arange(Ve) % eb
+        first = gt[:eb].cpu().numpy()
+        for _ in range(3):                              # the pinned ring holds the (synthetic) decoded BCF rows
+            s, view = e_eng.stage_acquire()
+            view[:first.shape[0], :stride] = first
+            slots[s] = view
+            e_eng.score_block(s, 0, host_rows[:0])
+        scores_host = None
+
+        def e2e_step():
+            e_eng.reset()
+            for r0 in range(0, Ve, eb):
+                nr = min(eb, Ve - r0)
+                s, _ = e_eng.stage_acquire()            # blocks until the slot's previous block is done
+                e_eng.score_block(s, nr, host_rows[r0:r0 + nr])
+            return e_eng.finish(want_loci=False)["scores"]
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            scores_host = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": float(n) * Ve * world / dt, "unit": "genotypes/s",
+               "h2d_bytes_per_step": int(stride) * Ve + 32 * Ve, "d2h_bytes_per_step": 8 * n + 8,
+               "variants_per_step": Ve, "ms_per_step": dt * 1e3,
+               "note": "npc_stage_acquire/npc_score_block from pinned host rows + npc_finish D2H; per rank"}
+        assert np.isfinite(scores_host).all()
+        e_eng.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, Vc, dt = cpu_oracle_rate(n, args.cpu_seconds, 1)
+        cpu = {"value": r, "unit": "genotypes/s", "cores": 1, "kind": "port",
+               "sample": f"{Vc} variants x {n} samples of the same cohort, {dt:.1f} s, single thread like the "
+                         "reference; AF-mismatch binomTest (warning only) not run"}
+
+    if rank == 0:
+        line = {
+            "metric": "genotypes scored/sec (variants x samples)", "value": value, "unit": "genotypes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config3 genome-wide PRS shard: {V} variants x {n} samples per GPU "
+                                   f"(1/8 of 1M x 500k), int8 diploid BCF GT, {MISS_RATE:.1%} missing, default policies",
+                       "samples": n, "variants_per_gpu": V, "block_rows": block_rows, "parallelism": f"variant-shard x{world}",
+                       "l2": "inputs larger than L2 (shard >> 126 MB), no flush needed"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+/*
+ * nimpress_cuda.h -- C ABI of libnimpress_cuda.so, the B200 (sm_100a) scoring engine.
+ *
+ * The reference (mpinese/nimpress, one Nim file) has no plugin or FFI interface of its own;
+ * its scoring path is the body of `computePolygenicScores` (src/nimpress.nim:592-649) and the
+ * procs it calls per locus.  This library sits exactly where those procs sit, so that a host
+ * (Nim via {.importc, dynlib.}, C++, or ctypes) keeps file reading / locus matching and hands
+ * the per-locus genotype work to the GPU:
+ *
+ *   reference proc (src/nimpress.nim)                replaced by
+ *   ------------------------------------------------ -------------------------------------
+ *   getRawDosages        :367-391  (GT decode)        count + accumulate kernels (npc_score_block*)
+ *   tallyAlleles         :32-47    (ngt/nmiss/neff)   count kernel, integer-exact
+ *   getImputedDosages    :565-571  (--maxmis rule)    decide kernel (IEEE fp64 divide + strict >)
+ *   imputeLocusDosages   :417-447  (locus constant)   decide kernel (constant rows)
+ *   absent-variant rule  :536-551                     decide kernel (kind = NPC_KIND_ABSENT)
+ *   imputeSampleDosages  :450-481  (per-sample fill)  decide kernel + accumulate LUT
+ *   scores[i] += d*beta  :639-641                     accumulate kernel, fp64, score-row order
+ *   scores /= 2*nloci; += offset :643-649             npc_finish
+ *
+ * What stays on the host: coverage lookup (:313-345), findVariant (:353-364), the FILTER
+ * string test (:553) and eaidx (:375-379); they enter as npc_row.kind / npc_row.eaidx.
+ *
+ * Conventions: plain C, no exceptions across the boundary.  Every call returns 0 (NPC_OK) or
+ * a negative NPC_E* code; npc_last_error() gives the text.  One producer thread per context,
+ * one context per GPU.  The library owns device memory and its pinned staging ring; buffers
+ * passed by pointer belong to the caller and may be reused when the call returns.  There is
+ * no CPU fallback: without a usable sm_100 device npc_create fails with NPC_ECUDA.
+ *
+ * Genotype rows are raw BCF FORMAT/GT payloads, untouched: per sample `ploidy` values of
+ * `gt_width` bytes (1, 2 or 4), value = (allele+1)<<1 | phased, 0|phase = missing allele,
+ * width-specific sentinels missing = MIN, vector_end = MIN+1 (both ignored, and a vector_end
+ * ends the sample), rows `row_stride` bytes apart (row_stride % 16 == 0).
+ */
+#ifndef NIMPRESS_CUDA_H
+#define NIMPRESS_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPC_OK            0
+#define NPC_EINVAL       -1   /* bad argument                                  */
+#define NPC_ECUDA        -2   /* CUDA runtime error, or no sm_100 device       */
+#define NPC_ENOMEM       -3   /* host or device allocation failed              */
+#define NPC_ESTATE       -4   /* call out of sequence (e.g. slot not acquired) */
+#define NPC_EUNSUPPORTED -5
+
+/* ImputeMethodLocus / Missing / Sample, declaration order of src/nimpress.nim:412-414 */
+enum { NPC_LOCUS_PS = 0, NPC_LOCUS_HOMREF = 1, NPC_LOCUS_FAIL = 2, NPC_LOCUS_IGNORE = 3 };
+enum { NPC_MISSING_HOMREF = 0, NPC_MISSING_IGNORE = 1 };
+enum { NPC_SAMPLE_PS = 0, NPC_SAMPLE_HOMREF = 1, NPC_SAMPLE_FAIL = 2, NPC_SAMPLE_INT_PS = 3,
+       NPC_SAMPLE_INT_FAIL = 4 };
+
+/* npc_row.kind: what the host already decided for the score row.  Same numbering as the
+ * class reported back in npc_locus.klass; NPC_CLASS_MAXMIS is only ever an output. */
+enum { NPC_KIND_GT = 0,      /* record found, FILTER passes: decode its genotypes          */
+       NPC_KIND_NOTCOV = 1,  /* --cov given and locus not covered      (:526-531)           */
+       NPC_KIND_ABSENT = 2,  /* findVariant returned nil               (:536-551)           */
+       NPC_KIND_FILTER = 3,  /* FILTER not in {".","PASS"}, !ignorefilt (:553-558)          */
+       NPC_CLASS_MAXMIS = 4  /* nmissing/n > maxmis                     (:565-571)          */ };
+
+typedef struct npc_ctx npc_ctx;
+
+typedef struct {
+    int32_t imp_locus;     /* NPC_LOCUS_*   (--imp-locus,   default ps)     */
+    int32_t imp_missing;   /* NPC_MISSING_* (--imp-missing, default homref) */
+    int32_t imp_sample;    /* NPC_SAMPLE_*  (--imp-sample,  default int_ps) */
+    int32_t reserved;
+    int64_t mincs;         /* --mincs  (default 100)  */
+    double  maxmis;        /* --maxmis (default 0.05) */
+} npc_policy;
+
+/* One score-file row, in score-file order (ScoreEntry, src/nimpress.nim:221-228, after the
+ * host-side lookup).  Several rows may name the same gt_row (different effect alleles). */
+typedef struct {
+    int32_t gt_row;        /* row of this block's genotype slab; -1 when kind != NPC_KIND_GT */
+    int32_t eaidx;         /* 0 = REF is the effect allele, k = k-th ALT (:375-379)          */
+    double  beta;
+    double  eaf;
+    int32_t ref_is_ea;     /* refseq == easeq: the homref dosage is 2.0 instead of 0.0       */
+    int32_t kind;          /* NPC_KIND_*                                                     */
+} npc_row;
+
+/* Per-row outcome, bit-exact against the reference's decision for that locus. */
+typedef struct {
+    int32_t klass;         /* 0 OK, else NPC_KIND_NOTCOV/ABSENT/FILTER or NPC_CLASS_MAXMIS   */
+    int32_t used;          /* 1 = entered the sum and nloci (getImputedDosages returned true) */
+    int32_t eaidx;         /* echo; -1 when the locus had no record                          */
+    int32_t reserved;
+    int64_t ngt;           /* tallyAlleles (:32-47) as exact integers; -1 when not tallied   */
+    int64_t nmiss;
+    int64_t neff;
+    double  imputed;       /* OK: dosage given to missing samples; else the locus constant   */
+} npc_locus;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* n_samples: samples held by THIS context (the whole cohort, or this GPU's slab when the
+ * sample axis is sharded).  max_rows_per_block bounds both genotype rows and score rows of
+ * one npc_score_block* call.  n_slots >= 2 pinned staging slots (0 = no staging ring: only
+ * the *_device entry points are usable). */
+int  npc_create(npc_ctx **out, int device, int64_t n_samples, int32_t ploidy, int32_t gt_width,
+                int64_t max_rows_per_block, int32_t n_slots);
+void npc_destroy(npc_ctx *ctx);
+const char *npc_last_error(const npc_ctx *ctx);   /* ctx may be NULL: text of the last npc_create failure */
+
+/* Launch on an existing CUDA stream (cudaStream_t as void*) instead of the context's own;
+ * NULL restores the internal stream.  For callers that time or order work themselves. */
+int npc_set_stream(npc_ctx *ctx, void *cuda_stream);
+
+int npc_set_policy(npc_ctx *ctx, const npc_policy *p);
+
+/* Cohort size used by the --maxmis rule when the sample axis is sharded across contexts
+ * (defaults to n_samples). */
+int npc_set_cohort_size(npc_ctx *ctx, int64_t n_total);
+
+/* Zero the per-sample sums, nloci and the locus log: start of a computePolygenicScores call
+ * (src/nimpress.nim:626-632). */
+int npc_reset(npc_ctx *ctx);
+
+/* ---- streaming blocks from host memory (pinned, double-buffered) ---------------------- */
+
+/* Blocks until a staging slot is free, then lends it: the caller copies up to
+ * max_rows_per_block raw GT rows to gt_host + r * row_stride. */
+int npc_stage_acquire(npc_ctx *ctx, int32_t *slot, void **gt_host, int64_t *row_stride);
+
+/* Asynchronous: H2D copy of n_gt_rows rows of `slot`, then for the n_rows score rows
+ * count -> decide -> accumulate, in row order.  The slot returns to the ring when the GPU is
+ * done with it.  `rows` is copied before the call returns. */
+int npc_score_block(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, const npc_row *rows, int64_t n_rows);
+
+/* ---- blocks already resident in device memory ------------------------------------------ */
+
+/* Same work on a device-resident slab (gt_dev % 16 == 0).  rows: host pointer, or a device
+ * pointer when rows_on_device != 0.  Asynchronous. */
+int npc_score_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows,
+                           const npc_row *rows, int64_t n_rows, int32_t rows_on_device);
+
+/* Split form for a sample-sharded cohort: (1) per-row (nmiss, neff) of this context's slab
+ * into counts_dev[n_rows][2] (int64, device), (2) the caller sums counts across contexts
+ * (exact integers: any order), (3) decide + accumulate with the summed counts. */
+int npc_count_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows,
+                           const npc_row *rows, int64_t n_rows, int32_t rows_on_device,
+                           int64_t *counts_dev);
+int npc_accumulate_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows,
+                                const npc_row *rows, int64_t n_rows, int32_t rows_on_device,
+                                const int64_t *counts_dev);
+
+/* ---- results ---------------------------------------------------------------------------- */
+
+/* Waits for all submitted blocks.  scores_out[n_samples] = sum / (2*nloci) + offset
+ * (:643-649; nloci == 0 gives NaN like the reference).  loci_out (may be NULL) receives the
+ * per-row outcomes of every row submitted since npc_reset, in submission order. */
+int npc_finish(npc_ctx *ctx, double offset, double *scores_out, int64_t *nloci_out,
+               npc_locus *loci_out, int64_t loci_cap, int64_t *n_loci_out);
+
+/* Variant-sharded cohorts: each context yields its raw partial sums and nloci; the caller
+ * adds partials in shard order and applies npc_normalise once. */
+int npc_partial(npc_ctx *ctx, double *sums_out, int64_t *nloci_out,
+                npc_locus *loci_out, int64_t loci_cap, int64_t *n_loci_out);
+int npc_partial_device_ptr(npc_ctx *ctx, double **sums_dev, int64_t **nloci_dev);
+/* sums[i] = sums[i] / (2*nloci) + offset on host memory: the reference's epilogue. */
+void npc_normalise(double *sums, int64_t n, int64_t nloci, double offset);
+
+/* Kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t npc_launch_count(const npc_ctx *ctx);
+
+/* ---- utilities (tests / bench) ----------------------------------------------------------- */
+
+/* Deterministic synthetic cohort written straight into device memory: int8 diploid GT rows
+ * for variants v0..v0+n_rows, a pure function of (seed, variant, sample); per-row arrays are
+ * device pointers.  Byte-identical to the oracle's generator. */
+int npc_synth_fill_device(npc_ctx *ctx, void *gt_dev, int64_t row_stride, int64_t v0, int64_t n_rows,
+                          uint64_t seed, const uint32_t *af_thr16_dev, const uint32_t *miss_thr24_dev,
+                          const int32_t *alt_code_dev);
+
+int npc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

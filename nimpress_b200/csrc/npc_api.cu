@@ -1,0 +1,408 @@
+// npc_api.cu -- C ABI of libnimpress_cuda.so (include/nimpress_cuda.h): contexts, the pinned
+// double-buffered staging ring, stream/event plumbing and kernel launches.  No CPU fallback:
+// every entry point either runs the CUDA kernels or fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "npc_kernels.cuh"
+
+using namespace npc;
+
+static thread_local std::string g_create_error;
+
+struct npc_ctx {
+    int device = 0;
+    int64_t n = 0;
+    int32_t ploidy = 2, width = 1;
+    int64_t max_rows = 0;
+    int32_t n_slots = 0;
+    int64_t row_stride = 0;                 // of the staging ring
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    std::vector<uint8_t *> h_gt, d_gt;
+    std::vector<cudaEvent_t> ev_h2d, ev_done;
+    std::vector<int> slot_state;            // 0 free, 1 lent to the caller, 2 in flight
+    int next_slot = 0;
+    double *d_sums = nullptr, *d_out = nullptr;
+    ull *d_nloci = nullptr, *d_counts = nullptr;
+    npc_row *d_rows = nullptr;
+    RowP *d_rowp = nullptr;
+    npc_locus *d_log = nullptr;
+    int64_t log_cap = 0, log_len = 0;
+    Policy pol{};
+    int64_t launches = 0;
+    std::string err;
+};
+
+#define NPC_CUDA(ctx, call)                                                                       \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return e_ == cudaErrorMemoryAllocation ? NPC_ENOMEM : NPC_ECUDA;                      \
+        }                                                                                         \
+    } while (0)
+
+static int fail(npc_ctx *ctx, int code, const char *msg) {
+    ctx->err = msg;
+    return code;
+}
+
+extern "C" int npc_version(void) { return 100; }
+
+extern "C" const char *npc_last_error(const npc_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" void npc_destroy(npc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto p : ctx->h_gt) if (p) cudaFreeHost(p);
+    for (auto p : ctx->d_gt) if (p) cudaFree(p);
+    for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
+    cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+static int create_impl(npc_ctx *c) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(c, NPC_ECUDA, "no CUDA device: libnimpress_cuda has no CPU fallback");
+    if (c->device < 0 || c->device >= ndev) return fail(c, NPC_EINVAL, "device index out of range");
+    NPC_CUDA(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    NPC_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10) return fail(c, NPC_ECUDA, "device is not sm_100 (B200): kernels are built for sm_100a only");
+    NPC_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    NPC_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    const int64_t n1 = std::max<int64_t>(c->n, 1), r1 = std::max<int64_t>(c->max_rows, 1);
+    NPC_CUDA(c, cudaMalloc(&c->d_sums, n1 * sizeof(double)));
+    NPC_CUDA(c, cudaMalloc(&c->d_out, n1 * sizeof(double)));
+    NPC_CUDA(c, cudaMalloc(&c->d_nloci, sizeof(ull)));
+    NPC_CUDA(c, cudaMalloc(&c->d_counts, r1 * 2 * sizeof(ull)));
+    NPC_CUDA(c, cudaMalloc(&c->d_rows, r1 * sizeof(npc_row)));
+    NPC_CUDA(c, cudaMalloc(&c->d_rowp, r1 * sizeof(RowP)));
+    c->log_cap = std::max<int64_t>(r1, 1024);
+    NPC_CUDA(c, cudaMalloc(&c->d_log, c->log_cap * sizeof(npc_locus)));
+    c->row_stride = ((c->n * c->ploidy * c->width + 127) / 128) * 128;
+    if (c->row_stride == 0) c->row_stride = 128;
+    c->h_gt.assign(c->n_slots, nullptr); c->d_gt.assign(c->n_slots, nullptr);
+    c->ev_h2d.assign(c->n_slots, nullptr); c->ev_done.assign(c->n_slots, nullptr);
+    c->slot_state.assign(c->n_slots, 0);
+    for (int s = 0; s < c->n_slots; s++) {
+        const size_t bytes = (size_t)c->row_stride * (size_t)r1;
+        NPC_CUDA(c, cudaMallocHost(&c->h_gt[s], bytes));
+        NPC_CUDA(c, cudaMalloc(&c->d_gt[s], bytes));
+        NPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_h2d[s], cudaEventDisableTiming));
+        NPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming));
+    }
+    NPC_CUDA(c, cudaMemsetAsync(c->d_sums, 0, n1 * sizeof(double), c->stream));
+    NPC_CUDA(c, cudaMemsetAsync(c->d_nloci, 0, sizeof(ull), c->stream));
+    NPC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NPC_OK;
+}
+
+extern "C" int npc_create(npc_ctx **out, int device, int64_t n_samples, int32_t ploidy, int32_t gt_width,
+                          int64_t max_rows_per_block, int32_t n_slots) {
+    if (!out) return NPC_EINVAL;
+    *out = nullptr;
+    if (n_samples < 0 || ploidy < 1 || ploidy > 64 || (gt_width != 1 && gt_width != 2 && gt_width != 4) ||
+        max_rows_per_block < 1 || n_slots < 0 || n_slots == 1) {
+        g_create_error = "npc_create: invalid argument";
+        return NPC_EINVAL;
+    }
+    npc_ctx *c = new npc_ctx();
+    c->device = device; c->n = n_samples; c->ploidy = ploidy; c->width = gt_width;
+    c->max_rows = max_rows_per_block; c->n_slots = n_slots;
+    c->pol.imp_locus = NPC_LOCUS_PS; c->pol.imp_missing = NPC_MISSING_HOMREF; c->pol.imp_sample = NPC_SAMPLE_INT_PS;
+    c->pol.mincs = 100; c->pol.maxmis = 0.05; c->pol.n_total = n_samples;      // defaults of main (:670-687)
+    int rc = create_impl(c);
+    if (rc != NPC_OK) {
+        g_create_error = c->err;
+        npc_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return NPC_OK;
+}
+
+extern "C" int npc_set_stream(npc_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return NPC_EINVAL;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NPC_OK;
+}
+
+extern "C" int npc_set_policy(npc_ctx *ctx, const npc_policy *p) {
+    if (!ctx || !p) return NPC_EINVAL;
+    if (p->imp_locus < 0 || p->imp_locus > 3 || p->imp_missing < 0 || p->imp_missing > 1 || p->imp_sample < 0 ||
+        p->imp_sample > 4)
+        return fail(ctx, NPC_EINVAL, "npc_set_policy: unknown imputation method");
+    ctx->pol.imp_locus = p->imp_locus; ctx->pol.imp_missing = p->imp_missing; ctx->pol.imp_sample = p->imp_sample;
+    ctx->pol.mincs = p->mincs; ctx->pol.maxmis = p->maxmis;
+    return NPC_OK;
+}
+
+extern "C" int npc_set_cohort_size(npc_ctx *ctx, int64_t n_total) {
+    if (!ctx || n_total < 0) return NPC_EINVAL;
+    ctx->pol.n_total = n_total;
+    return NPC_OK;
+}
+
+extern "C" int npc_reset(npc_ctx *ctx) {
+    if (!ctx) return NPC_EINVAL;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    NPC_CUDA(ctx, cudaMemsetAsync(ctx->d_sums, 0, std::max<int64_t>(ctx->n, 1) * sizeof(double), ctx->stream));
+    NPC_CUDA(ctx, cudaMemsetAsync(ctx->d_nloci, 0, sizeof(ull), ctx->stream));
+    ctx->log_len = 0;
+    return NPC_OK;
+}
+
+extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- internals ---------------------------------------------------------------------------
+
+static int ensure_log(npc_ctx *c, int64_t extra) {
+    if (c->log_len + extra <= c->log_cap) return NPC_OK;
+    int64_t cap = std::max(c->log_cap * 2, c->log_len + extra);
+    npc_locus *nl = nullptr;
+    NPC_CUDA(c, cudaMalloc(&nl, cap * sizeof(npc_locus)));
+    NPC_CUDA(c, cudaMemcpyAsync(nl, c->d_log, c->log_len * sizeof(npc_locus), cudaMemcpyDeviceToDevice, c->stream));
+    NPC_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_log);
+    c->d_log = nl; c->log_cap = cap;
+    return NPC_OK;
+}
+
+static int check_block(npc_ctx *c, const void *gt, int64_t row_stride, int64_t n_gt_rows, const npc_row *rows,
+                       int64_t n_rows) {
+    if (!c) return NPC_EINVAL;
+    if (n_rows < 0 || n_gt_rows < 0 || n_rows > c->max_rows || n_gt_rows > c->max_rows)
+        return fail(c, NPC_EINVAL, "block larger than max_rows_per_block");
+    if (n_rows && !rows) return fail(c, NPC_EINVAL, "rows is NULL");
+    if (n_gt_rows && (!gt || ((uintptr_t)gt & 15) || (row_stride & 15) || row_stride < c->n * c->ploidy * c->width))
+        return fail(c, NPC_EINVAL, "genotype slab must be 16-byte aligned with row_stride % 16 == 0 and >= n*ploidy*width");
+    return NPC_OK;
+}
+
+// rows -> d_rows on the compute stream.  A pageable source is staged by the runtime before the
+// call returns, so the caller may reuse `rows` immediately.
+static int upload_rows(npc_ctx *c, const npc_row *rows, int64_t n_rows, int on_device, const npc_row **d_rows) {
+    if (on_device) { *d_rows = rows; return NPC_OK; }
+    NPC_CUDA(c, cudaMemcpyAsync(c->d_rows, rows, n_rows * sizeof(npc_row), cudaMemcpyHostToDevice, c->stream));
+    *d_rows = c->d_rows;
+    return NPC_OK;
+}
+
+static int launch_count(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows,
+                        ull *counts) {
+    NPC_CUDA(c, cudaMemsetAsync(counts, 0, n_rows * 2 * sizeof(ull), c->stream));
+    if (n_rows == 0 || c->n == 0) return NPC_OK;
+    if (c->width == 1 && c->ploidy == 2) {
+        const int64_t nchunks = (c->n + 7) / 8;
+        const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>((nchunks + 1023) / 1024, 1), 65535);
+        k_count_i8x2<<<dim3((unsigned)n_rows, slabs), 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, counts);
+    } else {
+        const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>((c->n + 2047) / 2048, 1), 65535);
+        dim3 grid((unsigned)n_rows, slabs);
+        if (c->width == 1) k_count_generic<int8_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, c->ploidy, counts);
+        else if (c->width == 2) k_count_generic<int16_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, c->ploidy, counts);
+        else k_count_generic<int32_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, c->ploidy, counts);
+    }
+    c->launches++;
+    NPC_CUDA(c, cudaGetLastError());
+    return NPC_OK;
+}
+
+static int launch_decide_accum(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows,
+                               int64_t n_rows, const ull *counts) {
+    if (n_rows == 0) return NPC_OK;
+    int rc = ensure_log(c, n_rows);
+    if (rc) return rc;
+    k_decide<<<(unsigned)((n_rows + 127) / 128), 128, 0, c->stream>>>(d_rows, n_rows, counts, c->pol, c->n, c->d_rowp,
+                                                                      c->d_log + c->log_len, c->d_nloci);
+    c->launches++;
+    NPC_CUDA(c, cudaGetLastError());
+    c->log_len += n_rows;
+    if (c->n == 0) return NPC_OK;
+    if (c->width == 1 && c->ploidy == 2) {
+        const int64_t nchunks = (c->n + 7) / 8;
+        k_accum_i8x2<16, 8><<<(unsigned)((nchunks + 255) / 256), 256, 0, c->stream>>>(gt, row_stride, c->d_rowp, n_rows,
+                                                                                     c->n, c->d_sums);
+    } else {
+        const unsigned grid = (unsigned)((c->n + 255) / 256);
+        if (c->width == 1) k_accum_generic<int8_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, c->d_rowp, n_rows, c->n, c->ploidy, c->d_sums);
+        else if (c->width == 2) k_accum_generic<int16_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, c->d_rowp, n_rows, c->n, c->ploidy, c->d_sums);
+        else k_accum_generic<int32_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, c->d_rowp, n_rows, c->n, c->ploidy, c->d_sums);
+    }
+    c->launches++;
+    NPC_CUDA(c, cudaGetLastError());
+    return NPC_OK;
+}
+
+// ---- staged blocks -----------------------------------------------------------------------
+
+extern "C" int npc_stage_acquire(npc_ctx *ctx, int32_t *slot, void **gt_host, int64_t *row_stride) {
+    if (!ctx || !slot || !gt_host || !row_stride) return NPC_EINVAL;
+    if (ctx->n_slots == 0) return fail(ctx, NPC_ESTATE, "context was created without a staging ring");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int s = ctx->next_slot;
+    if (ctx->slot_state[s] == 1) return fail(ctx, NPC_ESTATE, "all staging slots are lent out: submit one first");
+    if (ctx->slot_state[s] == 2) {
+        NPC_CUDA(ctx, cudaEventSynchronize(ctx->ev_done[s]));
+        ctx->slot_state[s] = 0;
+    }
+    ctx->slot_state[s] = 1;
+    ctx->next_slot = (s + 1) % ctx->n_slots;
+    *slot = s; *gt_host = ctx->h_gt[s]; *row_stride = ctx->row_stride;
+    return NPC_OK;
+}
+
+extern "C" int npc_score_block(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, const npc_row *rows, int64_t n_rows) {
+    if (!ctx) return NPC_EINVAL;
+    if (slot < 0 || slot >= ctx->n_slots || ctx->slot_state[slot] != 1)
+        return fail(ctx, NPC_ESTATE, "slot was not acquired");
+    int rc = check_block(ctx, ctx->d_gt[slot], ctx->row_stride, n_gt_rows, rows, n_rows);
+    if (rc) return rc;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_gt_rows)
+        NPC_CUDA(ctx, cudaMemcpyAsync(ctx->d_gt[slot], ctx->h_gt[slot], (size_t)n_gt_rows * ctx->row_stride,
+                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+    NPC_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+    NPC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+    const npc_row *d_rows;
+    if ((rc = upload_rows(ctx, rows, n_rows, 0, &d_rows))) return rc;
+    if ((rc = launch_count(ctx, ctx->d_gt[slot], ctx->row_stride, d_rows, n_rows, ctx->d_counts))) return rc;
+    if ((rc = launch_decide_accum(ctx, ctx->d_gt[slot], ctx->row_stride, d_rows, n_rows, ctx->d_counts))) return rc;
+    // npc_stage_acquire waits on ev_done before lending the slot again, so the next H2D into
+    // it cannot overtake these kernels and copies into OTHER slots overlap them freely
+    NPC_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+    ctx->slot_state[slot] = 2;
+    return NPC_OK;
+}
+
+// ---- device-resident blocks ----------------------------------------------------------------
+
+extern "C" int npc_score_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows,
+                                      const npc_row *rows, int64_t n_rows, int32_t rows_on_device) {
+    int rc = check_block(ctx, gt_dev, row_stride, n_gt_rows, rows, n_rows);
+    if (rc) return rc;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const npc_row *d_rows;
+    if ((rc = upload_rows(ctx, rows, n_rows, rows_on_device, &d_rows))) return rc;
+    if ((rc = launch_count(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows, ctx->d_counts))) return rc;
+    return launch_decide_accum(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows, ctx->d_counts);
+}
+
+extern "C" int npc_count_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows,
+                                      const npc_row *rows, int64_t n_rows, int32_t rows_on_device,
+                                      int64_t *counts_dev) {
+    int rc = check_block(ctx, gt_dev, row_stride, n_gt_rows, rows, n_rows);
+    if (rc) return rc;
+    if (!counts_dev) return fail(ctx, NPC_EINVAL, "counts_dev is NULL");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const npc_row *d_rows;
+    if ((rc = upload_rows(ctx, rows, n_rows, rows_on_device, &d_rows))) return rc;
+    return launch_count(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows, (ull *)counts_dev);
+}
+
+extern "C" int npc_accumulate_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows,
+                                           const npc_row *rows, int64_t n_rows, int32_t rows_on_device,
+                                           const int64_t *counts_dev) {
+    int rc = check_block(ctx, gt_dev, row_stride, n_gt_rows, rows, n_rows);
+    if (rc) return rc;
+    if (!counts_dev) return fail(ctx, NPC_EINVAL, "counts_dev is NULL");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const npc_row *d_rows;
+    if ((rc = upload_rows(ctx, rows, n_rows, rows_on_device, &d_rows))) return rc;
+    return launch_decide_accum(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows, (const ull *)counts_dev);
+}
+
+// ---- results -------------------------------------------------------------------------------
+
+static int fetch_log(npc_ctx *c, npc_locus *loci_out, int64_t loci_cap, int64_t *n_loci_out) {
+    if (n_loci_out) *n_loci_out = c->log_len;
+    if (loci_out) {
+        if (loci_cap < c->log_len) return fail(c, NPC_EINVAL, "loci_out too small");
+        NPC_CUDA(c, cudaMemcpyAsync(loci_out, c->d_log, c->log_len * sizeof(npc_locus), cudaMemcpyDeviceToHost, c->stream));
+    }
+    return NPC_OK;
+}
+
+extern "C" int npc_finish(npc_ctx *ctx, double offset, double *scores_out, int64_t *nloci_out, npc_locus *loci_out,
+                          int64_t loci_cap, int64_t *n_loci_out) {
+    if (!ctx || !scores_out) return NPC_EINVAL;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n) {
+        k_finalize<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_sums, ctx->n, ctx->d_nloci, offset, ctx->d_out);
+        ctx->launches++;
+        NPC_CUDA(ctx, cudaGetLastError());
+        NPC_CUDA(ctx, cudaMemcpyAsync(scores_out, ctx->d_out, ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ull nl = 0;
+    NPC_CUDA(ctx, cudaMemcpyAsync(&nl, ctx->d_nloci, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = fetch_log(ctx, loci_out, loci_cap, n_loci_out);
+    if (rc) return rc;
+    NPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nloci_out) *nloci_out = (int64_t)nl;
+    return NPC_OK;
+}
+
+extern "C" int npc_partial(npc_ctx *ctx, double *sums_out, int64_t *nloci_out, npc_locus *loci_out, int64_t loci_cap,
+                           int64_t *n_loci_out) {
+    if (!ctx || !sums_out) return NPC_EINVAL;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n)
+        NPC_CUDA(ctx, cudaMemcpyAsync(sums_out, ctx->d_sums, ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ull nl = 0;
+    NPC_CUDA(ctx, cudaMemcpyAsync(&nl, ctx->d_nloci, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = fetch_log(ctx, loci_out, loci_cap, n_loci_out);
+    if (rc) return rc;
+    NPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nloci_out) *nloci_out = (int64_t)nl;
+    return NPC_OK;
+}
+
+extern "C" int npc_partial_device_ptr(npc_ctx *ctx, double **sums_dev, int64_t **nloci_dev) {
+    if (!ctx) return NPC_EINVAL;
+    if (sums_dev) *sums_dev = ctx->d_sums;
+    if (nloci_dev) *nloci_dev = (int64_t *)ctx->d_nloci;
+    return NPC_OK;
+}
+
+extern "C" void npc_normalise(double *sums, int64_t n, int64_t nloci, double offset) {
+    // host mirror of k_finalize; volatile keeps the two roundings apart under any -ffp-contract
+    const double denom = (double)nloci * 2.0;
+    for (int64_t i = 0; i < n; i++) {
+        volatile double q = sums[i] / denom;
+        sums[i] = q + offset;
+    }
+}
+
+extern "C" int npc_synth_fill_device(npc_ctx *ctx, void *gt_dev, int64_t row_stride, int64_t v0, int64_t n_rows,
+                                     uint64_t seed, const uint32_t *af_thr16_dev, const uint32_t *miss_thr24_dev,
+                                     const int32_t *alt_code_dev) {
+    if (!ctx || !gt_dev || ((uintptr_t)gt_dev & 15) || (row_stride & 15) || row_stride < ctx->n * 2 || n_rows < 0)
+        return ctx ? fail(ctx, NPC_EINVAL, "npc_synth_fill_device: bad slab") : NPC_EINVAL;
+    if (ctx->width != 1 || ctx->ploidy != 2) return fail(ctx, NPC_EUNSUPPORTED, "synthetic cohort is int8 diploid");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nchunks = (ctx->n + 7) / 8;
+    const unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>((nchunks + 255) / 256, 1), 4096);
+    for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, n_rows - r0);
+        k_synth<<<dim3(gx, (unsigned)nr), 256, 0, ctx->stream>>>((uint8_t *)gt_dev + r0 * row_stride, row_stride, ctx->n,
+                                                                v0 + r0, seed, af_thr16_dev + r0, miss_thr24_dev + r0,
+                                                                alt_code_dev + r0);
+        ctx->launches++;
+        NPC_CUDA(ctx, cudaGetLastError());
+    }
+    return NPC_OK;
+}

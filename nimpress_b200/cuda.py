@@ -1,0 +1,218 @@
+"""ctypes binding of libnimpress_cuda.so (include/nimpress_cuda.h).
+
+Fails loudly: a missing library or a missing sm_100 device raises; nothing here computes on
+the CPU."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+LOCUS = {"ps": 0, "homref": 1, "fail": 2, "ignore": 3}          # ImputeMethodLocus  (src/nimpress.nim:412)
+MISSING = {"homref": 0, "ignore": 1}                             # ImputeMethodMissing (:413)
+SAMPLE = {"ps": 0, "homref": 1, "fail": 2, "int_ps": 3, "int_fail": 4}   # ImputeMethodSample (:414)
+KIND_GT, KIND_NOTCOV, KIND_ABSENT, KIND_FILTER, CLASS_MAXMIS = range(5)
+
+ROW_DTYPE = np.dtype([("gt_row", "<i4"), ("eaidx", "<i4"), ("beta", "<f8"), ("eaf", "<f8"),
+                      ("ref_is_ea", "<i4"), ("kind", "<i4")], align=True)
+LOCUS_DTYPE = np.dtype([("klass", "<i4"), ("used", "<i4"), ("eaidx", "<i4"), ("reserved", "<i4"),
+                        ("ngt", "<i8"), ("nmiss", "<i8"), ("neff", "<i8"), ("imputed", "<f8")], align=True)
+assert ROW_DTYPE.itemsize == 32 and LOCUS_DTYPE.itemsize == 48
+
+
+class NpcError(RuntimeError):
+    pass
+
+
+class _Policy(C.Structure):
+    _fields_ = [("imp_locus", C.c_int32), ("imp_missing", C.c_int32), ("imp_sample", C.c_int32),
+                ("reserved", C.c_int32), ("mincs", C.c_int64), ("maxmis", C.c_double)]
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libnimpress_cuda.so")
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libnimpress_cuda.so and declare every export of include/nimpress_cuda.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise NpcError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pi64 = C.POINTER(C.c_int64)
+    sig = {
+        "npc_create": (C.c_int, [C.POINTER(vp), C.c_int, i64, i32, i32, i64, i32]),
+        "npc_destroy": (None, [vp]),
+        "npc_last_error": (C.c_char_p, [vp]),
+        "npc_set_stream": (C.c_int, [vp, vp]),
+        "npc_set_policy": (C.c_int, [vp, C.POINTER(_Policy)]),
+        "npc_set_cohort_size": (C.c_int, [vp, i64]),
+        "npc_reset": (C.c_int, [vp]),
+        "npc_stage_acquire": (C.c_int, [vp, C.POINTER(i32), C.POINTER(vp), pi64]),
+        "npc_score_block": (C.c_int, [vp, i32, i64, vp, i64]),
+        "npc_score_block_device": (C.c_int, [vp, vp, i64, i64, vp, i64, i32]),
+        "npc_count_block_device": (C.c_int, [vp, vp, i64, i64, vp, i64, i32, vp]),
+        "npc_accumulate_block_device": (C.c_int, [vp, vp, i64, i64, vp, i64, i32, vp]),
+        "npc_finish": (C.c_int, [vp, f64, vp, pi64, vp, i64, pi64]),
+        "npc_partial": (C.c_int, [vp, vp, pi64, vp, i64, pi64]),
+        "npc_partial_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "npc_normalise": (None, [vp, i64, i64, f64]),
+        "npc_launch_count": (i64, [vp]),
+        "npc_synth_fill_device": (C.c_int, [vp, vp, i64, i64, i64, C.c_uint64, vp, vp, vp]),
+        "npc_version": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError if the symbol is missing
+        fn.restype, fn.argtypes = res, args
+    L._npc_symbols = sorted(sig)
+    _lib = L
+    return L
+
+
+def _ptr(x):
+    """device pointer of a torch tensor / int, or host pointer of a numpy array"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()
+
+
+class Engine:
+    """One scoring context on one GPU: the state of one computePolygenicScores call
+    (src/nimpress.nim:592-649) -- per-sample fp64 sums, nloci and the per-locus log."""
+
+    def __init__(self, n_samples, ploidy=2, gt_width=1, max_rows_per_block=4096, n_slots=0, device=0):
+        self.L = load_library()
+        self.n = int(n_samples)
+        self.ploidy, self.gt_width, self.max_rows = int(ploidy), int(gt_width), int(max_rows_per_block)
+        h = C.c_void_p()
+        rc = self.L.npc_create(C.byref(h), device, self.n, ploidy, gt_width, max_rows_per_block, n_slots)
+        if rc:
+            raise NpcError(f"npc_create rc={rc}: {self.L.npc_last_error(None).decode()}")
+        self.h = h
+
+    def _ck(self, rc):
+        if rc:
+            raise NpcError(f"rc={rc}: {self.L.npc_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.npc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.npc_set_stream(self.h, cuda_stream))
+
+    def set_policy(self, imp_locus="ps", imp_missing="homref", imp_sample="int_ps", maxmis=0.05, mincs=100):
+        p = _Policy(LOCUS[imp_locus], MISSING[imp_missing], SAMPLE[imp_sample], 0, int(mincs), float(maxmis))
+        self._ck(self.L.npc_set_policy(self.h, C.byref(p)))
+
+    def set_cohort_size(self, n_total):
+        self._ck(self.L.npc_set_cohort_size(self.h, int(n_total)))
+
+    def reset(self):
+        self._ck(self.L.npc_reset(self.h))
+
+    # -- host blocks through the pinned ring
+    def stage_acquire(self):
+        slot, ptr, stride = C.c_int32(), C.c_void_p(), C.c_int64()
+        self._ck(self.L.npc_stage_acquire(self.h, C.byref(slot), C.byref(ptr), C.byref(stride)))
+        buf = (C.c_uint8 * (stride.value * self.max_rows)).from_address(ptr.value)
+        view = np.frombuffer(buf, dtype=np.uint8).reshape(self.max_rows, stride.value)
+        return slot.value, view
+
+    def score_block(self, slot, n_gt_rows, rows):
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        self._ck(self.L.npc_score_block(self.h, slot, int(n_gt_rows), rows.ctypes.data, len(rows)))
+
+    def score_host(self, gt, rows):
+        """Convenience: one block from a host array gt[n_gt_rows, >= n*ploidy*width bytes]."""
+        gt = np.ascontiguousarray(gt)
+        g8 = gt.view(np.uint8).reshape(gt.shape[0], -1) if gt.size else np.zeros((0, 0), np.uint8)
+        slot, view = self.stage_acquire()
+        if g8.shape[0]:
+            view[:g8.shape[0], :g8.shape[1]] = g8
+        self.score_block(slot, g8.shape[0], rows)
+
+    # -- device-resident blocks
+    def score_block_device(self, gt_dev, row_stride, n_gt_rows, rows, n_rows=None):
+        if isinstance(rows, np.ndarray):
+            rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+            self._ck(self.L.npc_score_block_device(self.h, _ptr(gt_dev), row_stride, n_gt_rows, rows.ctypes.data,
+                                                   len(rows), 0))
+        else:
+            self._ck(self.L.npc_score_block_device(self.h, _ptr(gt_dev), row_stride, n_gt_rows, _ptr(rows), n_rows, 1))
+
+    def count_block_device(self, gt_dev, row_stride, n_gt_rows, rows, counts_dev, n_rows=None):
+        on_dev = not isinstance(rows, np.ndarray)
+        if not on_dev:
+            rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+            n_rows = len(rows)
+        self._ck(self.L.npc_count_block_device(self.h, _ptr(gt_dev), row_stride, n_gt_rows, _ptr(rows), n_rows,
+                                               int(on_dev), _ptr(counts_dev)))
+
+    def accumulate_block_device(self, gt_dev, row_stride, n_gt_rows, rows, counts_dev, n_rows=None):
+        on_dev = not isinstance(rows, np.ndarray)
+        if not on_dev:
+            rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+            n_rows = len(rows)
+        self._ck(self.L.npc_accumulate_block_device(self.h, _ptr(gt_dev), row_stride, n_gt_rows, _ptr(rows), n_rows,
+                                                    int(on_dev), _ptr(counts_dev)))
+
+    # -- results
+    def finish(self, offset=0.0, want_loci=True, loci_cap=None):
+        scores = np.empty(self.n, dtype=np.float64)
+        nloci, nlog = C.c_int64(), C.c_int64()
+        cap = loci_cap
+        if want_loci and cap is None:
+            # ask for the log length first (cheap: no loci copy)
+            tmp = np.empty(self.n, dtype=np.float64)
+            self._ck(self.L.npc_partial(self.h, tmp.ctypes.data, C.byref(nloci), None, 0, C.byref(nlog)))
+            cap = nlog.value
+        loci = np.zeros(cap if want_loci else 0, dtype=LOCUS_DTYPE)
+        self._ck(self.L.npc_finish(self.h, float(offset), scores.ctypes.data, C.byref(nloci),
+                                   loci.ctypes.data if want_loci else None, len(loci), C.byref(nlog)))
+        return dict(scores=scores, nloci=nloci.value, loci=loci[:nlog.value])
+
+    def partial(self, want_loci=False):
+        sums = np.empty(self.n, dtype=np.float64)
+        nloci, nlog = C.c_int64(), C.c_int64()
+        self._ck(self.L.npc_partial(self.h, sums.ctypes.data, C.byref(nloci), None, 0, C.byref(nlog)))
+        loci = None
+        if want_loci:
+            loci = np.zeros(nlog.value, dtype=LOCUS_DTYPE)
+            self._ck(self.L.npc_partial(self.h, sums.ctypes.data, C.byref(nloci), loci.ctypes.data, len(loci),
+                                        C.byref(nlog)))
+        return dict(sums=sums, nloci=nloci.value, loci=loci)
+
+    def partial_device_ptr(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.npc_partial_device_ptr(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def normalise(self, sums, nloci, offset):
+        sums = np.ascontiguousarray(sums, dtype=np.float64).copy()
+        self.L.npc_normalise(sums.ctypes.data, len(sums), int(nloci), float(offset))
+        return sums
+
+    @property
+    def launches(self):
+        return self.L.npc_launch_count(self.h)
+
+    def synth_fill_device(self, gt_dev, row_stride, v0, n_rows, seed, af_thr16_dev, miss_thr24_dev, alt_code_dev):
+        self._ck(self.L.npc_synth_fill_device(self.h, _ptr(gt_dev), row_stride, v0, n_rows, seed, _ptr(af_thr16_dev),
+                                              _ptr(miss_thr24_dev), _ptr(alt_code_dev)))

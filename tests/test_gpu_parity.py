@@ -1,0 +1,261 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bars: per-locus {class, used, eaidx, ngt, nmiss, neff, imputed} and nloci bit-exact; per-sample
+scores bit-exact on one context (same rounded products, same order as the reference's chain),
+which is stricter than north_star's 1e-9 relative."""
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from util_cohort import random_cohort, random_rows, assert_parity, assert_loci_equal, bits
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import __graft_entry__ as g
+    g.build()
+    import nimpress_b200
+    return nimpress_b200
+
+
+def run_engine(nb, gt, n, rows, ploidy=2, offset=0.0, block_rows=None, staged=True, policy=None, max_rows=None):
+    width = gt.dtype.itemsize
+    policy = policy or {}
+    V = gt.shape[0]
+    block_rows = block_rows or max(len(rows), 1)
+    eng = nb.Engine(n, ploidy=ploidy, gt_width=width, max_rows_per_block=max_rows or max(block_rows, V, 1),
+                    n_slots=2 if staged else 0)
+    eng.set_policy(**policy)
+    eng.reset()
+    if staged:
+        for r0 in range(0, max(len(rows), 1), block_rows):
+            eng.score_host(gt, rows[r0:r0 + block_rows])
+    else:
+        import torch
+        d = torch.from_numpy(gt.view(np.uint8).reshape(V, -1) if V else np.zeros((0, 16), np.uint8)).cuda()
+        stride = d.shape[1] if V else 16
+        for r0 in range(0, max(len(rows), 1), block_rows):
+            eng.score_block_device(d if V else None, stride, V, rows[r0:r0 + block_rows])
+    out = eng.finish(offset=offset)
+    out["launches"] = eng.launches
+    eng.close()
+    return out
+
+
+def oracle(gt, n, rows, ploidy=2, offset=0.0, policy=None):
+    policy = policy or {}
+    return orc.score_matrix(gt, n, ploidy, rows, offset=offset, **policy)
+
+
+# ---- golden vectors of the reference through the CUDA path ---------------------------------
+
+CASES = json.load(open(os.path.join(G, "set1_expected.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["ref"] for c in CASES])
+def test_set1_golden_through_gpu(nb, case):
+    """tests/test_set1.nim: every expected vector, 1e-4 abs + NaN pattern (checkFloats :14-22),
+    and bit-equality with the oracle's file-level run."""
+    from util_vcf import build_block
+    S1 = os.path.join(G, "set1")
+    samples, offset, gt, rows = build_block(os.path.join(S1, "set1.score"), os.path.join(S1, "set1.vcf.gz"),
+                                            os.path.join(S1, "set1.bed") if case["cov"] else None,
+                                            ignorefilt=case["ignorefilt"])
+    pol = dict(imp_locus=case["imp_locus"], imp_missing=case["imp_missing"], imp_sample=case["imp_sample"],
+               maxmis=case["maxmis"], mincs=case["mincs"])
+    got = run_engine(nb, gt, len(samples), rows, offset=offset, policy=pol)
+    exp = np.array([np.nan if e is None else (e[1] - e[2] if isinstance(e, list) else e) for e in case["expected"]])
+    assert np.array_equal(np.isnan(got["scores"]), np.isnan(exp))
+    ok = ~np.isnan(exp)
+    assert np.all(np.abs(got["scores"][ok] - exp[ok]) <= 1e-4)
+    ref = orc.compute_scores_files(os.path.join(S1, "set1.score"), os.path.join(S1, "set1.vcf.gz"),
+                                   os.path.join(S1, "set1.bed") if case["cov"] else None,
+                                   afmisp=case["afmisp"], ignorefilt=case["ignorefilt"], **pol)
+    assert_parity(got, ref)
+
+
+# ---- randomised cohorts ----------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 255, 256, 257, 1000, 4099, 100003])
+def test_sample_count_edges_i8(nb, n):
+    rng = np.random.default_rng(n)
+    V = 37
+    gt = random_cohort(rng, n, V, miss_rate=0.03)
+    rows = random_rows(rng, V, n_rows=50)
+    assert_parity(run_engine(nb, gt, n, rows, offset=0.5), oracle(gt, n, rows, offset=0.5))
+
+
+@pytest.mark.parametrize("width,ploidy", [(1, 1), (1, 2), (1, 3), (2, 2), (2, 4), (4, 2), (4, 1)])
+def test_widths_and_ploidies(nb, width, ploidy):
+    rng = np.random.default_rng(100 * width + ploidy)
+    n, V = 3001, 40
+    gt = random_cohort(rng, n, V, width=width, ploidy=ploidy, miss_rate=0.03, n_alt=3, sentinel_rate=0.02)
+    rows = random_rows(rng, V, n_rows=60, n_alt=3)
+    assert_parity(run_engine(nb, gt, n, rows, ploidy=ploidy), oracle(gt, n, rows, ploidy=ploidy))
+
+
+def test_slow_path_alleles_sentinels_invalid(nb):
+    """int8 diploid rows with alleles >= 7 (bytes >= 16), vector_end / missing sentinels and raw
+    negative bytes: every chunk that is not 'all bytes < 16' takes the exact slow decode."""
+    rng = np.random.default_rng(5)
+    n, V = 5003, 48
+    gt = random_cohort(rng, n, V, miss_rate=0.04, n_alt=12, sentinel_rate=0.01, invalid_rate=0.001)
+    rows = random_rows(rng, V, n_rows=96, n_alt=12)
+    assert_parity(run_engine(nb, gt, n, rows), oracle(gt, n, rows))
+
+
+POLICIES = [dict(imp_locus=l, imp_missing=m, imp_sample=s, maxmis=x, mincs=c)
+            for l, m, s, x, c in itertools.product(("ps", "homref", "fail", "ignore"), ("homref", "ignore"),
+                                                   ("ps", "homref", "fail", "int_ps", "int_fail"),
+                                                   (0.0, 0.03, 1.0), (0, 1900))]
+
+
+def test_policy_grid(nb):
+    """Every --imp-locus x --imp-missing x --imp-sample x --maxmis x --mincs combination on one
+    cohort whose per-locus missing rates straddle the thresholds."""
+    rng = np.random.default_rng(11)
+    n, V = 2000, 60
+    gt = random_cohort(rng, n, V, miss_rate=0.03)
+    rows = random_rows(rng, V, n_rows=80)
+    for pol in POLICIES:
+        assert_parity(run_engine(nb, gt, n, rows, offset=-0.125, policy=pol), oracle(gt, n, rows, offset=-0.125, policy=pol))
+
+
+def test_maxmis_boundary_exact(nb):
+    """nmissing/n > maxmis is a strict fp64 compare (src/nimpress.nim:565-566): rows with exactly
+    k missing of n against thresholds k/n, nextafter(k/n) on both sides."""
+    n = 1000
+    rng = np.random.default_rng(3)
+    ks = [0, 1, 49, 50, 51, 333, 1000]
+    gt = random_cohort(rng, n, len(ks), miss_rate=0.0, halfcall_rate=0.0)
+    for i, k in enumerate(ks):
+        gt[i, :2 * k] = 0
+    rows = random_rows(rng, len(ks), n_rows=len(ks), kinds=(1, 0, 0, 0), shuffle_gt=False)
+    for k in (1, 50, 333):
+        for thr in (k / n, np.nextafter(k / n, 0), np.nextafter(k / n, 1)):
+            pol = dict(maxmis=float(thr), imp_sample="int_ps", mincs=0)
+            assert_parity(run_engine(nb, gt, n, rows, policy=pol), oracle(gt, n, rows, policy=pol))
+
+
+def test_empty_and_degenerate_blocks(nb):
+    rng = np.random.default_rng(1)
+    n = 100
+    gt = random_cohort(rng, n, 4)
+    # no rows at all: nloci = 0 -> 0/0 = NaN for everyone (reference: scores /= 0*2)
+    got = run_engine(nb, gt, n, np.zeros(0, dtype=orc.ROW_DTYPE), offset=1.0)
+    assert got["nloci"] == 0 and np.all(np.isnan(got["scores"]))
+    # only constant rows, no genotype slab
+    rows = random_rows(rng, 0, n_rows=9)
+    assert_parity(run_engine(nb, np.zeros((0, 16), np.int8), n, rows), oracle(np.zeros((1, 16), np.int8), n, rows))
+    # all rows ignored
+    pol = dict(imp_locus="ignore", imp_missing="ignore", maxmis=0.0)
+    gt2 = random_cohort(rng, n, 4, miss_rate=0.5)
+    rows = random_rows(rng, 4, n_rows=8)
+    assert_parity(run_engine(nb, gt2, n, rows, policy=pol), oracle(gt2, n, rows, policy=pol))
+    # beta = 0, inf and NaN, eaf NaN: NaN*0 = NaN must poison exactly the reference's samples
+    rows = random_rows(rng, 4, n_rows=12)
+    rows["beta"][:4] = [0.0, np.inf, np.nan, -0.0]
+    rows["eaf"][4:6] = np.nan
+    for pol in (dict(imp_sample="fail"), dict(imp_sample="ps"), dict(imp_locus="fail", maxmis=0.0)):
+        assert_parity(run_engine(nb, gt2, n, rows, policy=pol), oracle(gt2, n, rows, policy=pol))
+
+
+def test_streaming_blocks_equal_single_block(nb):
+    """Rows split over many npc_score_block calls (pinned ring, 3 in flight) give the same bits as
+    one block, and the device-resident entry point gives the same bits as the staged one."""
+    rng = np.random.default_rng(21)
+    n, V = 20011, 300
+    gt = random_cohort(rng, n, V, miss_rate=0.02)
+    rows = random_rows(rng, V, n_rows=300)
+    want = oracle(gt, n, rows)
+    one = run_engine(nb, gt, n, rows)
+    many = run_engine(nb, gt, n, rows, block_rows=17, max_rows=300)
+    dev = run_engine(nb, gt, n, rows, staged=False, block_rows=64, max_rows=300)
+    for got in (one, many, dev):
+        assert_parity(got, want)
+
+
+def test_split_count_accumulate_matches_fused(nb):
+    """npc_count_block_device + npc_accumulate_block_device (sample-sharded form) on two sample
+    slabs with summed integer counts == the whole cohort on one context, bit for bit."""
+    import torch
+    rng = np.random.default_rng(33)
+    n, V = 6000, 64
+    gt = random_cohort(rng, n, V, miss_rate=0.04)
+    rows = random_rows(rng, V, n_rows=90)
+    want = oracle(gt, n, rows, offset=0.1)
+    cut = 2504                                        # slab boundary, multiple of 8
+    slabs = [np.ascontiguousarray(gt[:, :2 * cut]), np.ascontiguousarray(gt[:, 2 * cut:2 * n])]
+    engs, dev, counts = [], [], []
+    for s in slabs:
+        ns = s.shape[1] // 2
+        pad = -(-s.shape[1] // 16) * 16
+        sp = np.zeros((V, pad), np.int8); sp[:, :s.shape[1]] = s
+        e = nb.Engine(ns, max_rows_per_block=128)
+        e.set_cohort_size(n); e.reset()
+        d = torch.from_numpy(sp.view(np.uint8)).cuda()
+        c = torch.zeros((len(rows), 2), dtype=torch.int64, device="cuda")
+        e.count_block_device(d, pad, V, rows, c)
+        engs.append(e); dev.append((d, pad)); counts.append(c)
+    torch.cuda.synchronize()
+    total = counts[0] + counts[1]                     # the all-reduce of a sharded run
+    scores = []
+    for e, (d, pad) in zip(engs, dev):
+        e.accumulate_block_device(d, pad, V, rows, total)
+        out = e.finish(offset=0.1)
+        scores.append(out["scores"])
+        assert_loci_equal(out["loci"], want["loci"])
+        assert out["nloci"] == want["nloci"]
+        e.close()
+    got = np.concatenate(scores)
+    assert np.array_equal(np.isnan(got), np.isnan(want["scores"]))
+    ok = ~np.isnan(got)
+    assert np.array_equal(bits(got[ok]), bits(want["scores"][ok]))
+
+
+def test_synth_generator_matches_oracle(nb):
+    import torch
+    rng = np.random.default_rng(9)
+    n, V = 10007, 33
+    af = rng.integers(600, 32768, size=V).astype(np.uint32)
+    ms = rng.integers(0, 1 << 20, size=V).astype(np.uint32)
+    alt = rng.integers(1, 4, size=V).astype(np.int32)
+    stride = -(-2 * n // 128) * 128
+    host = np.zeros((V, stride), np.int8)
+    orc.synth_fill(host, n, 1000, 0x6E696D70, af, ms, alt)
+    eng = nb.Engine(n, max_rows_per_block=64)
+    d = torch.zeros((V, stride), dtype=torch.int8, device="cuda")
+    eng.synth_fill_device(d, stride, 1000, V, 0x6E696D70, torch.from_numpy(af.view(np.int32)).cuda(),
+                          torch.from_numpy(ms.view(np.int32)).cuda(), torch.from_numpy(alt).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy()[:, :2 * n], host[:, :2 * n])
+    eng.close()
+
+
+def test_config2_shape_wood_100k(nb):
+    """BASELINE.json configs[1]: the 697 wood-height loci x 100,000 synthetic samples, 0.5% missing,
+    default policies; whole result bit-equal to the oracle."""
+    from util_vcf import read_score
+    offset, ents = read_score(os.path.join(G, "scores", "wood-25282103-height.scores"))
+    n, V = 100_000, len(ents)
+    rng = np.random.default_rng(0x6E696D70)
+    af = np.array([e["eaf"] for e in ents])
+    stride = -(-2 * n // 128) * 128
+    gt = np.zeros((V, stride), np.int8)
+    orc.synth_fill(gt, n, 0, 0x6E696D70, (af * 65536).astype(np.uint32), np.full(V, int(0.005 * (1 << 24)), np.uint32),
+                   np.ones(V, np.int32))
+    rows = np.zeros(V, dtype=orc.ROW_DTYPE)
+    rows["gt_row"] = np.arange(V)
+    rows["ref_is_ea"] = [int(e["ref"] == e["ea"]) for e in ents]
+    rows["eaidx"] = np.where(rows["ref_is_ea"] == 1, 0, 1)
+    rows["beta"] = [e["beta"] for e in ents]
+    rows["eaf"] = af
+    assert V == 697
+    assert_parity(run_engine(nb, gt, n, rows, offset=offset, staged=False), oracle(gt, n, rows, offset=offset))
