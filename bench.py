@@ -201,12 +201,16 @@ def b200_arm(args):
 
     n, V = args.samples, args.variants
     stride = -(-2 * n // 128) * 128
-    block_rows = args.block_rows or max(1, min(V, (48 << 20) // stride))      # ~48 MB tiles: second pass from L2
+    fused = os.environ.get("NPC_FUSED", "1") != "0"
+    # fused kernel: one persistent launch per block, any size; two-kernel path: ~48 MB tiles so
+    # that the accumulate pass finds the tile in L2
+    block_rows = args.block_rows or (min(V, 32768) if fused else max(1, min(V, (48 << 20) // stride)))
     v0 = rank * V                                                             # this rank's slice of the variant axis
     af, beta, ref_is_ea, af_thr, miss_thr, alt = cohort_params(v0, V)
     rows = make_rows(nb.ROW_DTYPE, V, af, beta, ref_is_ea)
 
     eng = nb.Engine(n, max_rows_per_block=max(block_rows, 1), n_slots=0, device=local)
+    shape = eng.kernel_shape
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     eng.set_policy()                                                          # nimpress defaults
@@ -287,7 +291,8 @@ def b200_arm(args):
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "count+decide+accumulate sequence over one shard (all launches of a step)",
+                "kernel": ("k_fused_i8x2 (count+decide+accumulate, one persistent launch per block)" if shape["fused"]
+                           else "k_count_i8x2 + k_decide + k_accum_i8x2 sequence (all launches of a step)"),
                 "algorithmic_bytes_per_step": alg_bytes}
 
     # end to end through the staged C-ABI call with host buffers
@@ -349,6 +354,7 @@ def b200_arm(args):
             "config": {"workload": f"config3 genome-wide PRS shard: {V} variants x {n} samples per GPU "
                                    f"(1/8 of 1M x 500k), int8 diploid BCF GT, {MISS_RATE:.1%} missing, default policies",
                        "samples": n, "variants_per_gpu": V, "block_rows": block_rows, "parallelism": f"variant-shard x{world}",
+                       "kernel_shape": shape,
                        "l2": "inputs larger than L2 (shard >> 126 MB), no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -167,6 +167,12 @@ void npc_normalise(double *sums, int64_t n, int64_t nloci, double offset);
 /* Kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t npc_launch_count(const npc_ctx *ctx);
 
+/* Which kernels npc_score_block* uses for this context: shape[0] = 1 for the fused persistent
+ * kernel (int8 diploid cohorts that fit one resident pass), 0 for the count/decide/accumulate
+ * sequence; then grid, consumer warps, chunks per thread, rows per tile, ring stages, lag,
+ * dynamic shared-memory bytes. */
+int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
+
 /* ---- utilities (tests / bench) ----------------------------------------------------------- */
 
 /* Deterministic synthetic cohort written straight into device memory: int8 diploid GT rows

@@ -3,11 +3,12 @@
 // every entry point either runs the CUDA kernels or fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "npc_kernels.cuh"
+#include "npc_fused.cuh"
 
 using namespace npc;
 
@@ -34,6 +35,11 @@ struct npc_ctx {
     Policy pol{};
     int64_t launches = 0;
     std::string err;
+    // fused persistent kernel (int8 diploid): launch shape fixed per context
+    bool fused_ok = false;
+    int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 4, f_S = 7, f_L = 2, f_slab = 0;
+    uint32_t f_smem = 0;
+    ull *d_fcounts = nullptr;               // [max_rows] packed tallies, then [max_rows] arrival counters
 };
 
 #define NPC_CUDA(ctx, call)                                                                       \
@@ -65,10 +71,54 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <int K> static cudaError_t fused_set_smem(uint32_t bytes) {
+    return cudaFuncSetAttribute(k_fused_i8x2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// Launch shape of the fused kernel: one CTA per SM, each owning a contiguous range of 16-byte
+// chunks; K chunks per consumer thread; R rows per tile and S ring stages sized to fill shared
+// memory.  NPC_FUSED_{K,R,S,L} override for tuning; NPC_FUSED=0 forces the two-kernel path.
+static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
+    c->fused_ok = false;
+    if (c->width != 1 || c->ploidy != 2 || c->n == 0 || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
+    const int64_t C = (c->n + 7) / 8;
+    c->num_sms = prop.multiProcessorCount;
+    c->f_grid = (int)std::min<int64_t>(c->num_sms, std::max<int64_t>(1, C / 32));
+    const int64_t nch = (C + c->f_grid - 1) / c->f_grid;
+    int K = env_int("NPC_FUSED_K", 0);
+    if (K != 1 && K != 2 && K != 4) K = nch <= 512 ? 1 : nch <= 1024 ? 2 : 4;
+    const int64_t nc = (nch + 32 * K - 1) / (32 * K);
+    if (nc > 16) return NPC_OK;                       // cohort too wide for one resident pass: two-kernel path
+    c->f_K = K; c->f_nc = (int)nc; c->f_slab = (int)(nch * 16);
+    const int max_smem = (int)prop.sharedMemPerBlockOptin;
+    const int per_row = c->f_slab + 2 * LUT_N * 8 + 16;
+    int ring_rows = std::max(2, std::min(64, (max_smem - 1024) / per_row));
+    int R = env_int("NPC_FUSED_R", 0), S = env_int("NPC_FUSED_S", 0), L = env_int("NPC_FUSED_L", 2);
+    if (R <= 0) R = std::max(1, std::min(4, ring_rows / 6));
+    if (S <= 0) S = std::min(8, ring_rows / R);
+    if (L < 1) L = 1;
+    if (S < L + 2) { L = 1; if (S < 3) return NPC_OK; }
+    if (R > 32) R = 32;
+    FusedSmem m = FusedSmem::make(R, S, c->f_slab);
+    if ((int)m.total > max_smem) return NPC_OK;
+    c->f_R = R; c->f_S = S; c->f_L = L; c->f_smem = m.total;
+    cudaError_t e = K == 1 ? fused_set_smem<1>(m.total) : K == 2 ? fused_set_smem<2>(m.total) : fused_set_smem<4>(m.total);
+    if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
+    const size_t words = (size_t)std::max<int64_t>(c->max_rows, 1);
+    NPC_CUDA(c, cudaMalloc(&c->d_fcounts, words * (sizeof(ull) + sizeof(unsigned))));
+    c->fused_ok = true;
+    return NPC_OK;
 }
 
 static int create_impl(npc_ctx *c) {
@@ -108,7 +158,7 @@ static int create_impl(npc_ctx *c) {
     NPC_CUDA(c, cudaMemsetAsync(c->d_sums, 0, n1 * sizeof(double), c->stream));
     NPC_CUDA(c, cudaMemsetAsync(c->d_nloci, 0, sizeof(ull), c->stream));
     NPC_CUDA(c, cudaStreamSynchronize(c->stream));
-    return NPC_OK;
+    return fused_configure(c, prop);
 }
 
 extern "C" int npc_create(npc_ctx **out, int device, int64_t n_samples, int32_t ploidy, int32_t gt_width,
@@ -167,6 +217,13 @@ extern "C" int npc_reset(npc_ctx *ctx) {
 }
 
 extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
+    if (!ctx || !shape) return NPC_EINVAL;
+    shape[0] = ctx->fused_ok ? 1 : 0; shape[1] = ctx->f_grid; shape[2] = ctx->f_nc; shape[3] = ctx->f_K;
+    shape[4] = ctx->f_R; shape[5] = ctx->f_S; shape[6] = ctx->f_L; shape[7] = (int32_t)ctx->f_smem;
+    return NPC_OK;
+}
 
 // ---- internals ---------------------------------------------------------------------------
 
@@ -248,6 +305,34 @@ static int launch_decide_accum(npc_ctx *c, const uint8_t *gt, int64_t row_stride
     return NPC_OK;
 }
 
+// count -> decide -> accumulate in one persistent cooperative launch (npc_fused.cuh)
+static int launch_fused(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
+    if (n_rows == 0) return NPC_OK;
+    int rc = ensure_log(c, n_rows);
+    if (rc) return rc;
+    const int64_t n_tiles = (n_rows + c->f_R - 1) / c->f_R;
+    unsigned *arrive = reinterpret_cast<unsigned *>(c->d_fcounts + n_rows);
+    NPC_CUDA(c, cudaMemsetAsync(c->d_fcounts, 0, n_rows * sizeof(ull) + n_tiles * sizeof(unsigned), c->stream));
+    FusedParams P;
+    P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
+    P.sums = c->d_sums; P.counts = c->d_fcounts; P.arrive = arrive; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
+    P.R = c->f_R; P.S = c->f_S; P.L = c->f_L; P.nc = c->f_nc; P.slab_stride = c->f_slab;
+    void *args[] = { &P };
+    const dim3 grid(c->f_grid), block((c->f_nc + 2) * 32);
+    const void *fn = c->f_K == 1 ? (const void *)k_fused_i8x2<1> : c->f_K == 2 ? (const void *)k_fused_i8x2<2> : (const void *)k_fused_i8x2<4>;
+    NPC_CUDA(c, cudaLaunchCooperativeKernel(fn, grid, block, args, c->f_smem, c->stream));
+    c->launches++;
+    c->log_len += n_rows;
+    return NPC_OK;
+}
+
+static int launch_block(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
+    if (c->fused_ok) return launch_fused(c, gt, row_stride, d_rows, n_rows);
+    int rc = launch_count(c, gt, row_stride, d_rows, n_rows, c->d_counts);
+    if (rc) return rc;
+    return launch_decide_accum(c, gt, row_stride, d_rows, n_rows, c->d_counts);
+}
+
 // ---- staged blocks -----------------------------------------------------------------------
 
 extern "C" int npc_stage_acquire(npc_ctx *ctx, int32_t *slot, void **gt_host, int64_t *row_stride) {
@@ -280,8 +365,7 @@ extern "C" int npc_score_block(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, co
     NPC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
     const npc_row *d_rows;
     if ((rc = upload_rows(ctx, rows, n_rows, 0, &d_rows))) return rc;
-    if ((rc = launch_count(ctx, ctx->d_gt[slot], ctx->row_stride, d_rows, n_rows, ctx->d_counts))) return rc;
-    if ((rc = launch_decide_accum(ctx, ctx->d_gt[slot], ctx->row_stride, d_rows, n_rows, ctx->d_counts))) return rc;
+    if ((rc = launch_block(ctx, ctx->d_gt[slot], ctx->row_stride, d_rows, n_rows))) return rc;
     // npc_stage_acquire waits on ev_done before lending the slot again, so the next H2D into
     // it cannot overtake these kernels and copies into OTHER slots overlap them freely
     NPC_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], ctx->stream));
@@ -298,8 +382,7 @@ extern "C" int npc_score_block_device(npc_ctx *ctx, const void *gt_dev, int64_t 
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));
     const npc_row *d_rows;
     if ((rc = upload_rows(ctx, rows, n_rows, rows_on_device, &d_rows))) return rc;
-    if ((rc = launch_count(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows, ctx->d_counts))) return rc;
-    return launch_decide_accum(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows, ctx->d_counts);
+    return launch_block(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows);
 }
 
 extern "C" int npc_count_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows,

@@ -315,7 +315,7 @@ k_accum_i8x2(const uint8_t *__restrict__ gt, int64_t row_stride, const RowP *__r
             const int rr = i / LUT_N, e = i - rr * LUT_N;
             const RowP &rp = rowp[r0 + rr];
             const int code = lut_code(e, rp.eaidx + 1);
-            s_lut[rr][e] = code == 0 ? rp.c0 : code == 1 ? rp.c1 : code == 2 ? rp.c2 : rp.cm;
+            s_lut[rr][e] = (rp.mode == MODE_CONST || code == 0) ? rp.c0 : code == 1 ? rp.c1 : code == 2 ? rp.c2 : rp.cm;
             if (e == 0) { s_mode[rr] = rp.mode; s_gtrow[rr] = rp.gt_row; s_eaidx[rr] = rp.eaidx; }
         }
         __syncthreads();

@@ -67,6 +67,7 @@ def load_library():
         "npc_partial_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "npc_normalise": (None, [vp, i64, i64, f64]),
         "npc_launch_count": (i64, [vp]),
+        "npc_kernel_shape": (C.c_int, [vp, C.POINTER(i32 * 8)]),
         "npc_synth_fill_device": (C.c_int, [vp, vp, i64, i64, i64, C.c_uint64, vp, vp, vp]),
         "npc_version": (C.c_int, []),
     }
@@ -208,6 +209,13 @@ class Engine:
         sums = np.ascontiguousarray(sums, dtype=np.float64).copy()
         self.L.npc_normalise(sums.ctypes.data, len(sums), int(nloci), float(offset))
         return sums
+
+    @property
+    def kernel_shape(self):
+        a = (C.c_int32 * 8)()
+        self._ck(self.L.npc_kernel_shape(self.h, C.byref(a)))
+        keys = ("fused", "grid", "consumer_warps", "chunks_per_thread", "rows_per_tile", "stages", "lag", "smem_bytes")
+        return dict(zip(keys, list(a)))
 
     @property
     def launches(self):

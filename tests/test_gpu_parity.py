@@ -259,3 +259,24 @@ def test_config2_shape_wood_100k(nb):
     rows["eaf"] = af
     assert V == 697
     assert_parity(run_engine(nb, gt, n, rows, offset=offset, staged=False), oracle(gt, n, rows, offset=offset))
+
+
+@pytest.mark.parametrize("env", [dict(NPC_FUSED="0"), dict(NPC_FUSED_R="1", NPC_FUSED_S="3", NPC_FUSED_L="1"),
+                                 dict(NPC_FUSED_R="8", NPC_FUSED_S="5", NPC_FUSED_L="3"), dict(NPC_FUSED_K="2"),
+                                 dict(NPC_FUSED_K="4", NPC_FUSED_R="3")],
+                         ids=lambda e: ",".join(f"{k[4:]}={v}" for k, v in e.items()))
+def test_kernel_paths_agree(nb, env, monkeypatch):
+    """The fused persistent kernel under several ring shapes and the two-kernel sequence all give
+    the oracle's bits (the launch shape must not change the summation order)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(77)
+    n, V = 40009, 203
+    gt = random_cohort(rng, n, V, miss_rate=0.03, n_alt=9, sentinel_rate=0.003)
+    rows = random_rows(rng, V, n_rows=260, n_alt=9)
+    want = oracle(gt, n, rows, offset=0.5)
+    eng = nb.Engine(n, max_rows_per_block=512)
+    assert eng.kernel_shape["fused"] == (0 if env.get("NPC_FUSED") == "0" else 1)
+    eng.close()
+    assert_parity(run_engine(nb, gt, n, rows, offset=0.5, staged=False, max_rows=512), want)
+    assert_parity(run_engine(nb, gt, n, rows, offset=0.5, staged=True, block_rows=37, max_rows=512), want)
