@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--brief", action="store_true", help="print value / roofline / shape only (tuning sweeps)")
     return ap.parse_args()
 
 
@@ -211,7 +212,11 @@ def b200_arm(args):
 
     eng = nb.Engine(n, max_rows_per_block=max(block_rows, 1), n_slots=0, device=local)
     shape = eng.kernel_shape
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the default stream's handle is 0, which npc_set_stream reads as
+    # "use the context's own stream" and the timing events below would then miss the kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     eng.set_policy()                                                          # nimpress defaults
     gt = torch.empty((V, stride), dtype=torch.uint8, device=dev)
@@ -358,7 +363,10 @@ def b200_arm(args):
                        "l2": "inputs larger than L2 (shard >> 126 MB), no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        if args.brief:
+            print(f"{value:.4e} genotypes/s  frac={roofline['frac']:.3f}  ms={ms_step:.3f}  {shape}")
+        else:
+            print(json.dumps(line))
     eng.close()
     if world > 1:
         dist.destroy_process_group()

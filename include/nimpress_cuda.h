@@ -107,7 +107,8 @@ void npc_destroy(npc_ctx *ctx);
 const char *npc_last_error(const npc_ctx *ctx);   /* ctx may be NULL: text of the last npc_create failure */
 
 /* Launch on an existing CUDA stream (cudaStream_t as void*) instead of the context's own;
- * NULL restores the internal stream.  For callers that time or order work themselves. */
+ * NULL restores the internal stream (so the legacy default stream, whose handle is 0, must be
+ * named as cudaStreamLegacy).  For callers that time or order work themselves. */
 int npc_set_stream(npc_ctx *ctx, void *cuda_stream);
 
 int npc_set_policy(npc_ctx *ctx, const npc_policy *p);
@@ -169,8 +170,8 @@ int64_t npc_launch_count(const npc_ctx *ctx);
 
 /* Which kernels npc_score_block* uses for this context: shape[0] = 1 for the fused persistent
  * kernel (int8 diploid cohorts that fit one resident pass), 0 for the count/decide/accumulate
- * sequence; then grid, consumer warps, chunks per thread, rows per tile, ring stages, lag,
- * dynamic shared-memory bytes. */
+ * sequence; then grid, consumer warps, chunks per thread, rows per tile, ring stages,
+ * lag * 100 + auxiliary warps, dynamic shared-memory bytes. */
 int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
 
 /* ---- utilities (tests / bench) ----------------------------------------------------------- */

@@ -37,9 +37,9 @@ struct npc_ctx {
     std::string err;
     // fused persistent kernel (int8 diploid): launch shape fixed per context
     bool fused_ok = false;
-    int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 4, f_S = 7, f_L = 2, f_slab = 0;
+    int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 2, f_S = 8, f_L = 4, f_A = 4, f_slab = 0;
     uint32_t f_smem = 0;
-    ull *d_fcounts = nullptr;               // [max_rows] packed tallies, then [max_rows] arrival counters
+    ull *d_fcounts = nullptr;               // [max_rows] arrivals | nmiss | neff words of the fused kernel
 };
 
 #define NPC_CUDA(ctx, call)                                                                       \
@@ -82,41 +82,49 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-template <int K> static cudaError_t fused_set_smem(uint32_t bytes) {
-    return cudaFuncSetAttribute(k_fused_i8x2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+typedef void (*fused_fn)(const FusedParams);
+static fused_fn fused_kernel(int K, int R) {
+#define NPC_F(k, r) if (K == k && R == r) return k_fused_i8x2<k, r>;
+    NPC_F(1, 1) NPC_F(1, 2) NPC_F(1, 3) NPC_F(1, 4) NPC_F(1, 8)
+    NPC_F(2, 1) NPC_F(2, 2) NPC_F(2, 3) NPC_F(2, 4) NPC_F(2, 8)
+#undef NPC_F
+    return nullptr;
 }
 
 // Launch shape of the fused kernel: one CTA per SM, each owning a contiguous range of 16-byte
 // chunks; K chunks per consumer thread; R rows per tile and S ring stages sized to fill shared
-// memory.  NPC_FUSED_{K,R,S,L} override for tuning; NPC_FUSED=0 forces the two-kernel path.
+// memory; the accumulate phase runs L tiles behind the count phase; A auxiliary warps.
+// NPC_FUSED_{K,R,S,L,A} override for tuning; NPC_FUSED=0 forces the two-kernel path.
 static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     c->fused_ok = false;
-    if (c->width != 1 || c->ploidy != 2 || c->n == 0 || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
+    if (c->width != 1 || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
     const int64_t C = (c->n + 7) / 8;
     c->num_sms = prop.multiProcessorCount;
     c->f_grid = (int)std::min<int64_t>(c->num_sms, std::max<int64_t>(1, C / 32));
     const int64_t nch = (C + c->f_grid - 1) / c->f_grid;
     int K = env_int("NPC_FUSED_K", 0);
-    if (K != 1 && K != 2 && K != 4) K = nch <= 512 ? 1 : nch <= 1024 ? 2 : 4;
+    if (K != 1 && K != 2) K = nch <= 512 ? 1 : 2;
     const int64_t nc = (nch + 32 * K - 1) / (32 * K);
     if (nc > 16) return NPC_OK;                       // cohort too wide for one resident pass: two-kernel path
-    c->f_K = K; c->f_nc = (int)nc; c->f_slab = (int)(nch * 16);
+    c->f_K = K; c->f_nc = (int)nc; c->f_slab = (int)(nc * 32 * K * 16);
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
-    const int per_row = c->f_slab + 2 * LUT_N * 8 + 16;
-    int ring_rows = std::max(2, std::min(64, (max_smem - 1024) / per_row));
-    int R = env_int("NPC_FUSED_R", 0), S = env_int("NPC_FUSED_S", 0), L = env_int("NPC_FUSED_L", 2);
-    if (R <= 0) R = std::max(1, std::min(4, ring_rows / 6));
-    if (S <= 0) S = std::min(8, ring_rows / R);
-    if (L < 1) L = 1;
-    if (S < L + 2) { L = 1; if (S < 3) return NPC_OK; }
-    if (R > 32) R = 32;
+    const int per_row = c->f_slab + LUT_N * 8 + 12;
+    const int fixed = (int)(FUSED_CNT_TABLES * LUT_N * 8) + 2048;
+    const int ring_rows = std::min(96, (max_smem - fixed) / per_row);
+    if (ring_rows < 3) return NPC_OK;
+    int R = env_int("NPC_FUSED_R", 0), S = env_int("NPC_FUSED_S", 0), L = env_int("NPC_FUSED_L", 0), A = env_int("NPC_FUSED_A", 4);
+    if (!fused_kernel(K, R)) R = ring_rows >= 24 ? 2 : 1;
+    if (S <= 0) S = std::min(32, ring_rows / R);
+    while (S >= 3 && (int)FusedSmem::make(R, S, c->f_slab).total > max_smem) S--;
+    if (S < 3) return NPC_OK;
+    if (L <= 0) L = std::max(1, (S * 55) / 100);      // about half the ring is lag, the rest prefetch
+    if (L > S - 2) L = S - 2;
+    A = std::max(1, std::min(5, A));
     FusedSmem m = FusedSmem::make(R, S, c->f_slab);
-    if ((int)m.total > max_smem) return NPC_OK;
-    c->f_R = R; c->f_S = S; c->f_L = L; c->f_smem = m.total;
-    cudaError_t e = K == 1 ? fused_set_smem<1>(m.total) : K == 2 ? fused_set_smem<2>(m.total) : fused_set_smem<4>(m.total);
+    c->f_R = R; c->f_S = S; c->f_L = L; c->f_A = A; c->f_smem = m.total;
+    cudaError_t e = cudaFuncSetAttribute(fused_kernel(K, R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.total);
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
-    const size_t words = (size_t)std::max<int64_t>(c->max_rows, 1);
-    NPC_CUDA(c, cudaMalloc(&c->d_fcounts, words * (sizeof(ull) + sizeof(unsigned))));
+    NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
     c->fused_ok = true;
     return NPC_OK;
 }
@@ -221,7 +229,7 @@ extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->laun
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!ctx || !shape) return NPC_EINVAL;
     shape[0] = ctx->fused_ok ? 1 : 0; shape[1] = ctx->f_grid; shape[2] = ctx->f_nc; shape[3] = ctx->f_K;
-    shape[4] = ctx->f_R; shape[5] = ctx->f_S; shape[6] = ctx->f_L; shape[7] = (int32_t)ctx->f_smem;
+    shape[4] = ctx->f_R; shape[5] = ctx->f_S; shape[6] = ctx->f_L * 100 + ctx->f_A; shape[7] = (int32_t)ctx->f_smem;
     return NPC_OK;
 }
 
@@ -310,17 +318,14 @@ static int launch_fused(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const
     if (n_rows == 0) return NPC_OK;
     int rc = ensure_log(c, n_rows);
     if (rc) return rc;
-    const int64_t n_tiles = (n_rows + c->f_R - 1) / c->f_R;
-    unsigned *arrive = reinterpret_cast<unsigned *>(c->d_fcounts + n_rows);
-    NPC_CUDA(c, cudaMemsetAsync(c->d_fcounts, 0, n_rows * sizeof(ull) + n_tiles * sizeof(unsigned), c->stream));
+    NPC_CUDA(c, cudaMemsetAsync(c->d_fcounts, 0, n_rows * sizeof(ull), c->stream));
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
-    P.sums = c->d_sums; P.counts = c->d_fcounts; P.arrive = arrive; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
-    P.R = c->f_R; P.S = c->f_S; P.L = c->f_L; P.nc = c->f_nc; P.slab_stride = c->f_slab;
+    P.sums = c->d_sums; P.counts = c->d_fcounts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
+    P.S = c->f_S; P.L = c->f_L; P.A = c->f_A; P.nc = c->f_nc; P.slab_stride = c->f_slab;
     void *args[] = { &P };
-    const dim3 grid(c->f_grid), block((c->f_nc + 2) * 32);
-    const void *fn = c->f_K == 1 ? (const void *)k_fused_i8x2<1> : c->f_K == 2 ? (const void *)k_fused_i8x2<2> : (const void *)k_fused_i8x2<4>;
-    NPC_CUDA(c, cudaLaunchCooperativeKernel(fn, grid, block, args, c->f_smem, c->stream));
+    const dim3 grid(c->f_grid), block((c->f_nc + 1 + c->f_A) * 32);
+    NPC_CUDA(c, cudaLaunchCooperativeKernel((const void *)fused_kernel(c->f_K, c->f_R), grid, block, args, c->f_smem, c->stream));
     c->launches++;
     c->log_len += n_rows;
     return NPC_OK;

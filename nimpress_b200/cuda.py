@@ -215,7 +215,9 @@ class Engine:
         a = (C.c_int32 * 8)()
         self._ck(self.L.npc_kernel_shape(self.h, C.byref(a)))
         keys = ("fused", "grid", "consumer_warps", "chunks_per_thread", "rows_per_tile", "stages", "lag", "smem_bytes")
-        return dict(zip(keys, list(a)))
+        d = dict(zip(keys, list(a)))
+        d["aux_warps"], d["lag"] = d["lag"] % 100, d["lag"] // 100
+        return d
 
     @property
     def launches(self):

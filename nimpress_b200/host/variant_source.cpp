@@ -1,0 +1,440 @@
+#include "variant_source.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+namespace nph {
+
+// ------------------------------------------------------------------------------------------
+// InflateStream
+// ------------------------------------------------------------------------------------------
+
+InflateStream::~InflateStream() {
+    if (zinit_) inflateEnd(&zs_);
+    if (fp_) fclose(fp_);
+}
+
+bool InflateStream::open(const std::string &path) {
+    fp_ = fopen(path.c_str(), "rb");
+    if (!fp_) return false;
+    in_.resize(1 << 20);
+    out_.resize(4 << 20);
+    unsigned char magic[2] = { 0, 0 };
+    size_t got = fread(magic, 1, 2, fp_);
+    fseek(fp_, 0, SEEK_SET);
+    compressed_ = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (compressed_) {
+        memset(&zs_, 0, sizeof zs_);
+        if (inflateInit2(&zs_, 15 + 16) != Z_OK) return false;
+        zinit_ = true;
+    }
+    return true;
+}
+
+bool InflateStream::fill() {
+    out_pos_ = out_len_ = 0;
+    if (eof_) return false;
+    if (!compressed_) {
+        out_len_ = fread(out_.data(), 1, out_.size(), fp_);
+        if (out_len_ == 0) eof_ = true;
+        return out_len_ > 0;
+    }
+    zs_.next_out = out_.data();
+    zs_.avail_out = (uInt)out_.size();
+    while (zs_.avail_out == out_.size()) {            // until something was produced
+        if (zs_.avail_in == 0) {
+            zs_.next_in = in_.data();
+            zs_.avail_in = (uInt)fread(in_.data(), 1, in_.size(), fp_);
+            if (zs_.avail_in == 0) { eof_ = true; break; }
+        }
+        int rc = inflate(&zs_, Z_NO_FLUSH);
+        if (rc == Z_STREAM_END) {                     // next BGZF block / gzip member
+            if (inflateReset(&zs_) != Z_OK) throw InputError("zlib: inflateReset failed");
+        } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+            throw InputError(std::string("zlib: corrupt compressed stream: ") + (zs_.msg ? zs_.msg : "?"));
+        }
+    }
+    out_len_ = out_.size() - zs_.avail_out;
+    return out_len_ > 0;
+}
+
+size_t InflateStream::read(void *dst, size_t n) {
+    size_t done = 0;
+    while (done < n) {
+        if (out_pos_ == out_len_ && !fill()) break;
+        size_t k = std::min(n - done, out_len_ - out_pos_);
+        memcpy((uint8_t *)dst + done, out_.data() + out_pos_, k);
+        out_pos_ += k;
+        done += k;
+    }
+    return done;
+}
+
+bool InflateStream::read_exact(void *dst, size_t n) { return read(dst, n) == n; }
+
+bool InflateStream::peek(void *dst, size_t n) {
+    if (out_pos_ == out_len_ && !fill()) return false;
+    if (out_len_ - out_pos_ < n) return false;        // only used at the very start of the stream
+    memcpy(dst, out_.data() + out_pos_, n);
+    return true;
+}
+
+bool InflateStream::getline(std::string &line) {
+    line.clear();
+    bool any = false;
+    for (;;) {
+        if (out_pos_ == out_len_ && !fill()) break;
+        any = true;
+        const uint8_t *b = out_.data() + out_pos_;
+        const uint8_t *nl = (const uint8_t *)memchr(b, '\n', out_len_ - out_pos_);
+        if (nl) {
+            line.append((const char *)b, nl - b);
+            out_pos_ += (nl - b) + 1;
+            break;
+        }
+        line.append((const char *)b, out_len_ - out_pos_);
+        out_pos_ = out_len_;
+    }
+    if (!any) return false;
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared: encode GT values into the narrowest BCF integer width, pad with vector_end
+// ------------------------------------------------------------------------------------------
+
+static void pack_gt(const std::vector<int32_t> &vals, const std::vector<int> &counts, int64_t n, int ploidy,
+                    std::vector<uint8_t> &out, int &width) {
+    int32_t mx = 0;
+    for (int32_t v : vals) mx = std::max(mx, v);
+    width = mx <= INT8_MAX ? 1 : mx <= INT16_MAX ? 2 : 4;
+    out.assign((size_t)n * ploidy * width, 0);
+    size_t src = 0;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < ploidy; k++) {
+            const bool have = k < counts[i];
+            const int32_t v = have ? vals[src + k] : 0;
+            const size_t j = (size_t)i * ploidy + k;
+            if (width == 1) ((int8_t *)out.data())[j] = have ? (int8_t)v : (int8_t)(INT8_MIN + 1);
+            else if (width == 2) ((int16_t *)out.data())[j] = have ? (int16_t)v : (int16_t)(INT16_MIN + 1);
+            else ((int32_t *)out.data())[j] = have ? v : INT32_MIN + 1;
+        }
+        src += counts[i];
+    }
+}
+
+// INFO/END=<n> overrides the REF length for overlap (htslib vcf_parse / tabix readrec)
+static int64_t rlen_from_info(const char *info, size_t len, int64_t pos, int64_t dflt) {
+    size_t i = 0;
+    while (i < len) {
+        size_t e = i;
+        while (e < len && info[e] != ';') e++;
+        if (e - i > 4 && !memcmp(info + i, "END=", 4)) {
+            long long end = atoll(std::string(info + i + 4, e - i - 4).c_str());
+            return end >= pos ? end - pos + 1 : dflt;
+        }
+        i = e + 1;
+    }
+    return dflt;
+}
+
+// ------------------------------------------------------------------------------------------
+// VCF text
+// ------------------------------------------------------------------------------------------
+
+class VcfTextSource : public VariantSource {
+public:
+    explicit VcfTextSource(std::unique_ptr<InflateStream> s) : in_(std::move(s)) {}
+    bool read_header() {
+        while (in_->getline(line_)) {
+            if (line_.size() >= 2 && line_[0] == '#' && line_[1] == '#') continue;
+            if (!line_.empty() && line_[0] == '#') {
+                std::vector<std::string> f = split_char(line_, '\t');
+                for (size_t i = 9; i < f.size(); i++) samples_.push_back(f[i]);
+                return true;
+            }
+            return false;                              // data before the #CHROM line
+        }
+        return false;
+    }
+    bool next(VariantRecord &rec) override {
+        for (;;) {
+            if (!in_->getline(line_)) return false;
+            if (!line_.empty()) break;
+        }
+        // split the 9 fixed columns in place
+        const char *p = line_.data(), *end = p + line_.size();
+        const char *col[10];
+        size_t len[10];
+        int nc = 0;
+        while (nc < 9 && p <= end) {
+            const char *t = (const char *)memchr(p, '\t', end - p);
+            col[nc] = p; len[nc] = (t ? t : end) - p; nc++;
+            if (!t) { p = end + 1; break; }
+            p = t + 1;
+        }
+        if (nc < 8) throw InputError("VCF: record with fewer than 8 columns");
+        contig_.assign(col[0], len[0]);
+        rec.contig = &contig_; rec.contig_id = -1;
+        rec.pos = parse_int_nim(std::string(col[1], len[1]), "VCF POS");
+        rec.ref.assign(col[3], len[3]);
+        rec.alts.clear();
+        if (!(len[4] == 1 && col[4][0] == '.')) rec.alts = split_char(std::string(col[4], len[4]), ',');
+        rec.filter.assign(col[6], len[6]);
+        rec.rlen = rlen_from_info(col[7], len[7], rec.pos, (int64_t)rec.ref.size());
+        rec.has_gt = false; rec.gt = nullptr; rec.ploidy = 0; rec.gt_width = 1;
+        if (nc < 9 || samples_.empty()) return true;
+        // FORMAT: index of GT
+        int gt_idx = -1, k = 0;
+        for (const char *q = col[8], *qe = col[8] + len[8]; q <= qe; k++) {
+            const char *t = (const char *)memchr(q, ':', qe - q);
+            size_t l = (t ? t : qe) - q;
+            if (l == 2 && q[0] == 'G' && q[1] == 'T') gt_idx = k;
+            if (!t) break;
+            q = t + 1;
+        }
+        if (gt_idx < 0) return true;
+        // per-sample GT strings -> (allele+1)<<1|phased, htslib vcf_parse_format
+        const int64_t n = n_samples();
+        vals_.clear(); counts_.assign(n, 0);
+        int maxp = 1;
+        for (int64_t i = 0; i < n; i++) {
+            const char *s = p <= end ? p : end, *se = end;
+            if (p <= end) {
+                const char *t = (const char *)memchr(p, '\t', end - p);
+                se = t ? t : end;
+                p = t ? t + 1 : end + 1;
+            }
+            for (int f = 0; f < gt_idx && s < se; f++) {          // skip to sub-field gt_idx
+                const char *t = (const char *)memchr(s, ':', se - s);
+                s = t ? t + 1 : se;
+            }
+            int l = 0, phased = 0;
+            for (;;) {
+                if (s < se && *s == '.') { s++; vals_.push_back(phased); l++; }
+                else if (s < se && *s >= '0' && *s <= '9') {
+                    uint32_t v = 0;
+                    while (s < se && *s >= '0' && *s <= '9') v = v * 10 + (uint32_t)(*s++ - '0');
+                    vals_.push_back((int32_t)(((v + 1) << 1) | (uint32_t)phased)); l++;
+                } else break;
+                if (s >= se) break;
+                phased = *s == '|';
+                if (*s != '|' && *s != '/') break;
+                s++;
+            }
+            if (!l) { vals_.push_back(0); l = 1; }                // empty field = one missing allele
+            counts_[i] = l;
+            maxp = std::max(maxp, l);
+        }
+        pack_gt(vals_, counts_, n, maxp, gt_, rec.gt_width);
+        rec.ploidy = maxp; rec.gt = gt_.data(); rec.has_gt = true;
+        return true;
+    }
+private:
+    std::unique_ptr<InflateStream> in_;
+    std::string line_, contig_;
+    std::vector<int32_t> vals_;
+    std::vector<int> counts_;
+    std::vector<uint8_t> gt_;
+};
+
+// ------------------------------------------------------------------------------------------
+// BCF2
+// ------------------------------------------------------------------------------------------
+
+class BcfSource : public VariantSource {
+public:
+    explicit BcfSource(std::unique_ptr<InflateStream> s) : in_(std::move(s)) {}
+    bool read_header() {
+        uint8_t magic[5];
+        uint32_t l_text = 0;
+        if (!in_->read_exact(magic, 5) || memcmp(magic, "BCF\2", 4) != 0) return false;
+        if (!in_->read_exact(&l_text, 4)) return false;
+        std::string text(l_text, '\0');
+        if (!in_->read_exact(&text[0], l_text)) return false;
+        parse_header(text);
+        return true;
+    }
+    bool next(VariantRecord &rec) override {
+        uint32_t lens[2];
+        size_t got = in_->read(lens, 8);
+        if (got == 0) return false;
+        if (got != 8) throw InputError("BCF: truncated record header");
+        shared_.resize(lens[0]); indiv_.resize(lens[1]);
+        if (!in_->read_exact(shared_.data(), lens[0]) || !in_->read_exact(indiv_.data(), lens[1]))
+            throw InputError("BCF: truncated record");
+        if (lens[0] < 24) throw InputError("BCF: shared block too short");
+        const uint8_t *p = shared_.data(), *e = p + shared_.size();
+        int32_t chrom, pos0, rlen; uint32_t nai, nfs;
+        memcpy(&chrom, p, 4); memcpy(&pos0, p + 4, 4); memcpy(&rlen, p + 8, 4);
+        memcpy(&nai, p + 16, 4); memcpy(&nfs, p + 20, 4);
+        p += 24;
+        const uint32_t n_allele = nai >> 16, n_info = nai & 0xFFFF, n_fmt = nfs >> 24, n_sample = nfs & 0xFFFFFF;
+        (void)n_info;
+        if (chrom < 0 || (size_t)chrom >= contigs_.size() || contigs_[chrom].empty()) throw InputError("BCF: CHROM id not in header");
+        rec.contig_id = chrom; rec.contig = &contigs_[chrom];
+        rec.pos = (int64_t)pos0 + 1; rec.rlen = rlen;
+        skip_typed(p, e);                                          // ID
+        rec.ref.clear(); rec.alts.clear();
+        for (uint32_t a = 0; a < n_allele; a++) {
+            std::string s = read_typed_string(p, e);
+            if (a == 0) rec.ref = std::move(s); else rec.alts.push_back(std::move(s));
+        }
+        // FILTER: typed int vector of dictionary ids
+        {
+            int type; uint32_t len;
+            read_desc(p, e, type, len);
+            rec.filter.clear();
+            if (len == 0) rec.filter = ".";
+            for (uint32_t i = 0; i < len; i++) {
+                int32_t id = read_int(p, e, type);
+                if (i) rec.filter += ';';
+                rec.filter += dict_name(id);
+            }
+        }
+        // FORMAT fields: find GT
+        rec.has_gt = false; rec.gt = nullptr; rec.ploidy = 0; rec.gt_width = 1;
+        const uint8_t *q = indiv_.data(), *qe = q + indiv_.size();
+        for (uint32_t f = 0; f < n_fmt && q < qe; f++) {
+            int kt; uint32_t kl;
+            read_desc(q, qe, kt, kl);
+            int32_t key = read_int(q, qe, kt);
+            int type; uint32_t len;
+            read_desc(q, qe, type, len);
+            const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
+            const size_t bytes = (size_t)n_sample * len * esz;
+            if (q + bytes > qe) throw InputError("BCF: FORMAT field overruns the record");
+            if (key == gt_key_ && (type == 1 || type == 2 || type == 3)) {
+                if ((int64_t)n_sample != n_samples()) throw InputError("BCF: record sample count differs from header");
+                rec.has_gt = true; rec.gt = q; rec.gt_width = (int)esz; rec.ploidy = (int)len;
+            }
+            q += bytes;
+        }
+        return true;
+    }
+private:
+    static void read_desc(const uint8_t *&p, const uint8_t *e, int &type, uint32_t &len) {
+        if (p >= e) throw InputError("BCF: truncated typed value");
+        const uint8_t d = *p++;
+        type = d & 0xF; len = d >> 4;
+        if (len == 15) {
+            int t2; uint32_t l2;
+            read_desc(p, e, t2, l2);
+            len = (uint32_t)read_int(p, e, t2);
+        }
+    }
+    static int32_t read_int(const uint8_t *&p, const uint8_t *e, int type) {
+        int32_t v = 0;
+        if (type == 1) { if (p + 1 > e) goto bad; v = (int8_t)*p; p += 1; }
+        else if (type == 2) { if (p + 2 > e) goto bad; int16_t t; memcpy(&t, p, 2); v = t; p += 2; }
+        else if (type == 3) { if (p + 4 > e) goto bad; memcpy(&v, p, 4); p += 4; }
+        else throw InputError("BCF: expected an integer typed value");
+        return v;
+    bad:
+        throw InputError("BCF: truncated integer");
+    }
+    static void skip_typed(const uint8_t *&p, const uint8_t *e) {
+        int type; uint32_t len;
+        read_desc(p, e, type, len);
+        const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
+        if (p + (size_t)len * esz > e) throw InputError("BCF: truncated typed value");
+        p += (size_t)len * esz;
+    }
+    static std::string read_typed_string(const uint8_t *&p, const uint8_t *e) {
+        int type; uint32_t len;
+        read_desc(p, e, type, len);
+        if (type != 7 && len != 0) throw InputError("BCF: expected a string typed value");
+        if (p + len > e) throw InputError("BCF: truncated string");
+        std::string s((const char *)p, len);
+        p += len;
+        while (!s.empty() && s.back() == '\0') s.pop_back();
+        return s;
+    }
+    const std::string &dict_name(int32_t id) const {
+        static const std::string unknown = "?";
+        return id >= 0 && (size_t)id < dict_.size() && !dict_[id].empty() ? dict_[id] : unknown;
+    }
+    // ID=..., optional IDX=... of one ##KEY=<...> line
+    static bool meta_id(const std::string &line, size_t lt, std::string &id, int &idx) {
+        idx = -1;
+        size_t p = line.find("ID=", lt);
+        if (p == std::string::npos) return false;
+        size_t e = line.find_first_of(",>", p);
+        id = line.substr(p + 3, (e == std::string::npos ? line.size() : e) - p - 3);
+        size_t q = line.find("IDX=", lt);
+        if (q != std::string::npos) idx = atoi(line.c_str() + q + 4);
+        return true;
+    }
+    void parse_header(const std::string &text) {
+        std::unordered_map<std::string, int> seen;
+        auto add_dict = [&](const std::string &id, int idx) {
+            auto it = seen.find(id);
+            if (it != seen.end()) return;
+            if (idx < 0) idx = (int)dict_next_++;
+            else dict_next_ = std::max<size_t>(dict_next_, (size_t)idx + 1);
+            if (dict_.size() <= (size_t)idx) dict_.resize(idx + 1);
+            dict_[idx] = id;
+            seen[id] = idx;
+        };
+        add_dict("PASS", 0);
+        size_t b = 0;
+        while (b < text.size()) {
+            size_t e = text.find('\n', b);
+            if (e == std::string::npos) e = text.size();
+            std::string line = text.substr(b, e - b);
+            while (!line.empty() && (line.back() == '\r' || line.back() == '\0')) line.pop_back();
+            b = e + 1;
+            if (line.rfind("##", 0) == 0) {
+                size_t eq = line.find("=<");
+                if (eq == std::string::npos) continue;
+                const std::string key = line.substr(2, eq - 2);
+                std::string id; int idx;
+                if (!meta_id(line, eq, id, idx)) continue;
+                if (key == "contig") {
+                    if (idx < 0) idx = (int)contig_next_++;
+                    else contig_next_ = std::max<size_t>(contig_next_, (size_t)idx + 1);
+                    if (contigs_.size() <= (size_t)idx) contigs_.resize(idx + 1);
+                    contigs_[idx] = id;
+                } else if (key == "FILTER" || key == "INFO" || key == "FORMAT") {
+                    add_dict(id, idx);
+                }
+            } else if (!line.empty() && line[0] == '#') {
+                std::vector<std::string> f = split_char(line, '\t');
+                for (size_t i = 9; i < f.size(); i++) samples_.push_back(f[i]);
+            }
+        }
+        auto it = seen.find("GT");
+        gt_key_ = it == seen.end() ? -1 : it->second;
+    }
+    std::unique_ptr<InflateStream> in_;
+    std::vector<std::string> contigs_, dict_;
+    size_t dict_next_ = 0, contig_next_ = 0;
+    int32_t gt_key_ = -1;
+    std::vector<uint8_t> shared_, indiv_;
+};
+
+std::unique_ptr<VariantSource> open_variant_source(const std::string &path) {
+    auto s = std::make_unique<InflateStream>();
+    if (!s->open(path)) return nullptr;
+    uint8_t magic[5] = { 0 };
+    try {
+        if (!s->peek(magic, 5)) return nullptr;
+        if (!memcmp(magic, "BCF\2", 4)) {
+            auto src = std::make_unique<BcfSource>(std::move(s));
+            if (!src->read_header()) return nullptr;
+            return src;
+        }
+        if (magic[0] != '#') return nullptr;
+        auto src = std::make_unique<VcfTextSource>(std::move(s));
+        if (!src->read_header()) return nullptr;
+        return src;
+    } catch (const InputError &) {
+        return nullptr;
+    }
+}
+
+}  // namespace nph

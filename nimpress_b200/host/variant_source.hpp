@@ -1,0 +1,65 @@
+// variant_source.hpp -- streaming reader of VCF text / BCF2, plain, gzip or BGZF, written against
+// zlib only.  It stands in for what the reference gets from hts-nim/htslib (third-party, not in
+// the reference tree): sample names, and per record CHROM, POS, rlen, REF, ALT, FILTER and the
+// FORMAT/GT payload.  For BCF the GT payload is handed out as the raw typed-value bytes of the
+// record -- exactly the slab the CUDA kernels decode -- without widening or per-sample parsing;
+// for VCF text the GT strings are encoded the way htslib's vcf_parse_format encodes them.
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "util.hpp"
+
+namespace nph {
+
+// Sequential byte stream over a plain / gzip / BGZF file (BGZF = concatenated gzip members).
+class InflateStream {
+public:
+    ~InflateStream();
+    bool open(const std::string &path);
+    size_t read(void *dst, size_t n);                 // up to n bytes; 0 at end of stream
+    bool read_exact(void *dst, size_t n);
+    bool getline(std::string &line);                  // strips \n and a preceding \r
+    bool peek(void *dst, size_t n);                   // look ahead without consuming (n <= 64)
+private:
+    bool fill();
+    FILE *fp_ = nullptr;
+    bool compressed_ = false, zinit_ = false, eof_ = false;
+    z_stream zs_{};
+    std::vector<uint8_t> in_, out_;
+    size_t out_pos_ = 0, out_len_ = 0;
+};
+
+struct VariantRecord {
+    int32_t contig_id = -1;
+    const std::string *contig = nullptr;
+    int64_t pos = 0;                                  // 1-based
+    int64_t rlen = 0;                                 // reference span used for overlap (REF length or INFO/END)
+    std::string ref;
+    std::vector<std::string> alts;
+    std::string filter;                               // ".", "PASS" or ';'-joined names
+    bool has_gt = false;
+    int gt_width = 1, ploidy = 0;                     // bytes per value, values per sample
+    const uint8_t *gt = nullptr;                      // n_samples * ploidy * gt_width bytes, valid until next()
+    int64_t end() const { return pos + rlen - 1; }    // 1-based inclusive
+};
+
+class VariantSource {
+public:
+    virtual ~VariantSource() = default;
+    virtual bool next(VariantRecord &rec) = 0;        // false at end of file; throws InputError on corrupt input
+    const std::vector<std::string> &samples() const { return samples_; }
+    int64_t n_samples() const { return (int64_t)samples_.size(); }
+protected:
+    std::vector<std::string> samples_;
+};
+
+// nullptr: the file cannot be opened or is neither VCF nor BCF (the reference: open() == false).
+std::unique_ptr<VariantSource> open_variant_source(const std::string &path);
+
+}  // namespace nph

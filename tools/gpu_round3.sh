@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+B="python bench.py --variants 32768 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --brief"
+echo "== default"; timeout 200 $B 2>&1 | tail -1
+echo "== two-kernel"; NPC_FUSED=0 timeout 300 $B 2>&1 | tail -1
+for cfg in "1 0 0 4" "2 0 0 4" "3 0 0 4" "4 0 0 4" "2 0 4 4" "2 0 6 4" "2 0 9 4" "1 0 8 4" "1 0 16 5" "2 0 0 2" "2 0 0 5" "4 0 2 4" "4 0 4 4"; do set -- $cfg
+  echo "== R=$1 S=$2 L=$3 A=$4"; NPC_FUSED_R=$1 NPC_FUSED_S=$2 NPC_FUSED_L=$3 NPC_FUSED_A=$4 timeout 200 $B 2>&1 | tail -1
+done 2>&1 | tee gpurun_out/sweep2.log
+echo "== K=2"; NPC_FUSED_K=2 timeout 200 $B 2>&1 | tail -1 | tee -a gpurun_out/sweep2.log
+echo "== ncu full fused"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_fused' -s 2 -c 1 -o gpurun_out/prof_fused_r2 -f \
+    python bench.py --variants 8192 --steps 1 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/ncu_fused.log 2>&1
+tail -2 gpurun_out/ncu_fused.log
