@@ -149,6 +149,25 @@ int npc_accumulate_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_st
                                 const npc_row *rows, int64_t n_rows, int32_t rows_on_device,
                                 const int64_t *counts_dev);
 
+/* ---- resident slab: upload first, then score in exact score-file order ----------------- */
+
+/* The reference adds loci to every sample's sum in score-file order, while records arrive in
+ * genotype-file order.  A host that wants the reference's summation order bit for bit uploads
+ * the matched records' GT rows into a device slab as they stream past (staging ring -> slab),
+ * then submits the score rows in score-file order, npc_row.gt_row naming slab rows.  Scoring is
+ * two orders of magnitude faster than PCIe, so deferring it costs nothing.
+ *
+ * npc_resident_reserve: (re)allocate the slab for capacity_rows rows of the context's
+ * row_stride; *granted_rows may come back smaller when device memory is short (the caller then
+ * scores and refills in rounds). */
+int npc_resident_reserve(npc_ctx *ctx, int64_t capacity_rows, int64_t *granted_rows);
+/* Asynchronous: copy n_gt_rows staged rows of `slot` to slab rows dst_row.. and return the slot
+ * to the ring when the copy is done. */
+int npc_stage_upload(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, int64_t dst_row);
+/* Asynchronous: count -> decide -> accumulate for n_rows score rows over the slab, in order
+ * (any n_rows: split internally into launches of at most max_rows_per_block rows). */
+int npc_score_resident(npc_ctx *ctx, const npc_row *rows, int64_t n_rows);
+
 /* ---- results ---------------------------------------------------------------------------- */
 
 /* Waits for all submitted blocks.  scores_out[n_samples] = sum / (2*nloci) + offset
@@ -170,8 +189,8 @@ int64_t npc_launch_count(const npc_ctx *ctx);
 
 /* Which kernels npc_score_block* uses for this context: shape[0] = 1 for the fused persistent
  * kernel (int8 diploid cohorts that fit one resident pass), 0 for the count/decide/accumulate
- * sequence; then grid, consumer warps, chunks per thread, rows per tile, ring stages,
- * lag * 100 + auxiliary warps, dynamic shared-memory bytes. */
+ * sequence; then grid, consumer warps, chunks per thread, rows per tile, raw stages * 1000 +
+ * index-ring tiles, lag * 100 + decider warps, dynamic shared-memory bytes. */
 int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
 
 /* ---- utilities (tests / bench) ----------------------------------------------------------- */

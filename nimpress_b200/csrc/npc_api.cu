@@ -37,8 +37,11 @@ struct npc_ctx {
     std::string err;
     // fused persistent kernel (int8 diploid): launch shape fixed per context
     bool fused_ok = false;
-    int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 2, f_S = 8, f_L = 4, f_A = 4, f_slab = 0;
+    int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 2, f_Sr = 4, f_Sc = 8, f_L = 7, f_A = 4, f_slab = 0;
     uint32_t f_smem = 0;
+    uint8_t *d_slab = nullptr;              // resident slab (npc_resident_reserve)
+    int64_t slab_rows = 0;
+    cudaEvent_t ev_slab = nullptr;          // last scoring launch that read the slab
     ull *d_fcounts = nullptr;               // [max_rows] arrivals | nmiss | neff words of the fused kernel
 };
 
@@ -71,7 +74,8 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_slab);
+    if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -92,9 +96,10 @@ static fused_fn fused_kernel(int K, int R) {
 }
 
 // Launch shape of the fused kernel: one CTA per SM, each owning a contiguous range of 16-byte
-// chunks; K chunks per consumer thread; R rows per tile and S ring stages sized to fill shared
-// memory; the accumulate phase runs L tiles behind the count phase; A auxiliary warps.
-// NPC_FUSED_{K,R,S,L,A} override for tuning; NPC_FUSED=0 forces the two-kernel path.
+// chunks; K chunks per consumer thread; R rows per tile; a raw ring of Sr stages (prefetch) and
+// an index ring of Sc tiles (rows counted but not yet decided) sized to fill shared memory; the
+// accumulate phase runs L tiles behind the count phase; A decider warps.
+// NPC_FUSED_{K,R,SR,SC,L,A} override for tuning; NPC_FUSED=0 forces the two-kernel path.
 static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     c->fused_ok = false;
     if (c->width != 1 || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
@@ -108,20 +113,21 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     if (nc > 16) return NPC_OK;                       // cohort too wide for one resident pass: two-kernel path
     c->f_K = K; c->f_nc = (int)nc; c->f_slab = (int)(nc * 32 * K * 16);
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
-    const int per_row = c->f_slab + LUT_N * 8 + 12;
-    const int fixed = (int)(FUSED_CNT_TABLES * LUT_N * 8) + 2048;
-    const int ring_rows = std::min(96, (max_smem - fixed) / per_row);
-    if (ring_rows < 3) return NPC_OK;
-    int R = env_int("NPC_FUSED_R", 0), S = env_int("NPC_FUSED_S", 0), L = env_int("NPC_FUSED_L", 0), A = env_int("NPC_FUSED_A", 4);
-    if (!fused_kernel(K, R)) R = ring_rows >= 24 ? 2 : 1;
-    if (S <= 0) S = std::min(32, ring_rows / R);
-    while (S >= 3 && (int)FusedSmem::make(R, S, c->f_slab).total > max_smem) S--;
-    if (S < 3) return NPC_OK;
-    if (L <= 0) L = std::max(1, (S * 55) / 100);      // about half the ring is lag, the rest prefetch
-    if (L > S - 2) L = S - 2;
-    A = std::max(1, std::min(5, A));
-    FusedSmem m = FusedSmem::make(R, S, c->f_slab);
-    c->f_R = R; c->f_S = S; c->f_L = L; c->f_A = A; c->f_smem = m.total;
+    int R = env_int("NPC_FUSED_R", 2), Sr = env_int("NPC_FUSED_SR", 0), Sc = env_int("NPC_FUSED_SC", 0);
+    int L = env_int("NPC_FUSED_L", 0), A = env_int("NPC_FUSED_A", 4);
+    if (!fused_kernel(K, R)) R = 2;
+    // raw ring: about 70 KB of loads in flight per SM (HBM latency x per-SM bandwidth, with margin)
+    if (Sr <= 0) Sr = std::max(2, std::min(16, (72 * 1024) / (R * c->f_slab)));
+    if (Sc <= 0) {
+        Sc = 64;
+        while (Sc > 2 && (int)FusedSmem::make(R, Sr, Sc, c->f_slab).total > max_smem) Sc--;
+    }
+    while (Sr > 2 && (int)FusedSmem::make(R, Sr, Sc, c->f_slab).total > max_smem) Sr--;
+    if ((int)FusedSmem::make(R, Sr, Sc, c->f_slab).total > max_smem || Sc < 2) return NPC_OK;
+    if (L <= 0 || L > Sc - 1) L = Sc - 1;
+    A = std::max(1, std::min(6, A));
+    FusedSmem m = FusedSmem::make(R, Sr, Sc, c->f_slab);
+    c->f_R = R; c->f_Sr = Sr; c->f_Sc = Sc; c->f_L = L; c->f_A = A; c->f_smem = m.total;
     cudaError_t e = cudaFuncSetAttribute(fused_kernel(K, R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.total);
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
@@ -229,7 +235,7 @@ extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->laun
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!ctx || !shape) return NPC_EINVAL;
     shape[0] = ctx->fused_ok ? 1 : 0; shape[1] = ctx->f_grid; shape[2] = ctx->f_nc; shape[3] = ctx->f_K;
-    shape[4] = ctx->f_R; shape[5] = ctx->f_S; shape[6] = ctx->f_L * 100 + ctx->f_A; shape[7] = (int32_t)ctx->f_smem;
+    shape[4] = ctx->f_R; shape[5] = ctx->f_Sr * 1000 + ctx->f_Sc; shape[6] = ctx->f_L * 100 + ctx->f_A; shape[7] = (int32_t)ctx->f_smem;
     return NPC_OK;
 }
 
@@ -322,9 +328,9 @@ static int launch_fused(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
     P.sums = c->d_sums; P.counts = c->d_fcounts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
-    P.S = c->f_S; P.L = c->f_L; P.A = c->f_A; P.nc = c->f_nc; P.slab_stride = c->f_slab;
+    P.Sr = c->f_Sr; P.Sc = c->f_Sc; P.L = c->f_L; P.A = c->f_A; P.nc = c->f_nc; P.slab_stride = c->f_slab;
     void *args[] = { &P };
-    const dim3 grid(c->f_grid), block((c->f_nc + 1 + c->f_A) * 32);
+    const dim3 grid(c->f_grid), block((c->f_nc + 2 + c->f_A) * 32);
     NPC_CUDA(c, cudaLaunchCooperativeKernel((const void *)fused_kernel(c->f_K, c->f_R), grid, block, args, c->f_smem, c->stream));
     c->launches++;
     c->log_len += n_rows;
@@ -412,6 +418,61 @@ extern "C" int npc_accumulate_block_device(npc_ctx *ctx, const void *gt_dev, int
     const npc_row *d_rows;
     if ((rc = upload_rows(ctx, rows, n_rows, rows_on_device, &d_rows))) return rc;
     return launch_decide_accum(ctx, (const uint8_t *)gt_dev, row_stride, d_rows, n_rows, (const ull *)counts_dev);
+}
+
+// ---- resident slab ---------------------------------------------------------------------------
+
+extern "C" int npc_resident_reserve(npc_ctx *ctx, int64_t capacity_rows, int64_t *granted_rows) {
+    if (!ctx || capacity_rows < 0) return NPC_EINVAL;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    NPC_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->d_slab) { cudaFree(ctx->d_slab); ctx->d_slab = nullptr; ctx->slab_rows = 0; }
+    if (!ctx->ev_slab) NPC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_slab, cudaEventDisableTiming));
+    size_t free_b = 0, total_b = 0;
+    NPC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const int64_t budget = (int64_t)(free_b - std::min<size_t>(free_b, (size_t)1 << 30)) / ctx->row_stride;   // keep 1 GiB spare
+    int64_t rows = std::min(capacity_rows, budget);
+    if (rows < 1 && capacity_rows > 0) return fail(ctx, NPC_ENOMEM, "no device memory for a resident slab");
+    if (rows > 0) NPC_CUDA(ctx, cudaMalloc(&ctx->d_slab, (size_t)rows * ctx->row_stride));
+    ctx->slab_rows = rows;
+    if (granted_rows) *granted_rows = rows;
+    return NPC_OK;
+}
+
+extern "C" int npc_stage_upload(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, int64_t dst_row) {
+    if (!ctx) return NPC_EINVAL;
+    if (slot < 0 || slot >= ctx->n_slots || ctx->slot_state[slot] != 1) return fail(ctx, NPC_ESTATE, "slot was not acquired");
+    if (n_gt_rows < 0 || n_gt_rows > ctx->max_rows || dst_row < 0 || dst_row + n_gt_rows > ctx->slab_rows)
+        return fail(ctx, NPC_EINVAL, "npc_stage_upload: rows outside the resident slab");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    // a scoring launch may still be reading the slab rows we are about to overwrite
+    NPC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_slab, 0));
+    if (n_gt_rows)
+        NPC_CUDA(ctx, cudaMemcpyAsync(ctx->d_slab + dst_row * ctx->row_stride, ctx->h_gt[slot], (size_t)n_gt_rows * ctx->row_stride,
+                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+    NPC_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+    NPC_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], ctx->copy_stream));      // the slot is free once copied
+    ctx->slot_state[slot] = 2;
+    return NPC_OK;
+}
+
+extern "C" int npc_score_resident(npc_ctx *ctx, const npc_row *rows, int64_t n_rows) {
+    if (!ctx || n_rows < 0 || (n_rows && !rows)) return NPC_EINVAL;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < n_rows; i++)
+        if (rows[i].kind == NPC_KIND_GT && rows[i].gt_row >= ctx->slab_rows)
+            return fail(ctx, NPC_EINVAL, "npc_score_resident: gt_row outside the resident slab");
+    // every upload issued so far must have landed
+    for (int s = 0; s < ctx->n_slots; s++) NPC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
+    for (int64_t r0 = 0; r0 < n_rows; r0 += ctx->max_rows) {
+        const int64_t nr = std::min(ctx->max_rows, n_rows - r0);
+        const npc_row *d_rows;
+        int rc = upload_rows(ctx, rows + r0, nr, 0, &d_rows);
+        if (rc) return rc;
+        if ((rc = launch_block(ctx, ctx->d_slab, ctx->row_stride, d_rows, nr))) return rc;
+    }
+    NPC_CUDA(ctx, cudaEventRecord(ctx->ev_slab, ctx->stream));
+    return NPC_OK;
 }
 
 // ---- results -------------------------------------------------------------------------------

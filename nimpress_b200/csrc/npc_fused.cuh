@@ -9,20 +9,21 @@
 //  * The sample axis is cut into 16-byte chunks (8 samples); CTA b owns a contiguous chunk
 //    range for the whole launch and keeps those samples' fp64 sums in registers.
 //  * Score rows are taken in tiles of R rows.  A producer warp streams each tile's slab
-//    (R x owned bytes) into a ring of S shared-memory stages with TMA bulk copies
+//    (R x owned bytes) into a RAW ring of Sr shared-memory stages with TMA bulk copies
 //    (cp.async.bulk + mbarrier complete_tx).
-//  * Consumer warps run two software-pipelined phases on the ring: COUNT on tile i (decode each
-//    sample to a table offset, tally through an integer table, write the offsets back in place)
-//    and ACCUMULATE on tile i-L (one 8-byte table load + one DADD per sample).
+//  * COUNT (consumer warps, tile i): decode every sample of the raw stage to a one-byte table
+//    index, tally through a byte table, write the 8 index bytes of each chunk to the tile's slot
+//    of the INDEX ring (half the size of the raw data) and release the raw stage at once.
 //  * Between the phases sits a grid-wide dependency, not a grid-wide barrier.  Each row has one
-//    64-bit word in global memory: [arrivals:8 | nmiss:28 | neff:28].  A CTA publishes its
-//    tallies of a row AND its arrival with a single RED on that word -- the data is the flag,
-//    so no fence is needed.  An auxiliary warp that owns the tile then polls the R words until
-//    the arrival byte reads gridDim.x, makes the reference's fp64 decision per row and builds the
-//    value tables.  Tiles rotate over A auxiliary warps so their latency chains overlap, and the
-//    accumulate phase runs L tiles behind the count phase so the chain is off the critical path.
-//  * Rows are accumulated strictly in order, with the same rounded products as the reference:
-//    sums are bit-identical to the two-kernel path and to the CPU oracle.
+//    64-bit word in global memory: [arrivals:8 | nmiss:28 | neff:28].  A publisher warp adds the
+//    CTA's tallies of a row AND its arrival with a single RED on that word -- the data is the
+//    flag, so no fence is needed.  Decider warps (tiles rotate over them) poll the R words of a
+//    tile until the arrival byte reads gridDim.x, make the reference's fp64 decision per row and
+//    build the tile's value tables.  Under a saturated memory system that chain takes several
+//    microseconds; the index ring is deep enough (Sc tiles) to keep counting meanwhile.
+//  * ACCUMULATE (consumer warps, tile i-L): one 8-byte table load + one DADD per sample, rows
+//    strictly in order, with the same rounded products as the reference: sums are bit-identical
+//    to the two-kernel path and to the CPU oracle.
 #pragma once
 #include "npc_kernels.cuh"
 
@@ -39,16 +40,17 @@ struct FusedParams {
     ull *counts;               // [n_rows] arrivals<<56 | nmiss<<28 | neff, zeroed before the launch
     npc_locus *log;
     ull *nloci;
-    int32_t S, L, A;           // ring stages, count->accumulate lag in tiles, auxiliary warps
+    int32_t Sr, Sc, L, A;      // raw stages, index-ring tiles, count->accumulate lag (tiles), decider warps
     int32_t nc;                // consumer warps
-    int32_t slab_stride;       // bytes per row in a stage = nc*32*K*16 (every consumer thread has a cell)
+    int32_t slab_stride;       // bytes per row in a raw stage = nc*32*K*16 (every consumer thread has a cell)
 };
 
 constexpr int FUSED_CNT_BITS = 28;
+constexpr ull FUSED_CNT_MASK = (1ull << FUSED_CNT_BITS) - 1;
 // The tally table of a row depends only on T = eaidx+1.  Fast-path codes are alleles REF..ALT6
 // (T <= 7); for T >= 8 no fast-path code can match, so table 8 serves every larger T.
 constexpr uint32_t FUSED_CNT_TABLES = 8;
-constexpr ull FUSED_CNT_MASK = (1ull << FUSED_CNT_BITS) - 1;
+constexpr uint32_t FUSED_CNT_STRIDE = 80;      // bytes per tally table (68 one-byte entries, padded)
 
 // ---- PTX helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,7 +86,6 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ ull ld_relaxed_gpu_u64(const ull *p) {
     ull v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -93,9 +94,9 @@ __device__ __forceinline__ ull ld_relaxed_gpu_u64(const ull *p) {
 __device__ __forceinline__ void red_relaxed_gpu_add_u64(ull *p, ull v) {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
@@ -108,23 +109,47 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void red_shared_add_u32(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Two raw words (4 samples) -> one word of four 6-bit table indices, bytes = samples [0, 2, 1, 3].
+// (w & 0x0E0E0E0E)*33 puts index(code0 | code1<<3) of a word's two samples at bits 6..11 and 22..27.
+__device__ __forceinline__ uint32_t pack_idx_bytes(uint32_t w0, uint32_t w1) {
+    const uint32_t p0 = (w0 & 0x0E0E0E0Eu) * 33u, p1 = (w1 & 0x0E0E0E0Eu) * 33u;
+    return ((p0 >> 6) & 0x003F003Fu) | ((p1 << 2) & 0x3F003F00u);
+}
+// exact decode of one int8 diploid sample (low 16 bits of h) -> canonical index 64 + {d | 3 = missing}
+__device__ __forceinline__ uint32_t slow_idx(uint32_t h, int eaidx) {
+    int8_t a[2] = { (int8_t)(h & 0xFF), (int8_t)((h >> 8) & 0xFF) };
+    int d; bool miss;
+    decode_sample<int8_t>(a, 2, eaidx, d, miss);
+    return (uint32_t)(64 + (miss ? 3 : d));
 }
 
 // shared-memory carve-up (byte offsets from the dynamic smem base)
 struct FusedSmem {
-    uint32_t bars, cntacc, mode, eaidx, lut, cnt, data, total;
-    __host__ __device__ static FusedSmem make(int R, int S, int slab_stride) {
+    uint32_t bars, cntacc, mode, risgt, reaidx, cnt, lut, idx, data, total;
+    __host__ __device__ static FusedSmem make(int R, int Sr, int Sc, int slab_stride) {
         FusedSmem m;
         uint32_t o = 0;
-        m.bars = o;   o += 4u * S * 8u;                  o = (o + 127u) & ~127u;   // full, cntdone, lutready, empty
-        m.cntacc = o; o += (uint32_t)S * R * 4u;         o = (o + 127u) & ~127u;
-        m.mode = o;   o += (uint32_t)S * R * 4u;         o = (o + 127u) & ~127u;
-        m.eaidx = o;  o += (uint32_t)S * R * 4u;         o = (o + 127u) & ~127u;
-        m.lut = o;    o += (uint32_t)S * R * LUT_N * 8u; o = (o + 127u) & ~127u;
-        m.cnt = o;    o += FUSED_CNT_TABLES * LUT_N * 8u; o = (o + 127u) & ~127u;   // tally tables, one per T = eaidx+1
-        m.data = o;   o += (uint32_t)S * R * (uint32_t)slab_stride;
+        m.bars = o;   o += (2u * Sr + 2u * Sc) * 8u;             o = (o + 127u) & ~127u;  // full, r_empty | cnt_done, lut_ready
+        m.cntacc = o; o += (uint32_t)Sc * R * 4u;                o = (o + 127u) & ~127u;
+        m.mode = o;   o += (uint32_t)Sc * R * 4u;                o = (o + 127u) & ~127u;
+        m.risgt = o;  o += (uint32_t)Sr * R * 4u;                o = (o + 127u) & ~127u;
+        m.reaidx = o; o += (uint32_t)Sr * R * 4u;                o = (o + 127u) & ~127u;
+        m.cnt = o;    o += FUSED_CNT_TABLES * FUSED_CNT_STRIDE;  o = (o + 127u) & ~127u;
+        m.lut = o;    o += (uint32_t)Sc * R * LUT_N * 8u;        o = (o + 127u) & ~127u;
+        m.idx = o;    o += (uint32_t)Sc * R * (uint32_t)(slab_stride / 2); o = (o + 127u) & ~127u;
+        m.data = o;   o += (uint32_t)Sr * R * (uint32_t)slab_stride;
         m.total = o;
         return m;
     }
@@ -132,16 +157,17 @@ struct FusedSmem {
 
 // K = 16-byte chunks (8 samples each) per consumer thread, R = score rows per tile
 template <int K, int R>
-__global__ void __launch_bounds__(704, 1)      // <= 16 consumer warps + producer + <= 5 auxiliary warps
+__global__ void __launch_bounds__(768, 1)      // <= 16 consumer warps + producer + publisher + <= 6 deciders
 k_fused_i8x2(const FusedParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int S = P.S, L = P.L, NC = P.nc, A = P.A;
-    const FusedSmem M = FusedSmem::make(R, S, P.slab_stride);
+    const int Sr = P.Sr, Sc = P.Sc, L = P.L, NC = P.nc, A = P.A;
+    const FusedSmem M = FusedSmem::make(R, Sr, Sc, P.slab_stride);
     const uint32_t sb = smem_u32(smem);
-    const uint32_t bar_full = sb + M.bars, bar_cnt = bar_full + 8u * S, bar_lut = bar_full + 16u * S, bar_empty = bar_full + 24u * S;
+    const uint32_t bar_full = sb + M.bars, bar_rempty = bar_full + 8u * Sr, bar_cnt = bar_rempty + 8u * Sr, bar_lut = bar_cnt + 8u * Sc;
     uint32_t *s_cntacc = reinterpret_cast<uint32_t *>(smem + M.cntacc);
     int32_t *s_mode = reinterpret_cast<int32_t *>(smem + M.mode);
-    int32_t *s_eaidx = reinterpret_cast<int32_t *>(smem + M.eaidx);
+    int32_t *s_risgt = reinterpret_cast<int32_t *>(smem + M.risgt);
+    int32_t *s_reaidx = reinterpret_cast<int32_t *>(smem + M.reaidx);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (P.n_rows + R - 1) / R;
@@ -154,78 +180,71 @@ k_fused_i8x2(const FusedParams P) {
     const uint32_t slab_bytes = (uint32_t)nch * 16u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) {
-            mbar_init(bar_full + 8u * s, 1);
-            mbar_init(bar_cnt + 8u * s, NC);
-            mbar_init(bar_lut + 8u * s, 1);
-            mbar_init(bar_empty + 8u * s, NC);
-        }
+        for (int s = 0; s < Sr; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_rempty + 8u * s, NC); }
+        for (int s = 0; s < Sc; s++) { mbar_init(bar_cnt + 8u * s, NC); mbar_init(bar_lut + 8u * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < S * R; i += blockDim.x) s_cntacc[i] = 0;
+    for (int i = threadIdx.x; i < Sc * R; i += blockDim.x) s_cntacc[i] = 0;
     for (int i = threadIdx.x; i < (int)FUSED_CNT_TABLES * LUT_N; i += blockDim.x) {
-        const int c = lut_code(i % LUT_N, i / LUT_N + 1);
-        reinterpret_cast<uint2 *>(smem + M.cnt)[i] = make_uint2(c == 3 ? 0x10000u : (uint32_t)c, 0u);
+        const int c = lut_code(i % LUT_N, i / LUT_N + 1);                  // entry = d | missing << 5
+        smem[M.cnt + (i / LUT_N) * FUSED_CNT_STRIDE + (i % LUT_N)] = (uint8_t)(c == 3 ? 32 : c);
     }
-    // cells beyond this CTA's owned range are decoded too (branch-free consumers) but never tallied
-    // or stored; give them defined contents once
-    for (uint32_t i = threadIdx.x; i < (uint32_t)S * R * (uint32_t)P.slab_stride / 16u; i += blockDim.x)
+    // raw cells beyond this CTA's owned range are decoded too (branch-free consumers) but never
+    // tallied or stored; give them defined contents once (TMA only ever writes the owned bytes)
+    for (uint32_t i = threadIdx.x; i < (uint32_t)Sr * R * (uint32_t)P.slab_stride / 16u; i += blockDim.x)
         reinterpret_cast<uint4 *>(smem + M.data)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (warp == NC) {
-        // ================= producer: row modes + TMA bulk loads ===============================
+        // ================= producer: row kinds + TMA bulk loads ===============================
         const uint64_t pol = l2_evict_first_policy();
+        int s = 0; uint32_t ph = 0;
         for (int64_t t = 0; t < n_tiles; t++) {
-            const int s = (int)(t % S);
-            mbar_wait(bar_empty + 8u * s, (uint32_t)((t / S) & 1) ^ 1u);
+            mbar_wait(bar_rempty + 8u * s, ph ^ 1u);
             const int nr = (int)min((int64_t)R, P.n_rows - t * R);
-            uint32_t n_gt = 0;
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                bool is_gt = false;
-                int ea = 0;
-                if (r < nr) {
-                    const npc_row row = P.rows[t * R + r];
-                    is_gt = row.kind == NPC_KIND_GT && row.gt_row >= 0;
-                    ea = row.eaidx;
-                    if (is_gt) n_gt++;
-                }
-                if (lane == 0) { s_mode[s * R + r] = is_gt ? MODE_DECODE : MODE_SKIP; s_eaidx[s * R + r] = ea; }
+            npc_row row;
+            bool is_gt = false;
+            if (lane < nr) {
+                row = P.rows[t * R + lane];
+                is_gt = row.kind == NPC_KIND_GT && row.gt_row >= 0;
             }
+            if (lane < R) { s_risgt[s * R + lane] = is_gt ? 1 : 0; s_reaidx[s * R + lane] = is_gt ? row.eaidx : 0; }
+            const uint32_t n_gt = __popc(__ballot_sync(0xffffffffu, is_gt));
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_expect_tx(bar_full + 8u * s, n_gt * slab_bytes);     // releases the mode writes too
-                for (int r = 0; r < nr; r++) {
-                    const npc_row row = P.rows[t * R + r];
-                    if (row.kind == NPC_KIND_GT && row.gt_row >= 0)
-                        tma_load_1d(sb + M.data + (uint32_t)(s * R + r) * (uint32_t)P.slab_stride,
-                                    P.gt + (int64_t)row.gt_row * P.row_stride + c0 * 16, slab_bytes, bar_full + 8u * s, pol);
-                }
-            }
+            if (lane == 0) mbar_arrive_expect_tx(bar_full + 8u * s, n_gt * slab_bytes);   // releases the kind writes too
             __syncwarp();
+            if (is_gt)
+                tma_load_1d(sb + M.data + (uint32_t)(s * R + lane) * (uint32_t)P.slab_stride,
+                            P.gt + (int64_t)row.gt_row * P.row_stride + c0 * 16, slab_bytes, bar_full + 8u * s, pol);
+            if (++s == Sr) { s = 0; ph ^= 1u; }
         }
-    } else if (warp > NC) {
-        // ================= auxiliary warps: publish tallies, wait for the grid, decide, build tables
-        const int a = warp - NC - 1;
-        for (int64_t t = a; t < n_tiles; t += A) {
-            const int s = (int)(t % S);
-            const uint32_t ph = (uint32_t)((t / S) & 1);
-            const int nr = (int)min((int64_t)R, P.n_rows - t * R);
+    } else if (warp == NC + 1) {
+        // ================= publisher: one RED per row = tallies + arrival ======================
+        int s = 0; uint32_t ph = 0;
+        for (int64_t t = 0; t < n_tiles; t++) {
             mbar_wait(bar_cnt + 8u * s, ph);
-            ull *word = P.counts + t * R + lane;
+            const int nr = (int)min((int64_t)R, P.n_rows - t * R);
             if (lane < nr) {
                 const uint32_t v = s_cntacc[s * R + lane];
                 s_cntacc[s * R + lane] = 0;
-                red_relaxed_gpu_add_u64(word, (1ull << 56) | ((ull)(v >> 16) << FUSED_CNT_BITS) | (ull)(v & 0xFFFFu));
+                red_relaxed_gpu_add_u64(P.counts + t * R + lane, (1ull << 56) | ((ull)(v >> 16) << FUSED_CNT_BITS) | (ull)(v & 0xFFFFu));
             }
+            if (++s == Sc) { s = 0; ph ^= 1u; }
+        }
+    } else if (warp > NC + 1) {
+        // ================= deciders: wait for the grid, decide, build the value tables ========
+        const int a = warp - NC - 2;
+        for (int64_t t = a; t < n_tiles; t += A) {
+            const int s = (int)(t % Sc);
+            const int nr = (int)min((int64_t)R, P.n_rows - t * R);
             RowP rp; rp.c0 = rp.c1 = rp.c2 = rp.cm = 0.0; rp.mode = MODE_SKIP; rp.eaidx = 0;
             int used = 0;
             if (lane < nr) {
+                const npc_row row = P.rows[t * R + lane];            // in flight while we poll
+                const ull *word = P.counts + t * R + lane;
                 ull v = ld_relaxed_gpu_u64(word);
-                while ((v >> 56) != (ull)gridDim.x) { __nanosleep(40); v = ld_relaxed_gpu_u64(word); }
-                const npc_row row = P.rows[t * R + lane];
+                while ((v >> 56) != (ull)gridDim.x) { __nanosleep(64); v = ld_relaxed_gpu_u64(word); }
                 npc_locus rec;
                 decide_row(P.pol, row, (v >> FUSED_CNT_BITS) & FUSED_CNT_MASK, v & FUSED_CNT_MASK, P.n, rp, rec);
                 used = rec.used;
@@ -254,83 +273,88 @@ k_fused_i8x2(const FusedParams P) {
         }
     } else {
         // ================= consumers: count tile i, accumulate tile i-L =======================
-        // thread (warp, lane) owns cells jc[k] = lane + 32*(warp + NC*k) of every row slab
-        uint32_t cell[K];                      // byte offset of the thread's cell inside a row slab
+        // thread (warp, lane) owns cell jc[k] = lane + 32*(warp + NC*k) of every row slab
+        uint32_t cell[K];                      // index of the thread's cell inside a row slab
         uint32_t own[K];                       // 0xFFFFFFFF when the cell holds samples of this CTA
         uint32_t tailor[K];                    // non-zero forces the exact decode (cohort's last, partial chunk)
         int valid[K];
-        double acc[K][8];
+        double acc[K][8];                      // sums, in index-byte order: samples [0,2,1,3,4,6,5,7] of the chunk
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int jc = lane + 32 * (warp + NC * k);
-            cell[k] = (uint32_t)jc * 16u;
+            cell[k] = (uint32_t)jc;
             const int64_t g = c0 + jc;
             valid[k] = jc < nch ? (int)min((int64_t)8, P.n - g * 8) : 0;
             own[k] = jc < nch ? 0xFFFFFFFFu : 0u;
             tailor[k] = (jc < nch && valid[k] < 8) ? 0xF0u : 0u;
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[k][e] = e < valid[k] ? P.sums[g * 8 + e] : 0.0;
+            for (int e = 0; e < 8; e++) {
+                const int smp = (e & 4) | ((e & 1) << 1) | ((e >> 1) & 1);          // byte position e holds sample smp
+                acc[k][e] = smp < valid[k] ? P.sums[g * 8 + smp] : 0.0;
+            }
         }
-        const uint32_t slab = (uint32_t)P.slab_stride;
-        int s_c = 0, s_a = 0;                  // ring positions of the count / accumulate phase
-        uint32_t ph_c = 0, ph_a = 0;
+        const uint32_t slab = (uint32_t)P.slab_stride, islab = slab >> 1;
+        int sr = 0, sc = 0, sa = 0;            // ring positions: raw stage, index slot being counted / accumulated
+        uint32_t ph_r = 0, ph_a = 0;
         for (int64_t i = 0; i < n_tiles + L; i++) {
             if (i < n_tiles) {
-                mbar_wait(bar_full + 8u * s_c, ph_c);
-                const uint32_t d0 = sb + M.data + (uint32_t)(s_c * R) * slab;
+                mbar_wait(bar_full + 8u * sr, ph_r);
+                const uint32_t d0 = sb + M.data + (uint32_t)(sr * R) * slab;
+                const uint32_t x0 = sb + M.idx + (uint32_t)(sc * R) * islab;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    if (s_mode[s_c * R + r] != MODE_DECODE) continue;
-                    const int ea = s_eaidx[s_c * R + r];
-                    const uint32_t cnt = sb + M.cnt + (uint32_t)min(ea, (int)FUSED_CNT_TABLES - 1) * (LUT_N * 8u);
+                    if (!s_risgt[sr * R + r]) continue;
+                    const int ea = s_reaidx[sr * R + r];
+                    const uint32_t cnt = sb + M.cnt + (uint32_t)min(ea, (int)FUSED_CNT_TABLES - 1) * FUSED_CNT_STRIDE;
                     uint32_t tally = 0;                          // low half: effect alleles, high half: missing samples
 #pragma unroll
                     for (int k = 0; k < K; k++) {
-                        const uint32_t addr = d0 + r * slab + cell[k];
-                        const uint4 w = lds_v4(addr);
-                        uint32_t ww[4] = { w.x, w.y, w.z, w.w }, o[4];
+                        const uint4 w = lds_v4(d0 + r * slab + cell[k] * 16u);
+                        uint32_t i0, i1;
                         if (((((w.x | w.y) | (w.z | w.w)) & 0xF0F0F0F0u) | tailor[k]) == 0u) {
-#pragma unroll
-                            for (int e = 0; e < 4; e++) o[e] = pack_idx8(ww[e]);
+                            i0 = pack_idx_bytes(w.x, w.y);
+                            i1 = pack_idx_bytes(w.z, w.w);
                         } else {
                             const int vk = own[k] ? valid[k] : 8;
+                            const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+                            uint32_t b[8];
 #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const uint32_t lo = 2 * e < vk ? slow_off8(ww[e] & 0xFFFFu, ea) : 64u * 8u;
-                                const uint32_t hi = 2 * e + 1 < vk ? slow_off8(ww[e] >> 16, ea) : 64u * 8u;
-                                o[e] = lo | (hi << 16);
-                            }
+                            for (int e = 0; e < 8; e++)
+                                b[e] = e < vk ? slow_idx((ww[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu, ea) : 64u;
+                            i0 = b[0] | (b[2] << 8) | (b[1] << 16) | (b[3] << 24);
+                            i1 = b[4] | (b[6] << 8) | (b[5] << 16) | (b[7] << 24);
                         }
                         uint32_t t = 0;
 #pragma unroll
-                        for (int e = 0; e < 4; e++) t += lds_u32(cnt + (o[e] & 0xFFFFu)) + lds_u32(cnt + (o[e] >> 16));
-                        tally += t & own[k];
-                        sts_v4(addr, make_uint4(o[0], o[1], o[2], o[3]));
+                        for (int e = 0; e < 4; e++)
+                            t += lds_u8(cnt + __byte_perm(i0, 0, 0x4440 + e)) + lds_u8(cnt + __byte_perm(i1, 0, 0x4440 + e));
+                        tally += ((t & 31u) | ((t >> 5) << 16)) & own[k];
+                        sts_v2(x0 + r * islab + cell[k] * 8u, i0, i1);
                     }
                     tally = __reduce_add_sync(0xffffffffu, tally);
-                    if (lane == 0 && tally) atomicAdd(&s_cntacc[s_c * R + r], tally);
+                    if (lane == 0) red_shared_add_u32(smem_u32(&s_cntacc[sc * R + r]), tally);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_cnt + 8u * s_c);
-                if (++s_c == S) { s_c = 0; ph_c ^= 1u; }
+                if (lane == 0) { mbar_arrive(bar_rempty + 8u * sr); mbar_arrive(bar_cnt + 8u * sc); }
+                if (++sr == Sr) { sr = 0; ph_r ^= 1u; }
+                if (++sc == Sc) sc = 0;
             }
             if (i >= L) {
-                mbar_wait(bar_lut + 8u * s_a, ph_a);
-                const uint32_t d0 = sb + M.data + (uint32_t)(s_a * R) * slab;
-                const uint32_t l0 = sb + M.lut + (uint32_t)(s_a * R) * (LUT_N * 8u);
+                mbar_wait(bar_lut + 8u * sa, ph_a);
+                const uint32_t x0 = sb + M.idx + (uint32_t)(sa * R) * islab;
+                const uint32_t l0 = sb + M.lut + (uint32_t)(sa * R) * (LUT_N * 8u);
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const int mode = s_mode[s_a * R + r];
+                    const int mode = s_mode[sa * R + r];
                     const uint32_t lut = l0 + r * (LUT_N * 8u);
                     if (mode == MODE_DECODE) {
 #pragma unroll
                         for (int k = 0; k < K; k++) {
-                            const uint4 w = lds_v4(d0 + r * slab + cell[k]);
-                            const uint32_t o[4] = { w.x, w.y, w.z, w.w };
+                            const uint2 v = lds_v2(x0 + r * islab + cell[k] * 8u);
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                acc[k][2 * e] = __dadd_rn(acc[k][2 * e], lds_f64(lut + (o[e] & 0xFFFFu)));
-                                acc[k][2 * e + 1] = __dadd_rn(acc[k][2 * e + 1], lds_f64(lut + (o[e] >> 16)));
+                                acc[k][e] = __dadd_rn(acc[k][e], lds_f64(lut + (__byte_perm(v.x, 0, 0x4440 + e) << 3)));
+                                acc[k][4 + e] = __dadd_rn(acc[k][4 + e], lds_f64(lut + (__byte_perm(v.y, 0, 0x4440 + e) << 3)));
                             }
                         }
                     } else if (mode == MODE_CONST) {
@@ -341,18 +365,17 @@ k_fused_i8x2(const FusedParams P) {
                             for (int e = 0; e < 8; e++) acc[k][e] = __dadd_rn(acc[k][e], c);
                     }
                 }
-                fence_proxy_async_smem();       // our in-place writes are ordered before the next TMA fill
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8u * s_a);
-                if (++s_a == S) { s_a = 0; ph_a ^= 1u; }
+                if (++sa == Sc) { sa = 0; ph_a ^= 1u; }
             }
         }
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            const int64_t g = c0 + (lane + 32 * (warp + NC * k));
+            const int64_t g = c0 + cell[k];
 #pragma unroll
-            for (int e = 0; e < 8; e++)
-                if (e < valid[k]) P.sums[g * 8 + e] = acc[k][e];
+            for (int e = 0; e < 8; e++) {
+                const int smp = (e & 4) | ((e & 1) << 1) | ((e >> 1) & 1);
+                if (smp < valid[k]) P.sums[g * 8 + smp] = acc[k][e];
+            }
         }
     }
 }

@@ -62,6 +62,9 @@ def load_library():
         "npc_score_block_device": (C.c_int, [vp, vp, i64, i64, vp, i64, i32]),
         "npc_count_block_device": (C.c_int, [vp, vp, i64, i64, vp, i64, i32, vp]),
         "npc_accumulate_block_device": (C.c_int, [vp, vp, i64, i64, vp, i64, i32, vp]),
+        "npc_resident_reserve": (C.c_int, [vp, i64, pi64]),
+        "npc_stage_upload": (C.c_int, [vp, i32, i64, i64]),
+        "npc_score_resident": (C.c_int, [vp, vp, i64]),
         "npc_finish": (C.c_int, [vp, f64, vp, pi64, vp, i64, pi64]),
         "npc_partial": (C.c_int, [vp, vp, pi64, vp, i64, pi64]),
         "npc_partial_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
@@ -149,6 +152,19 @@ class Engine:
             view[:g8.shape[0], :g8.shape[1]] = g8
         self.score_block(slot, g8.shape[0], rows)
 
+    # -- resident slab: upload as records stream past, score later in score-file order
+    def resident_reserve(self, capacity_rows):
+        g = C.c_int64()
+        self._ck(self.L.npc_resident_reserve(self.h, int(capacity_rows), C.byref(g)))
+        return g.value
+
+    def stage_upload(self, slot, n_gt_rows, dst_row):
+        self._ck(self.L.npc_stage_upload(self.h, slot, int(n_gt_rows), int(dst_row)))
+
+    def score_resident(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        self._ck(self.L.npc_score_resident(self.h, rows.ctypes.data, len(rows)))
+
     # -- device-resident blocks
     def score_block_device(self, gt_dev, row_stride, n_gt_rows, rows, n_rows=None):
         if isinstance(rows, np.ndarray):
@@ -216,7 +232,9 @@ class Engine:
         self._ck(self.L.npc_kernel_shape(self.h, C.byref(a)))
         keys = ("fused", "grid", "consumer_warps", "chunks_per_thread", "rows_per_tile", "stages", "lag", "smem_bytes")
         d = dict(zip(keys, list(a)))
-        d["aux_warps"], d["lag"] = d["lag"] % 100, d["lag"] // 100
+        d["decider_warps"], d["lag"] = d["lag"] % 100, d["lag"] // 100
+        d["raw_stages"], d["index_tiles"] = d["stages"] // 1000, d["stages"] % 1000
+        del d["stages"]
         return d
 
     @property

@@ -1,0 +1,215 @@
+#include "driver.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "stats.hpp"
+
+namespace nph {
+
+namespace {
+
+struct Ctx {                                       // RAII over npc_ctx
+    npc_ctx *h = nullptr;
+    ~Ctx() { if (h) npc_destroy(h); }
+    void ck(int rc, const char *what) const {
+        if (rc != NPC_OK) throw std::runtime_error(std::string(what) + ": " + npc_last_error(h) + " (rc " + std::to_string(rc) + ")");
+    }
+};
+
+// per-contig index of the score entries for the streaming findVariant
+struct ContigIndex {
+    std::vector<std::pair<int64_t, int64_t>> by_pos;   // (pos, entry index), sorted
+    int64_t max_reflen = 1;
+};
+
+enum { PENDING = -1 };                             // entry state before a record or EOF settles it
+
+// Re-encode one record's GT payload into the context layout (width w_dst, ploidy p_dst): wider
+// integers with the sentinels translated, missing trailing values padded with vector_end --
+// exactly the values htslib would hand the reference after widening.
+bool convert_gt(const VariantRecord &rec, int64_t n, int w_dst, int p_dst, uint8_t *dst) {
+    if (rec.ploidy > p_dst || rec.gt_width > w_dst) return false;
+    auto load = [&](int64_t j) -> int64_t {
+        if (rec.gt_width == 1) { int8_t v = ((const int8_t *)rec.gt)[j]; return v == INT8_MIN ? INT64_MIN : v == INT8_MIN + 1 ? INT64_MIN + 1 : v; }
+        if (rec.gt_width == 2) { int16_t v; memcpy(&v, rec.gt + 2 * j, 2); return v == INT16_MIN ? INT64_MIN : v == INT16_MIN + 1 ? INT64_MIN + 1 : v; }
+        int32_t v; memcpy(&v, rec.gt + 4 * j, 4); return v == INT32_MIN ? INT64_MIN : v == INT32_MIN + 1 ? INT64_MIN + 1 : v;
+    };
+    auto store = [&](int64_t j, int64_t v) {
+        if (w_dst == 1) ((int8_t *)dst)[j] = v == INT64_MIN ? INT8_MIN : v == INT64_MIN + 1 ? INT8_MIN + 1 : (int8_t)v;
+        else if (w_dst == 2) { int16_t t = v == INT64_MIN ? INT16_MIN : v == INT64_MIN + 1 ? INT16_MIN + 1 : (int16_t)v; memcpy(dst + 2 * j, &t, 2); }
+        else { int32_t t = v == INT64_MIN ? INT32_MIN : v == INT64_MIN + 1 ? INT32_MIN + 1 : (int32_t)v; memcpy(dst + 4 * j, &t, 4); }
+    };
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < p_dst; k++) store(i * p_dst + k, k < rec.ploidy ? load(i * rec.ploidy + k) : INT64_MIN + 1);
+    return true;
+}
+
+}  // namespace
+
+void compute_polygenic_scores(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals &cov,
+                              const ScoreParams &p, ScoreResult &out) {
+    const std::vector<ScoreEntry> &E = score.entries;
+    const int64_t nE = (int64_t)E.size(), n = vcf.n_samples();
+    out = ScoreResult();
+    out.samples = vcf.samples();
+
+    // ---- host-side classification that needs no genotypes ---------------------------------
+    std::vector<int32_t> kind(nE, PENDING), eaidx(nE, -1);
+    std::vector<int64_t> slab_row(nE, -1);
+    std::vector<std::string> filter_text(nE);
+    std::vector<uint8_t> contig_in_bed(nE, 1);
+    std::unordered_map<std::string, ContigIndex> index;
+    for (int64_t i = 0; i < nE; i++) {
+        if (p.use_cov) {                                            // :526, isVariantCovered :313-345
+            contig_in_bed[i] = cov.has_contig(E[i].contig);
+            if (!cov.covers(E[i])) { kind[i] = NPC_KIND_NOTCOV; continue; }   // the reference never looks these up
+        }
+        ContigIndex &ci = index[E[i].contig];
+        ci.by_pos.emplace_back(E[i].pos, i);
+        ci.max_reflen = std::max<int64_t>(ci.max_reflen, (int64_t)E[i].refseq.size());
+    }
+    int64_t n_lookup = 0;
+    for (auto &kv : index) { std::sort(kv.second.by_pos.begin(), kv.second.by_pos.end()); n_lookup += (int64_t)kv.second.by_pos.size(); }
+
+    // ---- GPU context: int8 diploid layout unless a matched record needs more --------------
+    // (the layout is fixed per context; a record that does not fit restarts the pass wider)
+    int gt_width = 1, ploidy = 2;
+    const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(4096, std::max<int64_t>(n_lookup, 1)));
+    Ctx ctx;
+    npc_policy pol = { p.imp_locus, p.imp_missing, p.imp_sample, 0, p.mincs, p.maxmis };
+
+    std::vector<int64_t> submitted;                 // entry index of every row sent to the GPU, in order
+    submitted.reserve(nE);
+    std::vector<npc_row> rows;
+    auto make_row = [&](int64_t i) {
+        npc_row r;
+        r.gt_row = kind[i] == NPC_KIND_GT ? (int32_t)slab_row[i] : -1;
+        r.eaidx = eaidx[i]; r.beta = E[i].beta; r.eaf = E[i].eaf;
+        r.ref_is_ea = E[i].ref_is_ea() ? 1 : 0; r.kind = kind[i];
+        return r;
+    };
+
+    ctx.ck(npc_create(&ctx.h, p.device, n, ploidy, gt_width, block_rows, 3), "npc_create");
+    ctx.ck(npc_set_policy(ctx.h, &pol), "npc_set_policy");
+    ctx.ck(npc_reset(ctx.h), "npc_reset");
+    int64_t slab_cap = 0;
+    ctx.ck(npc_resident_reserve(ctx.h, std::max<int64_t>(n_lookup, 1), &slab_cap), "npc_resident_reserve");
+
+    // staging state
+    int32_t slot = -1; uint8_t *stage = nullptr; int64_t stride = 0, staged = 0, slab_used = 0, slab_base = 0;
+    auto flush_stage = [&]() {
+        if (slot < 0) return;
+        ctx.ck(npc_stage_upload(ctx.h, slot, staged, slab_base), "npc_stage_upload");
+        slab_base += staged; staged = 0; slot = -1;
+    };
+    // next score-file index not yet submitted: rows are submitted strictly in score-file order
+    int64_t next_submit = 0;
+    auto score_round = [&](bool final_round) {
+        // Submit, in score-file order, the longest prefix of entries that is settled; on the final
+        // round everything is settled.  With one round (the normal case: all matched rows fit the
+        // slab) this is exactly the reference's loop order.
+        flush_stage();
+        rows.clear();
+        while (next_submit < nE && (final_round || kind[next_submit] != PENDING)) {
+            if (kind[next_submit] == PENDING) kind[next_submit] = NPC_KIND_ABSENT;
+            rows.push_back(make_row(next_submit));
+            submitted.push_back(next_submit);
+            next_submit++;
+        }
+        if (!rows.empty()) ctx.ck(npc_score_resident(ctx.h, rows.data(), (int64_t)rows.size()), "npc_score_resident");
+        out.rounds++;
+    };
+
+    // ---- one streaming pass over the genotype file (findVariant :353-364, eaidx :375-379) ---
+    VariantRecord rec;
+    std::vector<int64_t> hits;
+    while (vcf.next(rec)) {
+        out.records_read++;
+        auto it = index.find(*rec.contig);
+        if (it == index.end()) continue;
+        const ContigIndex &ci = it->second;
+        // entries overlapping [rec.pos, rec.end()]: entry.pos <= rec.end and entry.stop >= rec.pos
+        auto lo = std::lower_bound(ci.by_pos.begin(), ci.by_pos.end(), std::make_pair(rec.pos - ci.max_reflen + 1, (int64_t)-1));
+        hits.clear();
+        for (auto q = lo; q != ci.by_pos.end() && q->first <= rec.end(); ++q) {
+            const int64_t i = q->second;
+            if (kind[i] != PENDING) continue;                       // an earlier record already matched: first one wins
+            const ScoreEntry &e = E[i];
+            if (e.stop() < rec.pos || rec.ref != e.refseq) continue;
+            int ea = -1;
+            if (e.easeq == e.refseq) ea = 0;
+            else for (size_t a = 0; a < rec.alts.size(); a++) if (rec.alts[a] == e.easeq) { ea = (int)a + 1; break; }
+            if (ea < 0) continue;
+            eaidx[i] = ea;
+            hits.push_back(i);
+        }
+        if (hits.empty()) continue;
+        out.records_matched++;
+        bool need_gt = false;
+        for (int64_t i : hits) {
+            const bool filt = !p.ignorefilt && rec.filter != "." && rec.filter != "PASS";      // :553
+            kind[i] = filt ? NPC_KIND_FILTER : NPC_KIND_GT;
+            if (filt) filter_text[i] = rec.filter; else need_gt = true;
+        }
+        if (!need_gt) continue;
+        if (!rec.has_gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
+        if (rec.ploidy > ploidy || rec.gt_width > gt_width)
+            throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " needs GT layout width " +
+                             std::to_string(rec.gt_width) + " ploidy " + std::to_string(rec.ploidy) +
+                             " (this build streams int8 diploid rows)");
+        if (slab_base + staged >= slab_cap) {                       // slab full: score what is settled, start over
+            score_round(false);
+            slab_base = 0;
+        }
+        if (slot < 0) { void *ptr; ctx.ck(npc_stage_acquire(ctx.h, &slot, &ptr, &stride), "npc_stage_acquire"); stage = (uint8_t *)ptr; staged = 0; }
+        uint8_t *dst = stage + staged * stride;
+        if (rec.gt_width == gt_width && rec.ploidy == ploidy) memcpy(dst, rec.gt, (size_t)n * ploidy * gt_width);
+        else convert_gt(rec, n, gt_width, ploidy, dst);
+        for (int64_t i : hits) if (kind[i] == NPC_KIND_GT) slab_row[i] = slab_base + staged;
+        staged++;
+        if (staged == block_rows) flush_stage();
+        (void)slab_used;
+    }
+    score_round(true);
+
+    // ---- results ------------------------------------------------------------------------------
+    out.scores.assign(n, 0.0);
+    std::vector<npc_locus> log(submitted.size());
+    int64_t nlog = 0;
+    ctx.ck(npc_finish(ctx.h, score.offset, out.scores.data(), &out.nloci, log.data(), (int64_t)log.size(), &nlog), "npc_finish");
+    if (nlog != (int64_t)submitted.size()) throw std::runtime_error("locus log length mismatch");
+    out.loci.assign(nE, npc_locus());
+    for (size_t k = 0; k < submitted.size(); k++) out.loci[submitted[k]] = log[k];
+
+    // ---- WARN lines, in the reference's order (:326, :527-530, :538-541, :554-557, :567-570, :575-579)
+    std::string &w = out.warnings;
+    for (int64_t i = 0; i < nE; i++) {
+        const ScoreEntry &e = E[i];
+        const npc_locus &L = out.loci[i];
+        const std::string id = e.contig + ":" + std::to_string(e.pos) + ":" + e.refseq + ":" + e.easeq;
+        const std::string span = e.contig + ":" + std::to_string(e.pos) + "-" + std::to_string(e.stop());
+        if (L.klass == NPC_KIND_NOTCOV) {
+            if (!contig_in_bed[i]) w += "WARN Contig " + e.contig + " not present within the coverage BED file.\n";
+            w += "WARN Locus " + span + " is not covered by the sequence coverage BED.  Imputing all dosages at this locus.\n";
+        } else if (L.klass == NPC_KIND_ABSENT) {
+            if (!std::isnan(e.eaf) && binom_test(0, n * 2, e.eaf) < p.afmisp)
+                w += "WARN Variant " + id + " cohort EAF is 0 in " + std::to_string(n) + " samples.  This is highly unlikely given polygenic score EAF of " +
+                     format_float_nim(e.eaf) + "\n";
+        } else if (L.klass == NPC_KIND_FILTER) {
+            w += "WARN Variant " + id + " has a FILTER flag set (value \"" + filter_text[i] + "\").  Imputing all dosages at this locus.\n";
+        } else if (L.klass == NPC_CLASS_MAXMIS) {
+            const double missingrate = (double)L.nmiss / (double)n;
+            w += "WARN Locus " + span + " has " + format_float_nim(missingrate * 100) +
+                 "% of samples missing a genotype. This exceeds the missingness threshold; imputing all dosages at this locus.\n";
+        } else if (!std::isnan(e.eaf) && binom_test(L.neff, (n - L.nmiss) * 2, e.eaf) < p.afmisp) {
+            w += "WARN Variant " + id + " cohort EAF is " + format_float_nim((double)L.neff / (double)((n - L.nmiss) * 2)) + " in " +
+                 std::to_string(n) + " samples.  This is highly unlikely given polygenic score EAF of " + format_float_nim(e.eaf) + "\n";
+        }
+    }
+}
+
+}  // namespace nph

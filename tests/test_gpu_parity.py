@@ -261,9 +261,9 @@ def test_config2_shape_wood_100k(nb):
     assert_parity(run_engine(nb, gt, n, rows, offset=offset, staged=False), oracle(gt, n, rows, offset=offset))
 
 
-@pytest.mark.parametrize("env", [dict(NPC_FUSED="0"), dict(NPC_FUSED_R="1", NPC_FUSED_S="3", NPC_FUSED_L="1", NPC_FUSED_A="1"),
-                                 dict(NPC_FUSED_R="8", NPC_FUSED_S="5", NPC_FUSED_L="3"), dict(NPC_FUSED_K="2"),
-                                 dict(NPC_FUSED_K="2", NPC_FUSED_R="3", NPC_FUSED_A="5"), dict(NPC_FUSED_R="4", NPC_FUSED_L="1")],
+@pytest.mark.parametrize("env", [dict(NPC_FUSED="0"), dict(NPC_FUSED_R="1", NPC_FUSED_SR="2", NPC_FUSED_SC="2", NPC_FUSED_A="1"),
+                                 dict(NPC_FUSED_R="8", NPC_FUSED_SR="3", NPC_FUSED_SC="5", NPC_FUSED_L="3"), dict(NPC_FUSED_K="2"),
+                                 dict(NPC_FUSED_K="2", NPC_FUSED_R="3", NPC_FUSED_A="6"), dict(NPC_FUSED_R="4", NPC_FUSED_L="1")],
                          ids=lambda e: ",".join(f"{k[4:]}={v}" for k, v in e.items()))
 def test_kernel_paths_agree(nb, env, monkeypatch):
     """The fused persistent kernel under several ring shapes and the two-kernel sequence all give
