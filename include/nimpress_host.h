@@ -1,0 +1,88 @@
+/*
+ * nimpress_host.h -- C ABI of libnimpress_host.so: the C++ host of the B200 scoring engine.
+ *
+ * The reference's host language is Nim, which this build environment does not have; the host
+ * is therefore C++ and mirrors the reference's own entry points:
+ *
+ *   nph_compute_polygenic_scores  <->  computePolygenicScores  (src/nimpress.nim:592-649) after
+ *                                      open(VCF) / open(ScoreFile) / loadBedIntervals
+ *                                      (:233-244, :278-308), as tests/test_set1.nim:37-44 calls it
+ *   nph_main                      <->  main()                  (src/nimpress.nim:652-753)
+ *   nph_plan                      <->  the genotype-free half of getImputedDosages: coverage
+ *                                      (:526), findVariant (:353-364), eaidx (:375-379), the
+ *                                      FILTER test (:553) -- CPU only, for tests
+ *   nph_binom_test ...            <->  binomTest / dbinom / pbinom / betai (:54-188)
+ *
+ * Everything genotype-shaped goes through libnimpress_cuda.so (include/nimpress_cuda.h); this
+ * library never computes a score on the CPU.
+ */
+#ifndef NIMPRESS_HOST_H
+#define NIMPRESS_HOST_H
+#include <stdint.h>
+
+#include "nimpress_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPH_OK          0
+#define NPH_EOPEN_VCF  -1   /* reference: "FATAL Could not open input VCF file", quit(-1)            */
+#define NPH_EOPEN_SCORE -2  /* reference: "FATAL Could not open polygenic score file", quit(-1)      */
+#define NPH_EINPUT     -3   /* malformed input: the reference's doAssert / ValueError paths (exit 1) */
+#define NPH_ECAPACITY  -4   /* caller buffer too small                                               */
+#define NPH_EGPU       -5   /* CUDA library / device failure                                          */
+
+typedef struct {
+    int32_t imp_locus;      /* NPC_LOCUS_*   */
+    int32_t imp_missing;    /* NPC_MISSING_* */
+    int32_t imp_sample;     /* NPC_SAMPLE_*  */
+    int32_t ignorefilt;
+    int32_t use_cov;        /* restrictToCoveredRgns */
+    int32_t device;
+    int64_t mincs;
+    double  maxmis;
+    double  afmisp;
+} nph_params;
+
+typedef struct nph_result nph_result;
+
+/* Scores every sample of genotype_path (VCF text or BCF; plain, gzip or BGZF) against
+ * score_path; bed_path may be NULL.  On NPH_OK *out owns the result. */
+int nph_compute_polygenic_scores(const char *score_path, const char *genotype_path, const char *bed_path,
+                                 const nph_params *p, nph_result **out);
+int64_t nph_result_n_samples(const nph_result *r);
+int64_t nph_result_n_loci(const nph_result *r);          /* score rows                      */
+int64_t nph_result_nloci_used(const nph_result *r);      /* loci in the sum (the divisor/2) */
+int64_t nph_result_rounds(const nph_result *r);          /* 1 = exact reference summation order */
+const double *nph_result_scores(const nph_result *r);
+const npc_locus *nph_result_loci(const nph_result *r);   /* score-file order */
+const char *nph_result_sample(const nph_result *r, int64_t i);
+const char *nph_result_warnings(const nph_result *r);    /* "WARN ...\n" lines, reference order */
+void nph_result_free(nph_result *r);
+const char *nph_last_error(void);
+
+/* CPU only: per score row kind (NPC_KIND_*) and eaidx after coverage / lookup / FILTER. */
+int nph_plan(const char *score_path, const char *genotype_path, const char *bed_path, const nph_params *p,
+             int32_t *kind_out, int32_t *eaidx_out, int64_t cap, int64_t *n_rows_out, int64_t *n_samples_out);
+
+/* CPU only: raw GT payload of every record of a VCF/BCF, for reader tests.  Record r occupies
+ * out[r*row_bytes ..]; returns the record count, width and ploidy of the LAST record read. */
+int nph_read_gt(const char *genotype_path, uint8_t *out, int64_t row_bytes, int64_t max_records,
+                int64_t *n_records, int64_t *n_samples, int32_t *width, int32_t *ploidy);
+
+double nph_dbinom(int64_t x, int64_t n, double p);
+double nph_pbinom(int64_t x, int64_t n, double p);
+double nph_betai(double a, double b, double x);
+double nph_binom_test(int64_t x, int64_t n, double p);
+int nph_format_float(double v, char *buf, int32_t buflen);   /* Nim `$`(float), the output format */
+
+/* The command line of the reference: nimpress [options] <scoredef> <genotypes.vcf>; prints the
+ * reference's WARN lines and `sample<TAB>score` lines to stdout; returns the process exit code
+ * (0, 1 on malformed input / bad option, 255 when a file cannot be opened). */
+int nph_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -113,11 +113,11 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     if (nc > 16) return NPC_OK;                       // cohort too wide for one resident pass: two-kernel path
     c->f_K = K; c->f_nc = (int)nc; c->f_slab = (int)(nc * 32 * K * 16);
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
-    int R = env_int("NPC_FUSED_R", 2), Sr = env_int("NPC_FUSED_SR", 0), Sc = env_int("NPC_FUSED_SC", 0);
+    int R = env_int("NPC_FUSED_R", 4), Sr = env_int("NPC_FUSED_SR", 0), Sc = env_int("NPC_FUSED_SC", 0);
     int L = env_int("NPC_FUSED_L", 0), A = env_int("NPC_FUSED_A", 4);
-    if (!fused_kernel(K, R)) R = 2;
+    if (!fused_kernel(K, R)) R = 4;
     // raw ring: about 70 KB of loads in flight per SM (HBM latency x per-SM bandwidth, with margin)
-    if (Sr <= 0) Sr = std::max(2, std::min(16, (72 * 1024) / (R * c->f_slab)));
+    if (Sr <= 0) Sr = std::max(2, std::min(16, (80 * 1024) / (R * c->f_slab)));
     if (Sc <= 0) {
         Sc = 64;
         while (Sc > 2 && (int)FusedSmem::make(R, Sr, Sc, c->f_slab).total > max_smem) Sc--;

@@ -50,7 +50,7 @@ constexpr ull FUSED_CNT_MASK = (1ull << FUSED_CNT_BITS) - 1;
 // The tally table of a row depends only on T = eaidx+1.  Fast-path codes are alleles REF..ALT6
 // (T <= 7); for T >= 8 no fast-path code can match, so table 8 serves every larger T.
 constexpr uint32_t FUSED_CNT_TABLES = 8;
-constexpr uint32_t FUSED_CNT_STRIDE = 80;      // bytes per tally table (68 one-byte entries, padded)
+constexpr uint32_t FUSED_CNT_STRIDE = 256;     // one-byte entries; a PRMT forms (index byte | table << 8)
 
 // ---- PTX helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,11 +68,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware, do not spin
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier; the slab is read
 // once, so it is marked evict-first in L2.
@@ -137,16 +137,17 @@ __device__ __forceinline__ uint32_t slow_idx(uint32_t h, int eaidx) {
 
 // shared-memory carve-up (byte offsets from the dynamic smem base)
 struct FusedSmem {
-    uint32_t bars, cntacc, mode, risgt, reaidx, cnt, lut, idx, data, total;
+    uint32_t bars, cntacc, mode, cisgt, risgt, reaidx, cnt, lut, idx, data, total;
     __host__ __device__ static FusedSmem make(int R, int Sr, int Sc, int slab_stride) {
         FusedSmem m;
         uint32_t o = 0;
+        m.cnt = o;    o += FUSED_CNT_TABLES * FUSED_CNT_STRIDE;                            // first: 256-byte aligned tables
         m.bars = o;   o += (2u * Sr + 2u * Sc) * 8u;             o = (o + 127u) & ~127u;  // full, r_empty | cnt_done, lut_ready
-        m.cntacc = o; o += (uint32_t)Sc * R * 4u;                o = (o + 127u) & ~127u;
+        m.cntacc = o; o += (uint32_t)Sc * R * 16u * 4u;          o = (o + 127u) & ~127u;  // [slot][row][consumer warp]
         m.mode = o;   o += (uint32_t)Sc * R * 4u;                o = (o + 127u) & ~127u;
-        m.risgt = o;  o += (uint32_t)Sr * R * 4u;                o = (o + 127u) & ~127u;
+        m.cisgt = o;  o += (uint32_t)Sc * 4u;                    o = (o + 127u) & ~127u;  // per index slot: mask of rows with genotypes
+        m.risgt = o;  o += (uint32_t)Sr * 4u;                    o = (o + 127u) & ~127u;  // per raw stage: same mask
         m.reaidx = o; o += (uint32_t)Sr * R * 4u;                o = (o + 127u) & ~127u;
-        m.cnt = o;    o += FUSED_CNT_TABLES * FUSED_CNT_STRIDE;  o = (o + 127u) & ~127u;
         m.lut = o;    o += (uint32_t)Sc * R * LUT_N * 8u;        o = (o + 127u) & ~127u;
         m.idx = o;    o += (uint32_t)Sc * R * (uint32_t)(slab_stride / 2); o = (o + 127u) & ~127u;
         m.data = o;   o += (uint32_t)Sr * R * (uint32_t)slab_stride;
@@ -159,14 +160,15 @@ struct FusedSmem {
 template <int K, int R>
 __global__ void __launch_bounds__(768, 1)      // <= 16 consumer warps + producer + publisher + <= 6 deciders
 k_fused_i8x2(const FusedParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int Sr = P.Sr, Sc = P.Sc, L = P.L, NC = P.nc, A = P.A;
     const FusedSmem M = FusedSmem::make(R, Sr, Sc, P.slab_stride);
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar_full = sb + M.bars, bar_rempty = bar_full + 8u * Sr, bar_cnt = bar_rempty + 8u * Sr, bar_lut = bar_cnt + 8u * Sc;
     uint32_t *s_cntacc = reinterpret_cast<uint32_t *>(smem + M.cntacc);
     int32_t *s_mode = reinterpret_cast<int32_t *>(smem + M.mode);
-    int32_t *s_risgt = reinterpret_cast<int32_t *>(smem + M.risgt);
+    uint32_t *s_risgt = reinterpret_cast<uint32_t *>(smem + M.risgt);
+    uint32_t *s_cisgt = reinterpret_cast<uint32_t *>(smem + M.cisgt);
     int32_t *s_reaidx = reinterpret_cast<int32_t *>(smem + M.reaidx);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,7 +186,6 @@ k_fused_i8x2(const FusedParams P) {
         for (int s = 0; s < Sc; s++) { mbar_init(bar_cnt + 8u * s, NC); mbar_init(bar_lut + 8u * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < Sc * R; i += blockDim.x) s_cntacc[i] = 0;
     for (int i = threadIdx.x; i < (int)FUSED_CNT_TABLES * LUT_N; i += blockDim.x) {
         const int c = lut_code(i % LUT_N, i / LUT_N + 1);                  // entry = d | missing << 5
         smem[M.cnt + (i / LUT_N) * FUSED_CNT_STRIDE + (i % LUT_N)] = (uint8_t)(c == 3 ? 32 : c);
@@ -209,8 +210,10 @@ k_fused_i8x2(const FusedParams P) {
                 row = P.rows[t * R + lane];
                 is_gt = row.kind == NPC_KIND_GT && row.gt_row >= 0;
             }
-            if (lane < R) { s_risgt[s * R + lane] = is_gt ? 1 : 0; s_reaidx[s * R + lane] = is_gt ? row.eaidx : 0; }
-            const uint32_t n_gt = __popc(__ballot_sync(0xffffffffu, is_gt));
+            if (lane < R) s_reaidx[s * R + lane] = is_gt ? row.eaidx : 0;
+            const uint32_t gt_mask = __ballot_sync(0xffffffffu, is_gt);
+            const uint32_t n_gt = __popc(gt_mask);
+            if (lane == 0) s_risgt[s] = gt_mask;
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(bar_full + 8u * s, n_gt * slab_bytes);   // releases the kind writes too
             __syncwarp();
@@ -226,9 +229,13 @@ k_fused_i8x2(const FusedParams P) {
             mbar_wait(bar_cnt + 8u * s, ph);
             const int nr = (int)min((int64_t)R, P.n_rows - t * R);
             if (lane < nr) {
-                const uint32_t v = s_cntacc[s * R + lane];
-                s_cntacc[s * R + lane] = 0;
-                red_relaxed_gpu_add_u64(P.counts + t * R + lane, (1ull << 56) | ((ull)(v >> 16) << FUSED_CNT_BITS) | (ull)(v & 0xFFFFu));
+                ull miss = 0, eff = 0;
+                if ((s_cisgt[s] >> lane) & 1u)                            // row has genotypes: every consumer warp left a partial
+                    for (int w = 0; w < NC; w++) {
+                        const uint32_t v = s_cntacc[(s * R + lane) * 16 + w];
+                        miss += v >> 16; eff += v & 0xFFFFu;
+                    }
+                red_relaxed_gpu_add_u64(P.counts + t * R + lane, (1ull << 56) | (miss << FUSED_CNT_BITS) | eff);
             }
             if (++s == Sc) { s = 0; ph ^= 1u; }
         }
@@ -294,18 +301,23 @@ k_fused_i8x2(const FusedParams P) {
             }
         }
         const uint32_t slab = (uint32_t)P.slab_stride, islab = slab >> 1;
+        const uint32_t cnt0 = sb + M.cnt;
+        const int nt = (int)n_tiles;
         int sr = 0, sc = 0, sa = 0;            // ring positions: raw stage, index slot being counted / accumulated
         uint32_t ph_r = 0, ph_a = 0;
-        for (int64_t i = 0; i < n_tiles + L; i++) {
-            if (i < n_tiles) {
+        for (int i = 0; i < nt + L; i++) {
+            if (i < nt) {
                 mbar_wait(bar_full + 8u * sr, ph_r);
+                const uint32_t gt_mask = s_risgt[sr];
                 const uint32_t d0 = sb + M.data + (uint32_t)(sr * R) * slab;
                 const uint32_t x0 = sb + M.idx + (uint32_t)(sc * R) * islab;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    if (!s_risgt[sr * R + r]) continue;
+                    if (!((gt_mask >> r) & 1u)) continue;
                     const int ea = s_reaidx[sr * R + r];
-                    const uint32_t cnt = sb + M.cnt + (uint32_t)min(ea, (int)FUSED_CNT_TABLES - 1) * FUSED_CNT_STRIDE;
+                    // bits 8.. of the row's tally-table address (tables are 256-byte aligned): one PRMT then
+                    // forms the complete address, table bytes above the index byte -- no add
+                    const uint32_t thi = (cnt0 >> 8) + (uint32_t)min(ea, (int)FUSED_CNT_TABLES - 1);
                     uint32_t tally = 0;                          // low half: effect alleles, high half: missing samples
 #pragma unroll
                     for (int k = 0; k < K; k++) {
@@ -324,16 +336,17 @@ k_fused_i8x2(const FusedParams P) {
                             i0 = b[0] | (b[2] << 8) | (b[1] << 16) | (b[3] << 24);
                             i1 = b[4] | (b[6] << 8) | (b[5] << 16) | (b[7] << 24);
                         }
+                        sts_v2(x0 + r * islab + cell[k] * 8u, i0, i1);
                         uint32_t t = 0;
 #pragma unroll
                         for (int e = 0; e < 4; e++)
-                            t += lds_u8(cnt + __byte_perm(i0, 0, 0x4440 + e)) + lds_u8(cnt + __byte_perm(i1, 0, 0x4440 + e));
+                            t += lds_u8(__byte_perm(i0, thi, 0x6540 + e)) + lds_u8(__byte_perm(i1, thi, 0x6540 + e));
                         tally += ((t & 31u) | ((t >> 5) << 16)) & own[k];
-                        sts_v2(x0 + r * islab + cell[k] * 8u, i0, i1);
                     }
                     tally = __reduce_add_sync(0xffffffffu, tally);
-                    if (lane == 0) red_shared_add_u32(smem_u32(&s_cntacc[sc * R + r]), tally);
+                    if (lane == 0) s_cntacc[(sc * R + r) * 16 + warp] = tally;     // per-warp partial, summed by the publisher
                 }
+                if (warp == 0 && lane == 0) s_cisgt[sc] = gt_mask;
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bar_rempty + 8u * sr); mbar_arrive(bar_cnt + 8u * sc); }
                 if (++sr == Sr) { sr = 0; ph_r ^= 1u; }

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/nimpress_cuda.h"
@@ -35,8 +36,35 @@ struct ScoreResult {
     int64_t records_read = 0, records_matched = 0, rounds = 0;
 };
 
+// Host-side part of getImputedDosages that needs no genotypes: coverage (:526), the streaming
+// equivalent of findVariant (:353-364: first record in file order overlapping contig:pos-stop with
+// REF == refseq and the effect allele equal to REF or present in ALT), eaidx (:375-379) and the
+// FILTER test (:553).  Pure CPU: unit-tested without a GPU.
+class Matcher {
+public:
+    Matcher(const ScoreFile &score, const GenomeIntervals &cov, const ScoreParams &p);
+    // entries settled by this record (their kind / eaidx / filter text are set); empty if none
+    const std::vector<int64_t> &match(const VariantRecord &rec);
+    void finish();                                  // everything still pending is ABSENT (:536)
+    bool has_contig(const std::string &c) const { return index_.count(c) != 0; }
+    int64_t n_lookup() const { return n_lookup_; }
+
+    static constexpr int32_t PENDING = -1;
+    std::vector<int32_t> kind, eaidx;               // per score entry; kind is NPC_KIND_* or PENDING
+    std::vector<std::string> filter_text;           // FILTER string of the matched record (FILTER rows)
+    std::vector<uint8_t> contig_in_bed;
+private:
+    struct ContigIndex { std::vector<std::pair<int64_t, int64_t>> by_pos; int64_t max_reflen = 1; };
+    const std::vector<ScoreEntry> &E_;
+    bool ignorefilt_;
+    std::unordered_map<std::string, ContigIndex> index_;
+    std::vector<int64_t> hits_;
+    int64_t n_lookup_ = 0;
+};
+
 // Throws InputError where the reference raises; std::runtime_error on CUDA / library failure.
-void compute_polygenic_scores(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals &cov,
+// false: the genotype file cannot be opened (the reference: FATAL + quit(-1), :728-730).
+bool compute_polygenic_scores(const ScoreFile &score, const std::string &genotype_path, const GenomeIntervals &cov,
                               const ScoreParams &p, ScoreResult &out);
 
 }  // namespace nph

@@ -1,0 +1,228 @@
+// host_api.cpp -- C ABI of libnimpress_host.so (include/nimpress_host.h) and the command line.
+#include <cstring>
+#include <iostream>
+#include <string>
+
+#include "../../include/nimpress_host.h"
+#include "driver.hpp"
+#include "stats.hpp"
+
+using namespace nph;
+
+struct nph_result { ScoreResult r; };
+
+static thread_local std::string g_err;
+
+const char *nph_last_error(void) { return g_err.c_str(); }
+
+static ScoreParams to_params(const nph_params *p) {
+    ScoreParams q;
+    q.imp_locus = p->imp_locus; q.imp_missing = p->imp_missing; q.imp_sample = p->imp_sample;
+    q.ignorefilt = p->ignorefilt != 0; q.use_cov = p->use_cov != 0; q.device = p->device;
+    q.mincs = p->mincs; q.maxmis = p->maxmis; q.afmisp = p->afmisp;
+    return q;
+}
+
+// open(ScoreFile) + loadBedIntervals as main() sequences them (:728-740)
+static int load_inputs(const char *score_path, const char *bed_path, ScoreParams &q, ScoreFile &sf, GenomeIntervals &cov,
+                       std::string *fatal) {
+    if (!sf.load(score_path)) return NPH_EOPEN_SCORE;
+    if (q.use_cov && bed_path) {
+        if (!cov.load(bed_path) && fatal)            // the reference logs FATAL but carries on (:739-740)
+            *fatal += std::string("FATAL Could not open coverage BED file ") + bed_path + "\n";
+    }
+    return NPH_OK;
+}
+
+int nph_compute_polygenic_scores(const char *score_path, const char *genotype_path, const char *bed_path,
+                                 const nph_params *p, nph_result **out) {
+    if (!score_path || !genotype_path || !p || !out) return NPH_EINPUT;
+    *out = nullptr;
+    try {
+        ScoreParams q = to_params(p);
+        {   // main() opens the VCF first (:728): an unreadable VCF wins over an unreadable score file
+            std::unique_ptr<VariantSource> probe = open_variant_source(genotype_path);
+            if (!probe) { g_err = std::string("Could not open input VCF file ") + genotype_path; return NPH_EOPEN_VCF; }
+        }
+        ScoreFile sf; GenomeIntervals cov;
+        std::string fatal;
+        int rc = load_inputs(score_path, bed_path, q, sf, cov, &fatal);
+        if (rc) { g_err = std::string("Could not open polygenic score file ") + score_path; return rc; }
+        nph_result *res = new nph_result();
+        if (!compute_polygenic_scores(sf, genotype_path, cov, q, res->r)) {
+            delete res;
+            g_err = std::string("Could not open input VCF file ") + genotype_path;
+            return NPH_EOPEN_VCF;
+        }
+        res->r.warnings = fatal + res->r.warnings;
+        *out = res;
+        return NPH_OK;
+    } catch (const InputError &e) {
+        g_err = e.what();
+        return NPH_EINPUT;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return NPH_EGPU;
+    }
+}
+
+int64_t nph_result_n_samples(const nph_result *r) { return (int64_t)r->r.scores.size(); }
+int64_t nph_result_n_loci(const nph_result *r) { return (int64_t)r->r.loci.size(); }
+int64_t nph_result_nloci_used(const nph_result *r) { return r->r.nloci; }
+int64_t nph_result_rounds(const nph_result *r) { return r->r.rounds; }
+const double *nph_result_scores(const nph_result *r) { return r->r.scores.data(); }
+const npc_locus *nph_result_loci(const nph_result *r) { return r->r.loci.data(); }
+const char *nph_result_sample(const nph_result *r, int64_t i) { return r->r.samples[(size_t)i].c_str(); }
+const char *nph_result_warnings(const nph_result *r) { return r->r.warnings.c_str(); }
+void nph_result_free(nph_result *r) { delete r; }
+
+int nph_plan(const char *score_path, const char *genotype_path, const char *bed_path, const nph_params *p,
+             int32_t *kind_out, int32_t *eaidx_out, int64_t cap, int64_t *n_rows_out, int64_t *n_samples_out) {
+    try {
+        ScoreParams q = to_params(p);
+        std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path);
+        if (!vcf) return NPH_EOPEN_VCF;
+        ScoreFile sf; GenomeIntervals cov;
+        int rc = load_inputs(score_path, bed_path, q, sf, cov, nullptr);
+        if (rc) return rc;
+        if ((int64_t)sf.entries.size() > cap) return NPH_ECAPACITY;
+        Matcher M(sf, cov, q);
+        VariantRecord rec;
+        while (vcf->next(rec)) M.match(rec);
+        M.finish();
+        for (size_t i = 0; i < sf.entries.size(); i++) { kind_out[i] = M.kind[i]; eaidx_out[i] = M.eaidx[i]; }
+        *n_rows_out = (int64_t)sf.entries.size();
+        *n_samples_out = vcf->n_samples();
+        return NPH_OK;
+    } catch (const InputError &e) {
+        g_err = e.what();
+        return NPH_EINPUT;
+    }
+}
+
+int nph_read_gt(const char *genotype_path, uint8_t *out, int64_t row_bytes, int64_t max_records, int64_t *n_records,
+                int64_t *n_samples, int32_t *width, int32_t *ploidy) {
+    try {
+        std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path);
+        if (!vcf) return NPH_EOPEN_VCF;
+        VariantRecord rec;
+        int64_t k = 0;
+        *n_samples = vcf->n_samples();
+        while (vcf->next(rec)) {
+            if (k >= max_records) return NPH_ECAPACITY;
+            if (rec.has_gt) {
+                const int64_t bytes = vcf->n_samples() * rec.ploidy * rec.gt_width;
+                if (bytes > row_bytes) return NPH_ECAPACITY;
+                memcpy(out + k * row_bytes, rec.gt, (size_t)bytes);
+                *width = rec.gt_width; *ploidy = rec.ploidy;
+            }
+            k++;
+        }
+        *n_records = k;
+        return NPH_OK;
+    } catch (const InputError &e) {
+        g_err = e.what();
+        return NPH_EINPUT;
+    }
+}
+
+double nph_dbinom(int64_t x, int64_t n, double p) { return dbinom(x, n, p); }
+double nph_pbinom(int64_t x, int64_t n, double p) { return pbinom(x, n, p); }
+double nph_betai(double a, double b, double x) { return betai(a, b, x); }
+double nph_binom_test(int64_t x, int64_t n, double p) { return binom_test(x, n, p); }
+
+int nph_format_float(double v, char *buf, int32_t buflen) {
+    std::string s = format_float_nim(v);
+    if ((int32_t)s.size() + 1 > buflen) return -1;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+// ------------------------------------------------------------------------------------------
+// command line -- main() of the reference (src/nimpress.nim:652-753), docopt usage text :653-706
+// ------------------------------------------------------------------------------------------
+
+static const char *USAGE =
+    "Compute polygenic scores from a VCF/BCF.\n\n"
+    "Usage:\n"
+    "  nimpress [options] <scoredef> <genotypes.vcf>\n"
+    "  nimpress (-h | --help)\n"
+    "  nimpress --version\n\n"
+    "Options:\n"
+    "  -h --help          Show this screen.\n"
+    "  --version          Show version.\n"
+    "  --cov=<path>       Path to a BED file supplying genome regions that have been\n"
+    "                     genotyped in the genotypes.vcf file.\n"
+    "  --imp-locus=<m>    Imputation to apply for whole loci which are either not\n"
+    "                     in the sequenced BED regions, or fail (too many samples\n"
+    "                     with missing genotype, as set by --maxmis, or a FILTER field\n"
+    "                     other than \".\" / \"PASS\" if --ignorefilt is not set). Valid\n"
+    "                     values are ps, homref, fail, ignore [default: ps].\n"
+    "  --imp-missing=<m>  Imputation to apply for loci which are in the sequenced BED\n"
+    "                     regions (and thus should have been genotyped), but are\n"
+    "                     completely missing from the VCF. Valid values are homref,\n"
+    "                     ignore [default: homref].\n"
+    "  --imp-sample=<m>   Imputation to apply for an individual sample with missing\n"
+    "                     genotype. Valid values are ps, homref, fail, int_fail,\n"
+    "                     int_ps [default: int_ps].\n"
+    "  --maxmis=<f>       Maximum fraction of samples with missing genotypes allowed\n"
+    "                     at a locus [default: 0.05].\n"
+    "  --mincs=<n>        Minimum number of genotyped samples at a locus for internal\n"
+    "                     imputation [default: 100].\n"
+    "  --afmisp=<f>       p-value threshold for warning about allele frequency\n"
+    "                     mismatch [default: 0.001].\n"
+    "  --ignorefilt       Ignore the VCF FILTER field.\n"
+    "  --device=<n>       CUDA device to score on [default: 0] (not a reference option).\n";
+
+static int parse_enum(const std::string &v, std::initializer_list<const char *> names) {   // Nim parseEnum: style-insensitive beyond the first char is not reproduced
+    int i = 0;
+    for (const char *nm : names) { if (v == nm) return i; i++; }
+    throw InputError("invalid enum value: " + v);
+}
+
+int nph_main(int argc, char **argv) {
+    nph_params p = { NPC_LOCUS_PS, NPC_MISSING_HOMREF, NPC_SAMPLE_INT_PS, 0, 0, 0, 100, 0.05, 0.001 };
+    std::string cov, pos[2];
+    int npos = 0;
+    try {
+        for (int i = 1; i < argc; i++) {
+            std::string a = argv[i];
+            auto val = [&](const char *opt) -> std::string {      // --opt=value or --opt value
+                const size_t l = strlen(opt);
+                if (a.size() > l && a[l] == '=') return a.substr(l + 1);
+                if (i + 1 >= argc) throw InputError(std::string(opt) + " requires an argument");
+                return argv[++i];
+            };
+            auto is = [&](const char *opt) { const size_t l = strlen(opt); return a.compare(0, l, opt) == 0 && (a.size() == l || a[l] == '='); };
+            if (a == "-h" || a == "--help") { std::cout << USAGE; return 0; }
+            else if (a == "--version") { std::cout << "nimpress 1.0.0\n"; return 0; }        // :708
+            else if (is("--cov")) { cov = val("--cov"); p.use_cov = 1; }
+            else if (is("--imp-locus")) p.imp_locus = parse_enum(val("--imp-locus"), { "ps", "homref", "fail", "ignore" });
+            else if (is("--imp-missing")) p.imp_missing = parse_enum(val("--imp-missing"), { "homref", "ignore" });
+            else if (is("--imp-sample")) p.imp_sample = parse_enum(val("--imp-sample"), { "ps", "homref", "fail", "int_ps", "int_fail" });
+            else if (is("--maxmis")) p.maxmis = parse_float_nim(val("--maxmis"), "--maxmis");
+            else if (is("--mincs")) p.mincs = parse_int_nim(val("--mincs"), "--mincs");
+            else if (is("--afmisp")) p.afmisp = parse_float_nim(val("--afmisp"), "--afmisp");
+            else if (is("--device")) p.device = (int)parse_int_nim(val("--device"), "--device");
+            else if (a == "--ignorefilt") p.ignorefilt = 1;
+            else if (a.size() > 1 && a[0] == '-') throw InputError("unknown option " + a);
+            else if (npos < 2) pos[npos++] = a;
+            else throw InputError("too many arguments");
+        }
+        if (npos != 2) throw InputError("expected <scoredef> <genotypes.vcf>");
+    } catch (const InputError &e) {
+        std::cerr << e.what() << "\n" << "Usage:\n  nimpress [options] <scoredef> <genotypes.vcf>\n";
+        return 1;
+    }
+    nph_result *r = nullptr;
+    int rc = nph_compute_polygenic_scores(pos[0].c_str(), pos[1].c_str(), p.use_cov ? cov.c_str() : nullptr, &p, &r);
+    if (rc == NPH_EOPEN_VCF) { std::cout << "FATAL Could not open input VCF file " << pos[1] << "\n"; return 255; }          // :729-730
+    if (rc == NPH_EOPEN_SCORE) { std::cout << "FATAL Could not open polygenic score file " << pos[0] << "\n"; return 255; } // :733-734
+    if (rc) { std::cerr << "nimpress: " << nph_last_error() << "\n"; return 1; }
+    std::cout << nph_result_warnings(r);
+    const double *s = nph_result_scores(r);
+    for (int64_t i = 0; i < nph_result_n_samples(r); i++)                      // :752-753
+        std::cout << nph_result_sample(r, i) << "\t" << format_float_nim(s[i]) << "\n";
+    nph_result_free(r);
+    return 0;
+}
