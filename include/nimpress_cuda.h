@@ -187,12 +187,21 @@ void npc_normalise(double *sums, int64_t n, int64_t nloci, double offset);
 /* Kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t npc_launch_count(const npc_ctx *ctx);
 
-/* Which kernels npc_score_block* uses for this context: shape[0] = 1 for the fused persistent
- * kernel (int8 diploid cohorts that fit one resident pass), 0 for the count/decide/accumulate
- * sequence; then grid, consumer warps, chunks per thread, rows per tile, raw stages * 1000 +
- * index-ring tiles, lag * 100 + decider warps, dynamic shared-memory bytes. */
-int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
+/* Summation order of the int8 diploid fused kernels.  on = 0 (default): a tile of four score
+ * rows is summed first and then added to each sample's running sum -- same rounded products
+ * fl(dosage*beta) as the reference, different association, scores within a few ulp of the running
+ * sum (<= 1e-12 relative in the tests; contract 1e-9).  on = 1: every product is added in
+ * score-row order like `scores[i] += dosages[i]*beta` (src/nimpress.nim:639-640): bit-identical
+ * to the reference's chain, at a lower speed.  The generic (int16/int32/other ploidy) kernels
+ * and the split count/accumulate calls are always exact. */
+int npc_set_exact_order(npc_ctx *ctx, int32_t on);
 
+/* Which kernels npc_score_block* uses for this context: shape[0] = 2 for the 4-row-tile fused
+ * kernel, 1 for the exact-order fused kernel (int8 diploid cohorts that fit one resident pass),
+ * 0 for the count/decide/accumulate sequence; then grid, consumer warps, chunks per thread, rows
+ * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + decider warps, dynamic
+ * shared-memory bytes. */
+int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
 /* ---- utilities (tests / bench) ----------------------------------------------------------- */
 
 /* Deterministic synthetic cohort written straight into device memory: int8 diploid GT rows

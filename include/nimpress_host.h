@@ -40,6 +40,8 @@ typedef struct {
     int32_t ignorefilt;
     int32_t use_cov;        /* restrictToCoveredRgns */
     int32_t device;
+    int32_t exact_order;    /* 1: npc_set_exact_order(ctx, 1) -- the reference's summation order bit for bit */
+    int32_t reserved;
     int64_t mincs;
     double  maxmis;
     double  afmisp;

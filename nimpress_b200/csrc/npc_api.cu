@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "npc_fused.cuh"
+#include "npc_fused4.cuh"
 
 using namespace npc;
 
@@ -36,9 +36,13 @@ struct npc_ctx {
     int64_t launches = 0;
     std::string err;
     // fused persistent kernel (int8 diploid): launch shape fixed per context
-    bool fused_ok = false;
+    bool fused_ok = false;                  // exact-order kernel (npc_fused.cuh) usable
+    bool fast_ok = false;                   // 4-row-tile kernel (npc_fused4.cuh) usable
+    bool exact = false;                     // npc_set_exact_order
     int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 2, f_Sr = 4, f_Sc = 8, f_L = 7, f_A = 4, f_slab = 0;
     uint32_t f_smem = 0;
+    int q_Sr = 3, q_Sc = 16, q_L = 15, q_A = 4;   // launch shape of the 4-row-tile kernel
+    uint32_t q_smem = 0;
     uint8_t *d_slab = nullptr;              // resident slab (npc_resident_reserve)
     int64_t slab_rows = 0;
     cudaEvent_t ev_slab = nullptr;          // last scoring launch that read the slab
@@ -132,6 +136,26 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
     c->fused_ok = true;
+    // 4-row-tile kernel: raw ring ~80 KB, the rest of shared memory is index-ring slots
+    {
+        int qSr = env_int("NPC_FAST_SR", 0), qSc = env_int("NPC_FAST_SC", 0), qL = env_int("NPC_FAST_L", 0), qA = env_int("NPC_FAST_A", 4);
+        if (qSr <= 0) qSr = std::max(2, std::min(8, (84 * 1024) / (F4_R * c->f_slab)));
+        if (qSc <= 0) {
+            qSc = 32;
+            while (qSc > 2 && (int)Fused4Smem::make(qSr, qSc, c->f_slab).total > max_smem) qSc--;
+        }
+        while (qSr > 2 && (int)Fused4Smem::make(qSr, qSc, c->f_slab).total > max_smem) qSr--;
+        if ((int)Fused4Smem::make(qSr, qSc, c->f_slab).total <= max_smem && qSc >= 2 && env_int("NPC_FAST", 1) != 0) {
+            if (qL <= 0 || qL > qSc - 1) qL = qSc - 1;
+            c->q_Sr = qSr; c->q_Sc = qSc; c->q_L = qL; c->q_A = std::max(1, std::min(6, qA));
+            c->q_smem = Fused4Smem::make(qSr, qSc, c->f_slab).total;
+            const void *fn = K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
+            cudaError_t e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem);
+            if (e2 != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e2); return NPC_ECUDA; }
+            c->fast_ok = true;
+        }
+    }
+    c->exact = env_int("NPC_EXACT", 0) != 0;
     return NPC_OK;
 }
 
@@ -234,8 +258,19 @@ extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->laun
 
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!ctx || !shape) return NPC_EINVAL;
-    shape[0] = ctx->fused_ok ? 1 : 0; shape[1] = ctx->f_grid; shape[2] = ctx->f_nc; shape[3] = ctx->f_K;
-    shape[4] = ctx->f_R; shape[5] = ctx->f_Sr * 1000 + ctx->f_Sc; shape[6] = ctx->f_L * 100 + ctx->f_A; shape[7] = (int32_t)ctx->f_smem;
+    const bool fast = ctx->fused_ok && ctx->fast_ok && !ctx->exact;
+    shape[0] = !ctx->fused_ok ? 0 : fast ? 2 : 1; shape[1] = ctx->f_grid; shape[2] = ctx->f_nc; shape[3] = ctx->f_K;
+    if (fast) {
+        shape[4] = F4_R; shape[5] = ctx->q_Sr * 1000 + ctx->q_Sc; shape[6] = ctx->q_L * 100 + ctx->q_A; shape[7] = (int32_t)ctx->q_smem;
+    } else {
+        shape[4] = ctx->f_R; shape[5] = ctx->f_Sr * 1000 + ctx->f_Sc; shape[6] = ctx->f_L * 100 + ctx->f_A; shape[7] = (int32_t)ctx->f_smem;
+    }
+    return NPC_OK;
+}
+
+extern "C" int npc_set_exact_order(npc_ctx *ctx, int32_t on) {
+    if (!ctx) return NPC_EINVAL;
+    ctx->exact = on != 0;
     return NPC_OK;
 }
 
@@ -328,10 +363,18 @@ static int launch_fused(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
     P.sums = c->d_sums; P.counts = c->d_fcounts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
-    P.Sr = c->f_Sr; P.Sc = c->f_Sc; P.L = c->f_L; P.A = c->f_A; P.nc = c->f_nc; P.slab_stride = c->f_slab;
+    P.nc = c->f_nc; P.slab_stride = c->f_slab;
     void *args[] = { &P };
-    const dim3 grid(c->f_grid), block((c->f_nc + 2 + c->f_A) * 32);
-    NPC_CUDA(c, cudaLaunchCooperativeKernel((const void *)fused_kernel(c->f_K, c->f_R), grid, block, args, c->f_smem, c->stream));
+    const dim3 grid(c->f_grid);
+    if (c->fast_ok && !c->exact) {
+        P.Sr = c->q_Sr; P.Sc = c->q_Sc; P.L = c->q_L; P.A = c->q_A;
+        const void *fn = c->f_K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
+        NPC_CUDA(c, cudaLaunchCooperativeKernel(fn, grid, dim3((c->f_nc + 2 + c->q_A) * 32), args, c->q_smem, c->stream));
+    } else {
+        P.Sr = c->f_Sr; P.Sc = c->f_Sc; P.L = c->f_L; P.A = c->f_A;
+        NPC_CUDA(c, cudaLaunchCooperativeKernel((const void *)fused_kernel(c->f_K, c->f_R), grid, dim3((c->f_nc + 2 + c->f_A) * 32), args,
+                                                c->f_smem, c->stream));
+    }
     c->launches++;
     c->log_len += n_rows;
     return NPC_OK;

@@ -71,6 +71,7 @@ def load_library():
         "npc_normalise": (None, [vp, i64, i64, f64]),
         "npc_launch_count": (i64, [vp]),
         "npc_kernel_shape": (C.c_int, [vp, C.POINTER(i32 * 8)]),
+        "npc_set_exact_order": (C.c_int, [vp, i32]),
         "npc_synth_fill_device": (C.c_int, [vp, vp, i64, i64, i64, C.c_uint64, vp, vp, vp]),
         "npc_version": (C.c_int, []),
     }
@@ -124,6 +125,9 @@ class Engine:
     def set_policy(self, imp_locus="ps", imp_missing="homref", imp_sample="int_ps", maxmis=0.05, mincs=100):
         p = _Policy(LOCUS[imp_locus], MISSING[imp_missing], SAMPLE[imp_sample], 0, int(mincs), float(maxmis))
         self._ck(self.L.npc_set_policy(self.h, C.byref(p)))
+
+    def set_exact_order(self, on=True):
+        self._ck(self.L.npc_set_exact_order(self.h, int(bool(on))))
 
     def set_cohort_size(self, n_total):
         self._ck(self.L.npc_set_cohort_size(self.h, int(n_total)))

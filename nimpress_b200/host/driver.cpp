@@ -111,6 +111,7 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
     npc_policy pol = { p.imp_locus, p.imp_missing, p.imp_sample, 0, p.mincs, p.maxmis };
     ctx.ck(npc_create(&ctx.h, p.device, n, ploidy, gt_width, block_rows, 3), "npc_create");
     ctx.ck(npc_set_policy(ctx.h, &pol), "npc_set_policy");
+    if (p.exact_order) ctx.ck(npc_set_exact_order(ctx.h, 1), "npc_set_exact_order");
     ctx.ck(npc_reset(ctx.h), "npc_reset");
     int64_t slab_cap = 0;
     ctx.ck(npc_resident_reserve(ctx.h, std::max<int64_t>(n_lookup, 1), &slab_cap), "npc_resident_reserve");

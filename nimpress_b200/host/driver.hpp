@@ -25,6 +25,7 @@ struct ScoreParams {
     bool ignorefilt = false;               // --ignorefilt
     bool use_cov = false;                  // --cov given (restrictToCoveredRgns)
     int device = 0;                        // CUDA device (not a reference option)
+    bool exact_order = false;              // npc_set_exact_order: bit-for-bit reference summation order
 };
 
 struct ScoreResult {

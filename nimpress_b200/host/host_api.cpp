@@ -18,7 +18,7 @@ const char *nph_last_error(void) { return g_err.c_str(); }
 static ScoreParams to_params(const nph_params *p) {
     ScoreParams q;
     q.imp_locus = p->imp_locus; q.imp_missing = p->imp_missing; q.imp_sample = p->imp_sample;
-    q.ignorefilt = p->ignorefilt != 0; q.use_cov = p->use_cov != 0; q.device = p->device;
+    q.ignorefilt = p->ignorefilt != 0; q.use_cov = p->use_cov != 0; q.device = p->device; q.exact_order = p->exact_order != 0;
     q.mincs = p->mincs; q.maxmis = p->maxmis; q.afmisp = p->afmisp;
     return q;
 }
@@ -172,7 +172,10 @@ static const char *USAGE =
     "  --afmisp=<f>       p-value threshold for warning about allele frequency\n"
     "                     mismatch [default: 0.001].\n"
     "  --ignorefilt       Ignore the VCF FILTER field.\n"
-    "  --device=<n>       CUDA device to score on [default: 0] (not a reference option).\n";
+    "  --device=<n>       CUDA device to score on [default: 0] (not a reference option).\n"
+    "  --exact-order      Add every locus to the running sums in score-file order, bit for bit\n"
+    "                     like the reference (default: sum tiles of four loci first; same\n"
+    "                     products, scores equal to ~1e-15 relative) (not a reference option).\n";
 
 static int parse_enum(const std::string &v, std::initializer_list<const char *> names) {   // Nim parseEnum: style-insensitive beyond the first char is not reproduced
     int i = 0;
@@ -181,7 +184,7 @@ static int parse_enum(const std::string &v, std::initializer_list<const char *> 
 }
 
 int nph_main(int argc, char **argv) {
-    nph_params p = { NPC_LOCUS_PS, NPC_MISSING_HOMREF, NPC_SAMPLE_INT_PS, 0, 0, 0, 100, 0.05, 0.001 };
+    nph_params p = { NPC_LOCUS_PS, NPC_MISSING_HOMREF, NPC_SAMPLE_INT_PS, 0, 0, 0, 0, 0, 100, 0.05, 0.001 };
     std::string cov, pos[2];
     int npos = 0;
     try {
@@ -205,6 +208,7 @@ int nph_main(int argc, char **argv) {
             else if (is("--afmisp")) p.afmisp = parse_float_nim(val("--afmisp"), "--afmisp");
             else if (is("--device")) p.device = (int)parse_int_nim(val("--device"), "--device");
             else if (a == "--ignorefilt") p.ignorefilt = 1;
+            else if (a == "--exact-order") p.exact_order = 1;
             else if (a.size() > 1 && a[0] == '-') throw InputError("unknown option " + a);
             else if (npos < 2) pos[npos++] = a;
             else throw InputError("too many arguments");

@@ -25,7 +25,7 @@ def declared_symbols(header):
 
 def test_exports_match_header(lib):
     syms = declared_symbols("nimpress_cuda.h")
-    assert len(syms) >= 23
+    assert len(syms) >= 24
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/nimpress_cuda.h but not exported"
     assert sorted(lib._npc_symbols) == syms, "python binding and header disagree"

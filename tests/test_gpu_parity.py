@@ -1,7 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
-Bars: per-locus {class, used, eaidx, ngt, nmiss, neff, imputed} and nloci bit-exact; per-sample
-scores bit-exact on one context (same rounded products, same order as the reference's chain),
-which is stricter than north_star's 1e-9 relative."""
+Bars: per-locus {class, used, eaidx, ngt, nmiss, neff, imputed} and nloci bit-exact in every mode.
+Per-sample scores: bit-exact for the generic kernels and the exact-order fused kernel (same rounded
+products, same order as the reference's chain); <= 1e-12 relative for the default 4-row-tile fused
+kernel (same products, tile-wise association) -- north_star's bar is 1e-9 relative."""
 import itertools
 import json
 import os
@@ -25,7 +26,10 @@ def nb():
     return nimpress_b200
 
 
-def run_engine(nb, gt, n, rows, ploidy=2, offset=0.0, block_rows=None, staged=True, policy=None, max_rows=None):
+MODES = ["tile4", "exact"]
+
+
+def run_engine(nb, gt, n, rows, ploidy=2, offset=0.0, block_rows=None, staged=True, policy=None, max_rows=None, mode="exact"):
     width = gt.dtype.itemsize
     policy = policy or {}
     V = gt.shape[0]
@@ -33,6 +37,7 @@ def run_engine(nb, gt, n, rows, ploidy=2, offset=0.0, block_rows=None, staged=Tr
     eng = nb.Engine(n, ploidy=ploidy, gt_width=width, max_rows_per_block=max_rows or max(block_rows, V, 1),
                     n_slots=2 if staged else 0)
     eng.set_policy(**policy)
+    eng.set_exact_order(mode == "exact")
     eng.reset()
     if staged:
         for r0 in range(0, max(len(rows), 1), block_rows):
@@ -59,8 +64,9 @@ def oracle(gt, n, rows, ploidy=2, offset=0.0, policy=None):
 CASES = json.load(open(os.path.join(G, "set1_expected.json")))["cases"]
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("case", CASES, ids=[c["ref"] for c in CASES])
-def test_set1_golden_through_gpu(nb, case):
+def test_set1_golden_through_gpu(nb, case, mode):
     """tests/test_set1.nim: every expected vector, 1e-4 abs + NaN pattern (checkFloats :14-22),
     and bit-equality with the oracle's file-level run."""
     from util_vcf import build_block
@@ -70,7 +76,7 @@ def test_set1_golden_through_gpu(nb, case):
                                             ignorefilt=case["ignorefilt"])
     pol = dict(imp_locus=case["imp_locus"], imp_missing=case["imp_missing"], imp_sample=case["imp_sample"],
                maxmis=case["maxmis"], mincs=case["mincs"])
-    got = run_engine(nb, gt, len(samples), rows, offset=offset, policy=pol)
+    got = run_engine(nb, gt, len(samples), rows, offset=offset, policy=pol, mode=mode)
     exp = np.array([np.nan if e is None else (e[1] - e[2] if isinstance(e, list) else e) for e in case["expected"]])
     assert np.array_equal(np.isnan(got["scores"]), np.isnan(exp))
     ok = ~np.isnan(exp)
@@ -78,18 +84,19 @@ def test_set1_golden_through_gpu(nb, case):
     ref = orc.compute_scores_files(os.path.join(S1, "set1.score"), os.path.join(S1, "set1.vcf.gz"),
                                    os.path.join(S1, "set1.bed") if case["cov"] else None,
                                    afmisp=case["afmisp"], ignorefilt=case["ignorefilt"], **pol)
-    assert_parity(got, ref)
+    assert_parity(got, ref, exact=mode == "exact")
 
 
 # ---- randomised cohorts ----------------------------------------------------------------------
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("n", [1, 7, 8, 9, 255, 256, 257, 1000, 4099, 100003])
-def test_sample_count_edges_i8(nb, n):
+def test_sample_count_edges_i8(nb, n, mode):
     rng = np.random.default_rng(n)
     V = 37
     gt = random_cohort(rng, n, V, miss_rate=0.03)
     rows = random_rows(rng, V, n_rows=50)
-    assert_parity(run_engine(nb, gt, n, rows, offset=0.5), oracle(gt, n, rows, offset=0.5))
+    assert_parity(run_engine(nb, gt, n, rows, offset=0.5, mode=mode), oracle(gt, n, rows, offset=0.5), exact=mode == "exact")
 
 
 @pytest.mark.parametrize("width,ploidy", [(1, 1), (1, 2), (1, 3), (2, 2), (2, 4), (4, 2), (4, 1)])
@@ -101,14 +108,15 @@ def test_widths_and_ploidies(nb, width, ploidy):
     assert_parity(run_engine(nb, gt, n, rows, ploidy=ploidy), oracle(gt, n, rows, ploidy=ploidy))
 
 
-def test_slow_path_alleles_sentinels_invalid(nb):
+@pytest.mark.parametrize("mode", MODES)
+def test_slow_path_alleles_sentinels_invalid(nb, mode):
     """int8 diploid rows with alleles >= 7 (bytes >= 16), vector_end / missing sentinels and raw
     negative bytes: every chunk that is not 'all bytes < 16' takes the exact slow decode."""
     rng = np.random.default_rng(5)
     n, V = 5003, 48
     gt = random_cohort(rng, n, V, miss_rate=0.04, n_alt=12, sentinel_rate=0.01, invalid_rate=0.001)
     rows = random_rows(rng, V, n_rows=96, n_alt=12)
-    assert_parity(run_engine(nb, gt, n, rows), oracle(gt, n, rows))
+    assert_parity(run_engine(nb, gt, n, rows, mode=mode), oracle(gt, n, rows), exact=mode == "exact")
 
 
 POLICIES = [dict(imp_locus=l, imp_missing=m, imp_sample=s, maxmis=x, mincs=c)
@@ -117,7 +125,8 @@ POLICIES = [dict(imp_locus=l, imp_missing=m, imp_sample=s, maxmis=x, mincs=c)
                                                    (0.0, 0.03, 1.0), (0, 1900))]
 
 
-def test_policy_grid(nb):
+@pytest.mark.parametrize("mode", MODES)
+def test_policy_grid(nb, mode):
     """Every --imp-locus x --imp-missing x --imp-sample x --maxmis x --mincs combination on one
     cohort whose per-locus missing rates straddle the thresholds."""
     rng = np.random.default_rng(11)
@@ -125,10 +134,12 @@ def test_policy_grid(nb):
     gt = random_cohort(rng, n, V, miss_rate=0.03)
     rows = random_rows(rng, V, n_rows=80)
     for pol in POLICIES:
-        assert_parity(run_engine(nb, gt, n, rows, offset=-0.125, policy=pol), oracle(gt, n, rows, offset=-0.125, policy=pol))
+        assert_parity(run_engine(nb, gt, n, rows, offset=-0.125, policy=pol, mode=mode), oracle(gt, n, rows, offset=-0.125, policy=pol),
+                      exact=mode == "exact")
 
 
-def test_maxmis_boundary_exact(nb):
+@pytest.mark.parametrize("mode", MODES)
+def test_maxmis_boundary_exact(nb, mode):
     """nmissing/n > maxmis is a strict fp64 compare (src/nimpress.nim:565-566): rows with exactly
     k missing of n against thresholds k/n, nextafter(k/n) on both sides."""
     n = 1000
@@ -141,33 +152,36 @@ def test_maxmis_boundary_exact(nb):
     for k in (1, 50, 333):
         for thr in (k / n, np.nextafter(k / n, 0), np.nextafter(k / n, 1)):
             pol = dict(maxmis=float(thr), imp_sample="int_ps", mincs=0)
-            assert_parity(run_engine(nb, gt, n, rows, policy=pol), oracle(gt, n, rows, policy=pol))
+            assert_parity(run_engine(nb, gt, n, rows, policy=pol, mode=mode), oracle(gt, n, rows, policy=pol), exact=mode == "exact")
 
 
-def test_empty_and_degenerate_blocks(nb):
+@pytest.mark.parametrize("mode", MODES)
+def test_empty_and_degenerate_blocks(nb, mode):
     rng = np.random.default_rng(1)
     n = 100
     gt = random_cohort(rng, n, 4)
     # no rows at all: nloci = 0 -> 0/0 = NaN for everyone (reference: scores /= 0*2)
-    got = run_engine(nb, gt, n, np.zeros(0, dtype=orc.ROW_DTYPE), offset=1.0)
+    ex = mode == "exact"
+    got = run_engine(nb, gt, n, np.zeros(0, dtype=orc.ROW_DTYPE), offset=1.0, mode=mode)
     assert got["nloci"] == 0 and np.all(np.isnan(got["scores"]))
     # only constant rows, no genotype slab
     rows = random_rows(rng, 0, n_rows=9)
-    assert_parity(run_engine(nb, np.zeros((0, 16), np.int8), n, rows), oracle(np.zeros((1, 16), np.int8), n, rows))
+    assert_parity(run_engine(nb, np.zeros((0, 16), np.int8), n, rows, mode=mode), oracle(np.zeros((1, 16), np.int8), n, rows), exact=ex)
     # all rows ignored
     pol = dict(imp_locus="ignore", imp_missing="ignore", maxmis=0.0)
     gt2 = random_cohort(rng, n, 4, miss_rate=0.5)
     rows = random_rows(rng, 4, n_rows=8)
-    assert_parity(run_engine(nb, gt2, n, rows, policy=pol), oracle(gt2, n, rows, policy=pol))
+    assert_parity(run_engine(nb, gt2, n, rows, policy=pol, mode=mode), oracle(gt2, n, rows, policy=pol), exact=ex)
     # beta = 0, inf and NaN, eaf NaN: NaN*0 = NaN must poison exactly the reference's samples
     rows = random_rows(rng, 4, n_rows=12)
     rows["beta"][:4] = [0.0, np.inf, np.nan, -0.0]
     rows["eaf"][4:6] = np.nan
     for pol in (dict(imp_sample="fail"), dict(imp_sample="ps"), dict(imp_locus="fail", maxmis=0.0)):
-        assert_parity(run_engine(nb, gt2, n, rows, policy=pol), oracle(gt2, n, rows, policy=pol))
+        assert_parity(run_engine(nb, gt2, n, rows, policy=pol, mode=mode), oracle(gt2, n, rows, policy=pol), exact=ex)
 
 
-def test_streaming_blocks_equal_single_block(nb):
+@pytest.mark.parametrize("mode", MODES)
+def test_streaming_blocks_equal_single_block(nb, mode):
     """Rows split over many npc_score_block calls (pinned ring, 3 in flight) give the same bits as
     one block, and the device-resident entry point gives the same bits as the staged one."""
     rng = np.random.default_rng(21)
@@ -175,11 +189,11 @@ def test_streaming_blocks_equal_single_block(nb):
     gt = random_cohort(rng, n, V, miss_rate=0.02)
     rows = random_rows(rng, V, n_rows=300)
     want = oracle(gt, n, rows)
-    one = run_engine(nb, gt, n, rows)
-    many = run_engine(nb, gt, n, rows, block_rows=17, max_rows=300)
-    dev = run_engine(nb, gt, n, rows, staged=False, block_rows=64, max_rows=300)
+    one = run_engine(nb, gt, n, rows, mode=mode)
+    many = run_engine(nb, gt, n, rows, block_rows=17, max_rows=300, mode=mode)
+    dev = run_engine(nb, gt, n, rows, staged=False, block_rows=64, max_rows=300, mode=mode)
     for got in (one, many, dev):
-        assert_parity(got, want)
+        assert_parity(got, want, exact=mode == "exact")
 
 
 def test_split_count_accumulate_matches_fused(nb):
@@ -239,7 +253,8 @@ def test_synth_generator_matches_oracle(nb):
     eng.close()
 
 
-def test_config2_shape_wood_100k(nb):
+@pytest.mark.parametrize("mode", MODES)
+def test_config2_shape_wood_100k(nb, mode):
     """BASELINE.json configs[1]: the 697 wood-height loci x 100,000 synthetic samples, 0.5% missing,
     default policies; whole result bit-equal to the oracle."""
     from util_vcf import read_score
@@ -258,16 +273,21 @@ def test_config2_shape_wood_100k(nb):
     rows["beta"] = [e["beta"] for e in ents]
     rows["eaf"] = af
     assert V == 697
-    assert_parity(run_engine(nb, gt, n, rows, offset=offset, staged=False), oracle(gt, n, rows, offset=offset))
+    assert_parity(run_engine(nb, gt, n, rows, offset=offset, staged=False, mode=mode), oracle(gt, n, rows, offset=offset),
+                  exact=mode == "exact")
 
 
-@pytest.mark.parametrize("env", [dict(NPC_FUSED="0"), dict(NPC_FUSED_R="1", NPC_FUSED_SR="2", NPC_FUSED_SC="2", NPC_FUSED_A="1"),
-                                 dict(NPC_FUSED_R="8", NPC_FUSED_SR="3", NPC_FUSED_SC="5", NPC_FUSED_L="3"), dict(NPC_FUSED_K="2"),
-                                 dict(NPC_FUSED_K="2", NPC_FUSED_R="3", NPC_FUSED_A="6"), dict(NPC_FUSED_R="4", NPC_FUSED_L="1")],
+@pytest.mark.parametrize("env", [dict(NPC_FUSED="0"),
+                                 dict(NPC_EXACT="1", NPC_FUSED_R="1", NPC_FUSED_SR="2", NPC_FUSED_SC="2", NPC_FUSED_A="1"),
+                                 dict(NPC_EXACT="1", NPC_FUSED_R="8", NPC_FUSED_SR="3", NPC_FUSED_SC="5", NPC_FUSED_L="3"),
+                                 dict(NPC_EXACT="1", NPC_FUSED_K="2", NPC_FUSED_R="3", NPC_FUSED_A="6"),
+                                 dict(NPC_FAST="0"), dict(NPC_FAST_SR="2", NPC_FAST_SC="2", NPC_FAST_A="1"),
+                                 dict(NPC_FAST_SR="5", NPC_FAST_SC="9", NPC_FAST_L="3", NPC_FAST_A="6"), dict(NPC_FUSED_K="2")],
                          ids=lambda e: ",".join(f"{k[4:]}={v}" for k, v in e.items()))
 def test_kernel_paths_agree(nb, env, monkeypatch):
-    """The fused persistent kernel under several ring shapes and the two-kernel sequence all give
-    the oracle's bits (the launch shape must not change the summation order)."""
+    """Every kernel path and launch shape gives the oracle's per-locus records; the exact-order
+    kernels (two-kernel sequence, exact fused kernel under several ring shapes) give its bits, the
+    4-row-tile kernel agrees to 1e-12 under every ring shape."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     rng = np.random.default_rng(77)
@@ -276,7 +296,22 @@ def test_kernel_paths_agree(nb, env, monkeypatch):
     rows = random_rows(rng, V, n_rows=260, n_alt=9)
     want = oracle(gt, n, rows, offset=0.5)
     eng = nb.Engine(n, max_rows_per_block=512)
-    assert eng.kernel_shape["fused"] == (0 if env.get("NPC_FUSED") == "0" else 1)
+    kind = eng.kernel_shape["fused"]
     eng.close()
-    assert_parity(run_engine(nb, gt, n, rows, offset=0.5, staged=False, max_rows=512), want)
-    assert_parity(run_engine(nb, gt, n, rows, offset=0.5, staged=True, block_rows=37, max_rows=512), want)
+    exact = "NPC_EXACT" in env or env.get("NPC_FUSED") == "0" or env.get("NPC_FAST") == "0"
+    assert kind == (0 if env.get("NPC_FUSED") == "0" else 1 if exact else 2)
+    mode = None                                        # leave the context's default (set by the environment)
+    for kw in (dict(staged=False, max_rows=512), dict(staged=True, block_rows=37, max_rows=512)):
+        V_ = gt.shape[0]
+        eng = nb.Engine(n, max_rows_per_block=512, n_slots=2 if kw["staged"] else 0)
+        eng.set_policy(); eng.reset()
+        if kw["staged"]:
+            for r0 in range(0, len(rows), 37):
+                eng.score_host(gt, rows[r0:r0 + 37])
+        else:
+            import torch
+            d = torch.from_numpy(gt.view(np.uint8).reshape(V_, -1)).cuda()
+            eng.score_block_device(d, d.shape[1], V_, rows)
+        got = eng.finish(offset=0.5)
+        eng.close()
+        assert_parity(got, want, exact=exact)

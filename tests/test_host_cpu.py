@@ -1,0 +1,186 @@
+"""CPU tests of the C++ host (libnimpress_host.so): parsers, VCF/BCF readers, the streaming
+findVariant, stats and output formatting -- against the oracle and the reference's known answers.
+No GPU needed: nothing here computes a score."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import orc
+from util_bcf import write_bcf, write_vcf
+from util_files import make_dataset
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+S1 = os.path.join(G, "set1")
+
+
+@pytest.fixture(scope="module")
+def api():
+    import __graft_entry__ as g
+    g.build()
+    from nimpress_b200 import api
+    api.load_host_library()
+    return api
+
+
+def plan(api, score, vcf, bed=None, ignorefilt=False):
+    L = api.load_host_library()
+    p = api._Params(0, 0, 3, int(ignorefilt), int(bed is not None), 0, 0, 0, 100, 0.05, 0.001)
+    kind = np.zeros(1 << 16, np.int32); ea = np.zeros(1 << 16, np.int32)
+    n_rows, n_s = C.c_int64(), C.c_int64()
+    rc = L.nph_plan(os.fsencode(score), os.fsencode(vcf), os.fsencode(bed) if bed else None, C.byref(p),
+                    kind.ctypes.data, ea.ctypes.data, len(kind), C.byref(n_rows), C.byref(n_s))
+    return rc, kind[:n_rows.value].copy(), ea[:n_rows.value].copy(), n_s.value
+
+
+def read_gt(api, path, row_bytes, max_records=4096):
+    L = api.load_host_library()
+    out = np.zeros((max_records, row_bytes), np.uint8)
+    nrec, ns, w, pl = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    rc = L.nph_read_gt(os.fsencode(path), out.ctypes.data, row_bytes, max_records, C.byref(nrec), C.byref(ns), C.byref(w), C.byref(pl))
+    assert rc == 0, rc
+    return out[:nrec.value], ns.value, w.value, pl.value
+
+
+def oracle_plan(score, vcf, bed=None, ignorefilt=False):
+    r = orc.compute_scores_files(score, vcf, bed, maxmis=1.0, ignorefilt=ignorefilt, skip_aftest=True)
+    kind = np.where(r["loci"]["klass"] == orc.CLASS_MAXMIS, 0, r["loci"]["klass"])
+    return kind, r["loci"]["eaidx"]
+
+
+def test_exports_match_header(api):
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "nimpress_host.h")).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(nph_[a-z_0-9]+)\s*\(", txt)))
+    L = api.load_host_library()
+    for s in syms:
+        assert hasattr(L, s), s
+    assert syms == L._nph_symbols
+
+
+def test_stats_known_answers(api):
+    """tests/test_stats.nim through the product's stats (bisection instead of enumeration)."""
+    L = api.load_host_library()
+    fns = {"dbinom": L.nph_dbinom, "pbinom": L.nph_pbinom, "binom_test": L.nph_binom_test, "betai": L.nph_betai}
+    for k in json.load(open(os.path.join(G, "stats_kat.json")))["kats"]:
+        a = k["args"]
+        v = fns[k["fn"]](a[0], a[1], a[2]) if k["fn"] == "betai" else fns[k["fn"]](int(a[0]), int(a[1]), a[2])
+        t = k["target"]
+        if k["kind"] == "exact":
+            assert v == t, k
+        elif abs(t) < 1e-9:
+            assert abs(v - t) < 1e-9, k
+        else:
+            assert abs((v - t) / t) < 1e-5, k
+
+
+def test_binom_test_bisection_equals_enumeration(api):
+    """The O(log n) tail search returns the same p-value as the reference's O(n) enumeration."""
+    L, O = api.load_host_library(), orc.lib()
+    rng = np.random.default_rng(5)
+    for n in (2, 7, 40, 1000, 20000, 200000):
+        for _ in range(60):
+            p = float(rng.choice([rng.uniform(0.001, 0.999), 0.5, 0.25, 0.01]))
+            x = int(rng.integers(0, n + 1)) if rng.random() < 0.5 else int(np.clip(rng.normal(n * p, 3 * np.sqrt(n * p * (1 - p)) + 1), 0, n))
+            a, b = L.nph_binom_test(x, n, p), O.orc_binom_test(x, n, p)
+            assert a == b or abs(a - b) <= 1e-12 * max(abs(b), 1e-300), (x, n, p, a, b)
+
+
+def test_float_format_corpus(api):
+    L = api.load_host_library()
+    buf = C.create_string_buffer(64)
+    for v in open(os.path.join(G, "res_format_corpus.tsv")).read().split():
+        L.nph_format_float(float(v), buf, 64)
+        assert buf.value.decode() == v
+    for x, s in ((2.0, "2.0"), (float("nan"), "nan"), (-float("inf"), "-inf"), (1e22, "1e+22"), (-3.0, "-3.0"), (0.1, "0.1")):
+        L.nph_format_float(x, buf, 64)
+        assert buf.value.decode() == s
+
+
+@pytest.mark.parametrize("bed,ign", [(None, False), (os.path.join(S1, "set1.bed"), False), (None, True)])
+def test_plan_set1(api, bed, ign):
+    rc, kind, ea, n = plan(api, os.path.join(S1, "set1.score"), os.path.join(S1, "set1.vcf.gz"), bed, ign)
+    assert rc == 0 and n == 6
+    ok, oea = oracle_plan(os.path.join(S1, "set1.score"), os.path.join(S1, "set1.vcf.gz"), bed, ign)
+    assert list(kind) == list(ok) and list(ea) == list(oea)
+
+
+def test_set1_gt_payload(api):
+    """CRLF BGZF VCF text -> int8 diploid payload identical to a hand transcription of the file."""
+    gt, n, w, pl = read_gt(api, os.path.join(S1, "set1.vcf.gz"), 16)
+    assert (n, w, pl, len(gt)) == (6, 1, 2, 7)
+    # record 5: 1:300 GA>T,CT   0/0 2/2 0/1 1/0 ./. 1/1
+    assert list(gt[4, :12].view(np.int8)) == [2, 2, 6, 6, 2, 4, 4, 2, 0, 0, 4, 4]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_plan_and_payload_vcf_bcf_oracle(api, tmp_path, seed):
+    """Streaming findVariant on VCF text and on BCF == the oracle's scan, incl. duplicate sites,
+    multi-base REF overlap at another POS, INFO/END spans, missing ALT, unknown contigs, and the
+    BED off-by-one traps; both readers hand out byte-identical GT payloads."""
+    rng = np.random.default_rng(seed)
+    d = make_dataset(str(tmp_path), rng, n=50, V=90, sorted_scores=seed != 3)
+    for bed in (None, d["bed"]):
+        for ign in (False, True):
+            ok, oea = oracle_plan(d["score"], d["vcf"], bed, ign)
+            for f in (d["vcf"], d["bcf"]):
+                rc, kind, ea, n = plan(api, d["score"], f, bed, ign)
+                assert rc == 0 and n == 50
+                assert np.array_equal(kind, ok), f
+                assert np.array_equal(ea, oea), f
+    a, n1, w1, p1 = read_gt(api, d["vcf"], 128)
+    b, n2, w2, p2 = read_gt(api, d["bcf"], 128)
+    assert (n1, w1, p1) == (n2, w2, p2) == (50, 1, 2) and np.array_equal(a, b)
+    want = np.stack([r["gt"].reshape(-1).view(np.uint8) for r in d["records"]])
+    assert np.array_equal(a[:, :100], want)
+
+
+def test_bcf_variants(api, tmp_path):
+    """BCF details: IDX= permuted dictionary, a FORMAT field before GT, int16 GT, haploid calls
+    padded with vector_end, uncompressed BCF, gzip (non-BGZF) VCF."""
+    rng = np.random.default_rng(9)
+    d = make_dataset(str(tmp_path), rng, n=20, V=30, haploid_rate=0.2)
+    ok, oea = oracle_plan(d["score"], d["vcf"], None, False)
+    contigs = ["1", "2", "X"]
+    for name, kw in (("idx.bcf", dict(with_idx=True)), ("fmt.bcf", dict(extra_fmt=True)), ("raw.bcf", dict(compress=None))):
+        p = os.path.join(str(tmp_path), name)
+        write_bcf(p, d["samples"], d["records"], contigs, filters=("FAIL", "LowQ"), **kw)
+        rc, kind, ea, n = plan(api, d["score"], p)
+        assert rc == 0 and np.array_equal(kind, ok) and np.array_equal(ea, oea), name
+        a, *_ = read_gt(api, p, 64)
+        b, *_ = read_gt(api, d["bcf"], 64)
+        assert np.array_equal(a, b), name
+    p = os.path.join(str(tmp_path), "gz.vcf.gz")
+    write_vcf(p, d["samples"], d["records"], contigs=contigs, filters=("FAIL", "LowQ"), compress="gzip", crlf=True)
+    rc, kind, ea, n = plan(api, d["score"], p)
+    assert rc == 0 and np.array_equal(kind, ok)
+    recs16 = [dict(r, gt=r["gt"].astype(np.int16)) for r in d["records"]]
+    for r in recs16:
+        r["gt"][r["gt"] == -127] = -32767
+    p = os.path.join(str(tmp_path), "w16.bcf")
+    write_bcf(p, d["samples"], recs16, contigs, filters=("FAIL", "LowQ"))
+    a, n, w, pl = read_gt(api, p, 128)
+    assert (w, pl) == (2, 2) and np.array_equal(a[:, :80].view(np.int16), np.stack([r["gt"].reshape(-1) for r in recs16]))
+
+
+def test_input_errors(api, tmp_path):
+    """The reference's doAssert / ValueError paths surface as NPH_EINPUT, unopenable files as -1/-2."""
+    vcf = os.path.join(S1, "set1.vcf.gz")
+    good = open(os.path.join(S1, "set1.score")).read()
+    cases = {"blank_tail": good + "\n\n", "five_cols": good + "\n1\t2\tA\tC\t0.1", "bad_float": good.replace("0.123", "abc"),
+             "bad_pos": good.replace("\n1\t100\t", "\n1\tx100\t")}
+    for name, txt in cases.items():
+        p = os.path.join(str(tmp_path), name)
+        open(p, "w").write(txt)
+        assert plan(api, p, vcf)[0] == -3, name
+    assert plan(api, os.path.join(str(tmp_path), "missing"), vcf)[0] == -2
+    assert plan(api, os.path.join(S1, "set1.score"), os.path.join(str(tmp_path), "missing.vcf"))[0] == -1
+    bed = os.path.join(str(tmp_path), "two_cols.bed")
+    open(bed, "w").write("1\t5\n")
+    assert plan(api, os.path.join(S1, "set1.score"), vcf, bed)[0] == -3
+    notvcf = os.path.join(str(tmp_path), "not.vcf")
+    open(notvcf, "w").write("hello\n")
+    assert plan(api, os.path.join(S1, "set1.score"), notvcf)[0] == -1

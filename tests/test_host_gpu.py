@@ -1,0 +1,105 @@
+"""GPU tests of the whole product path: C++ host (readers, streaming findVariant, staging into
+the resident slab) -> libnimpress_cuda -> scores, against the oracle run on the same files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+from util_cohort import assert_loci_equal, bits
+from util_files import make_dataset
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+S1 = os.path.join(ROOT, "tests", "golden", "set1")
+LOC = ("ps", "homref", "fail", "ignore"); MIS = ("homref", "ignore"); SAM = ("ps", "homref", "fail", "int_ps", "int_fail")
+
+
+@pytest.fixture(scope="module")
+def api():
+    import __graft_entry__ as g
+    g.build()
+    from nimpress_b200 import api
+    return api
+
+
+def compare(api, score, geno, vcf_for_oracle, bed, exact, **pol):
+    want = orc.compute_scores_files(score, vcf_for_oracle, bed, **pol)
+    got = api.run(score, geno, bed, imp_locus=orc.LOCUS[pol.get("imp_locus", "ps")], imp_missing=orc.MISSING[pol.get("imp_missing", "homref")],
+                  imp_sample=orc.SAMPLE[pol.get("imp_sample", "int_ps")], maxmis=pol.get("maxmis", 0.05), afmisp=pol.get("afmisp", 0.001),
+                  mincs=pol.get("mincs", 100), ignorefilt=pol.get("ignorefilt", False), exact_order=exact)
+    assert got.samples == want["samples"] and got.nloci == want["nloci"] and got.rounds == 1
+    assert_loci_equal(got.loci, want["loci"])
+    a, b = got.scores, want["scores"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = np.isfinite(b)
+    if exact:
+        assert np.array_equal(bits(a[ok]), bits(b[ok]))
+    else:
+        assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(np.abs(b[ok]), 1e-3))
+    assert got.warnings == want["warn"]
+    return got
+
+
+@pytest.mark.parametrize("exact", [False, True], ids=["tile4", "exact-order"])
+def test_set1_all_policies_vs_oracle(api, exact):
+    """Every policy combination on the reference fixture: scores, per-locus records and the WARN
+    text (incl. the AF-mismatch binomial test at the default --afmisp) equal the oracle's."""
+    sc, vc, bed = (os.path.join(S1, f) for f in ("set1.score", "set1.vcf.gz", "set1.bed"))
+    for l in LOC:
+        for m in MIS:
+            for s in SAM:
+                for mm, cs in ((1.0, 100), (0.2, 3), (0.05, 0)):
+                    for b in (None, bed):
+                        compare(api, sc, vc, vc, b, exact, imp_locus=l, imp_missing=m, imp_sample=s, maxmis=mm, mincs=cs)
+    compare(api, sc, vc, vc, None, exact, ignorefilt=True, afmisp=1.0)
+
+
+@pytest.mark.parametrize("seed,exact", [(11, True), (12, False), (13, True)])
+def test_synthetic_files_vcf_and_bcf(api, tmp_path, seed, exact):
+    """Synthetic cohort with the lookup corner cases, as BGZF VCF text and as BCF: both equal the
+    oracle (which reads the VCF text), under several policies, with and without --cov."""
+    rng = np.random.default_rng(seed)
+    d = make_dataset(str(tmp_path), rng, n=1203, V=300, sorted_scores=seed != 13)
+    for geno in (d["vcf"], d["bcf"]):
+        for bed in (None, d["bed"]):
+            compare(api, d["score"], geno, d["vcf"], bed, exact)
+            compare(api, d["score"], geno, d["vcf"], bed, exact, imp_locus="homref", imp_sample="fail", maxmis=0.02, afmisp=0.05)
+            compare(api, d["score"], geno, d["vcf"], bed, exact, imp_locus="ignore", imp_missing="ignore", imp_sample="int_fail", mincs=1100,
+                    ignorefilt=True)
+
+
+def test_wider_layouts_restart(api, tmp_path):
+    """A matched record with int16 GT or ploidy 3 makes the host rerun the pass with that layout
+    (generic kernels): results still equal the oracle bit for bit."""
+    from util_bcf import write_bcf, write_vcf
+    rng = np.random.default_rng(21)
+    d = make_dataset(str(tmp_path), rng, n=211, V=60, gt_dtype=np.int16)
+    compare(api, d["score"], d["bcf"], d["vcf"], None, True)
+    d = make_dataset(str(tmp_path), rng, n=97, V=45, ploidy=3, haploid_rate=0.1)
+    compare(api, d["score"], d["bcf"], d["vcf"], d["bed"], True)
+    compare(api, d["score"], d["vcf"], d["vcf"], None, True)
+
+
+def test_cli_stdout_matches_oracle_cli(api, tmp_path):
+    """`nimpress [options] <scoredef> <genotypes>`: stdout (WARN lines then sample<TAB>score in the
+    reference's float format) and exit codes, against the oracle's CLI."""
+    exe = os.path.join(ROOT, "nimpress_b200", "bin", "nimpress")
+    orc_exe = os.path.join(ROOT, "oracle", "_build", "nimpress_oracle")
+    sc, vc, bed = (os.path.join(S1, f) for f in ("set1.score", "set1.vcf.gz", "set1.bed"))
+    for opts in ([], ["--imp-sample=fail", "--maxmis=0.2"], [f"--cov={bed}", "--imp-locus=homref", "--mincs=3"],
+                 ["--ignorefilt", "--imp-locus=ignore", "--imp-missing=ignore", "--maxmis=1.0", "--mincs=0", "--afmisp=1.0"]):
+        a = subprocess.run([exe, "--exact-order", *opts, sc, vc], capture_output=True, text=True)
+        b = subprocess.run([orc_exe, *opts, sc, vc], capture_output=True, text=True)
+        assert a.returncode == 0 and a.stdout == b.stdout, (opts, a.stdout, b.stdout, a.stderr)
+    rng = np.random.default_rng(3)
+    d = make_dataset(str(tmp_path), rng, n=400, V=150)
+    a = subprocess.run([exe, "--exact-order", f"--cov={d['bed']}", d["score"], d["bcf"]], capture_output=True, text=True)
+    b = subprocess.run([orc_exe, f"--cov={d['bed']}", d["score"], d["vcf"]], capture_output=True, text=True)
+    assert a.returncode == 0 and a.stdout == b.stdout
+    assert subprocess.run([exe, sc, "/no/such.vcf"], capture_output=True, text=True).returncode == 255
+    assert subprocess.run([exe, "/no/such.score", vc], capture_output=True, text=True).returncode == 255
+    assert subprocess.run([exe, "--imp-locus=bogus", sc, vc], capture_output=True, text=True).returncode == 1
+    v = subprocess.run([exe, "--version"], capture_output=True, text=True)
+    assert v.stdout.strip() == "nimpress 1.0.0"

@@ -76,8 +76,11 @@ def assert_loci_equal(got, want):
     assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
 
 
-def assert_parity(got, want, exact=True, rtol=1e-9):
-    """got: Engine.finish() dict; want: orc.score_matrix() dict."""
+def assert_parity(got, want, exact=True, rtol=1e-12):
+    """got: Engine.finish() dict; want: orc.score_matrix() dict.  exact: scores bit-equal (generic
+    kernels, exact-order fused kernel).  Otherwise (default 4-row-tile kernel: same rounded products,
+    different association) |a-b| <= rtol*max(|b|, 1e-3) with rtol 1e-12 -- a thousand times tighter
+    than north_star's 1e-9 -- and identical NaN / inf patterns."""
     assert got["nloci"] == want["nloci"], (got["nloci"], want["nloci"])
     assert_loci_equal(got["loci"], want["loci"])
     a, b = got["scores"], want["scores"]
@@ -87,6 +90,8 @@ def assert_parity(got, want, exact=True, rtol=1e-9):
         bad = np.nonzero(bits(a[ok]) != bits(b[ok]))[0]
         assert bad.size == 0, f"{bad.size} scores differ in bits, first {a[ok][bad[:3]]} vs {b[ok][bad[:3]]}"
     else:
-        ok = ~np.isnan(a) & np.isfinite(a)
-        denom = np.maximum(np.abs(b[ok]), 1e-300)
-        assert np.all(np.abs(a[ok] - b[ok]) / denom <= rtol)
+        inf = np.isinf(b)
+        assert np.array_equal(np.isinf(a), inf) and np.array_equal(a[inf], b[inf]), "inf pattern differs"
+        ok = np.isfinite(b)
+        err = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-3)
+        assert err.size == 0 or err.max() <= rtol, f"max relative error {err.max():.3e} > {rtol}"
