@@ -189,6 +189,7 @@ def b200_arm(args):
     import torch
     import torch.distributed as dist
     import nimpress_b200 as nb
+    from nimpress_b200 import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,7 +231,6 @@ def b200_arm(args):
     d_rows = torch.from_numpy(rows_rel.view(np.uint8).reshape(V, -1)).to(dev)
     torch.cuda.synchronize()
 
-    gather = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
     sums_ptr, nloci_ptr = eng.partial_device_ptr()
 
     class _Wrap:   # expose the library-owned partial sums to torch.distributed without a copy
@@ -244,14 +244,8 @@ def b200_arm(args):
         for r0 in range(0, V, block_rows):
             nr = min(block_rows, V - r0)
             eng.score_block_device(gt[r0], stride, nr, d_rows[r0], n_rows=nr)
-        if world > 1:                                  # combine: gather partials, add in rank order
-            dist.all_gather(gather, t_sums)
-            total = gather[0].clone()
-            for g in gather[1:]:
-                total += g
-            nl = t_nloci.clone()
-            dist.all_reduce(nl)
-            return total, nl
+        if world > 1:                                  # combine: gather partials, add in rank order (NCCL over NVLink)
+            return shard.combine_partials(t_sums, t_nloci)
         return t_sums, t_nloci
 
     def barrier():

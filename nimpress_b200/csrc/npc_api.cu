@@ -139,7 +139,7 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     // 4-row-tile kernel: raw ring ~80 KB, the rest of shared memory is index-ring slots
     {
         int qSr = env_int("NPC_FAST_SR", 0), qSc = env_int("NPC_FAST_SC", 0), qL = env_int("NPC_FAST_L", 0), qA = env_int("NPC_FAST_A", 4);
-        if (qSr <= 0) qSr = std::max(2, std::min(8, (84 * 1024) / (F4_R * c->f_slab)));
+        if (qSr <= 0) qSr = std::max(2, std::min(8, (112 * 1024) / (F4_R * c->f_slab)));
         if (qSc <= 0) {
             qSc = 32;
             while (qSc > 2 && (int)Fused4Smem::make(qSr, qSc, c->f_slab).total > max_smem) qSc--;

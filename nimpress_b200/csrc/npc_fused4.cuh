@@ -12,13 +12,15 @@
 //    (per row: dosage | missing<<4, summed over 4 samples per register), once per tile.
 //  * The index ring therefore holds 1 byte per sample per 4 rows (1/8 of the raw data): the
 //    grid-wide dependency (see npc_fused.cuh) can lag by dozens of rows at no cost.
-//  * DECIDE builds, per tile, a 256-entry fp64 table T[b] = ((v0[b0]+v1[b1])+v2[b2])+v3[b3] of
-//    the four rows' contributions (constant rows and dropped rows fold in as constants).
-//  * ACCUMULATE: sums[s] += T[byte(s)] -- one 8-byte table load and one DADD per sample per
-//    FOUR genotypes, no per-row branches.
+//  * DECIDE builds, per tile, two 16-entry fp64 tables T01[b0|b1<<2] = v0[b0]+v1[b1] and
+//    T23[b2|b3<<2] = v2[b2]+v3[b3] of the rows' contributions (constant rows and dropped rows fold
+//    in as constants).  16 doubles span exactly the 32 banks: every lookup is conflict-free (one
+//    256-entry table was measured at 3-way conflicts: its hot entries share 9 of 16 bank pairs).
+//  * ACCUMULATE: sums[s] = (sums[s] + T01[..]) + T23[..] -- two 8-byte table loads and two DADDs
+//    per sample per FOUR genotypes, no per-row branches.
 //
-// Rounding: a tile's four contributions are added to each other first and then to the running
-// sum.  Every addend is still the reference's rounded product fl(dosage*beta); only the
+// Rounding: the contributions of rows (0,1) and of rows (2,3) of a tile are added to each other
+// first and then, in that order, to the running sum.  Every addend is still the reference's rounded product fl(dosage*beta); only the
 // association differs from the reference's left-to-right chain (src/nimpress.nim:639-640), so
 // scores agree to a few ulp of the running sum (tests assert <= 1e-12 relative; the contract is
 // 1e-9).  The result is deterministic and independent of the launch shape.  npc_set_exact_order
@@ -38,13 +40,13 @@ struct Fused4Smem {
         uint32_t o = 0;
         m.code = o;   o += F4_CODE_TABLES * 256u;                        // first: 256-byte aligned
         m.tt = o;     o += 256u * 4u;
+        m.vtab = o;   o += (uint32_t)Sc * 256u;                          // 256-byte aligned: T01 at +0, T23 at +128
         m.vrow = o;   o += 8u * 16u * 8u;                                // per decider warp: 4 rows x 4 values
         m.bars = o;   o += (2u * Sr + 2u * Sc) * 8u;            o = (o + 127u) & ~127u;
         m.cntacc = o; o += (uint32_t)Sc * F4_R * 16u * 4u;      o = (o + 127u) & ~127u;
         m.cisgt = o;  o += (uint32_t)Sc * 4u;                   o = (o + 127u) & ~127u;
         m.risgt = o;  o += (uint32_t)Sr * 4u;                   o = (o + 127u) & ~127u;
         m.reaidx = o; o += (uint32_t)Sr * F4_R * 4u;            o = (o + 127u) & ~127u;
-        m.vtab = o;   o += (uint32_t)Sc * 256u * 8u;            o = (o + 127u) & ~127u;
         m.idx = o;    o += (uint32_t)Sc * (uint32_t)(slab_stride / 2);  o = (o + 127u) & ~127u;
         m.data = o;   o += (uint32_t)Sr * F4_R * (uint32_t)slab_stride;
         m.total = o;
@@ -190,13 +192,10 @@ k_fused_tile4(const FusedParams P) {
                 if (lane == 0 && used) atomicAdd(P.nloci, (ull)used);
             }
             __syncwarp();
-            double *tab = reinterpret_cast<double *>(smem + M.vtab) + s * 256;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int b = lane + 32 * j;
-                const double x = __dadd_rn(__dadd_rn(__dadd_rn(vrow[b & 3], vrow[4 + ((b >> 2) & 3)]), vrow[8 + ((b >> 4) & 3)]),
-                                           vrow[12 + (b >> 6)]);
-                tab[b] = x;
+            {   // lanes 0..15: T01[lane] = v0[lane&3] + v1[lane>>2]; lanes 16..31: T23 likewise from rows 2, 3
+                double *tab = reinterpret_cast<double *>(smem + M.vtab) + s * 32;
+                const int h = lane >> 4, e = lane & 15;
+                tab[lane] = __dadd_rn(vrow[8 * h + (e & 3)], vrow[8 * h + 4 + (e >> 2)]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_lut + 8u * s);
@@ -295,14 +294,22 @@ k_fused_tile4(const FusedParams P) {
             }
             if (i >= L) {
                 mbar_wait(bar_lut + 8u * sa, ph_a);
-                const uint32_t tab = sb + M.vtab + (uint32_t)sa * 2048u;
+                const uint32_t thi = (sb + M.vtab + (uint32_t)sa * 256u) >> 8;     // bits 8.. of the slot's table block
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const uint2 v = lds_v2(sb + M.idx + (uint32_t)sa * islab + cell[k] * 8u);
+                    const uint32_t vv[2] = { v.x, v.y };
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        acc[k][e] = __dadd_rn(acc[k][e], lds_f64(tab + (__byte_perm(v.x, 0, 0x4440 + e) << 3)));
-                        acc[k][4 + e] = __dadd_rn(acc[k][4 + e], lds_f64(tab + (__byte_perm(v.y, 0, 0x4440 + e) << 3)));
+                    for (int h = 0; h < 2; h++) {
+                        // byte offsets of 4 samples at once: T01 entry (b & 15) * 8, T23 entry 128 + (b >> 4) * 8
+                        const uint32_t lo = (vv[h] & 0x0F0F0F0Fu) << 3;
+                        const uint32_t hi = ((vv[h] >> 1) & 0x78787878u) | 0x80808080u;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const double x01 = lds_f64(__byte_perm(lo, thi, 0x6540 + e));
+                            const double x23 = lds_f64(__byte_perm(hi, thi, 0x6540 + e));
+                            acc[k][4 * h + e] = __dadd_rn(__dadd_rn(acc[k][4 * h + e], x01), x23);
+                        }
                     }
                 }
                 if (++sa == Sc) { sa = 0; ph_a ^= 1u; }

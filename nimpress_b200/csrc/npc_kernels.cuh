@@ -210,12 +210,12 @@ __device__ __forceinline__ void decide_row(const Policy &p, const npc_row &row, 
     int klass = row.kind;
     if (row.kind == NPC_KIND_NOTCOV) {                                   // :526-531
         used = constant = locus_value(p, row, v);
+    } else if (row.kind == NPC_KIND_FILTER) {                            // :553-558 (never decoded: gt_row may be -1)
+        rec.eaidx = row.eaidx;
+        used = constant = locus_value(p, row, v);
     } else if (row.kind == NPC_KIND_ABSENT || row.gt_row < 0) {          // :536-551
         klass = NPC_KIND_ABSENT;
         if (p.imp_missing == NPC_MISSING_HOMREF) { v = row.ref_is_ea ? 2.0 : 0.0; used = constant = true; }
-    } else if (row.kind == NPC_KIND_FILTER) {                            // :553-558
-        rec.eaidx = row.eaidx;
-        used = constant = locus_value(p, row, v);
     } else {
         rec.eaidx = row.eaidx;
         const double nmiss = (double)nmiss_u, neff = (double)neff_u;

@@ -746,9 +746,9 @@ static void *matrix_range(void *arg) {
             used = impute_locus(dos, n, row->eaf, row->ref_is_ea, j->p->imp_locus, &rec->imputed);
         } else {
             const int32_t *g = NULL;
-            if (row->kind != ORC_CLASS_ABSENT && row->gt_row >= 0) {
-                if (row->kind != ORC_CLASS_FILTER)   /* a FILTER-failed record is never decoded (:553-558) */
-                    widen_row(wide, (const char *)j->gt + row->gt_row * j->row_stride, j->gt_width, n, j->ploidy);
+            if (row->kind == ORC_CLASS_FILTER) g = wide;      /* a FILTER-failed record is never decoded (:553-558) */
+            else if (row->kind != ORC_CLASS_ABSENT && row->gt_row >= 0) {
+                widen_row(wide, (const char *)j->gt + row->gt_row * j->row_stride, j->gt_width, n, j->ploidy);
                 g = wide;
             }
             used = locus_after_lookup(dos, n, g, j->ploidy, row->eaidx, row->kind == ORC_CLASS_FILTER, NULL,

@@ -50,10 +50,10 @@ def random_rows(rng, V, n_rows=None, n_alt=1, kinds=(0.8, 0.07, 0.07, 0.06), nan
     rows = np.zeros(n_rows, dtype=ROW_DTYPE)
     rows["kind"] = rng.choice(4, size=n_rows, p=kinds)
     g = rng.integers(0, max(V, 1), size=n_rows) if shuffle_gt else np.arange(n_rows) % max(V, 1)
-    rows["gt_row"] = np.where((rows["kind"] == 0) | (rows["kind"] == 3), g, -1)
+    rows["gt_row"] = np.where((rows["kind"] == 0) | ((rows["kind"] == 3) & (rng.random(n_rows) < 0.5)), g, -1)   # FILTER rows: with or without a slab row
     rows["ref_is_ea"] = rng.random(n_rows) < 0.27
     rows["eaidx"] = np.where(rows["ref_is_ea"] == 1, 0, rng.integers(1, n_alt + 1, size=n_rows))
-    rows["eaidx"] = np.where(rows["gt_row"] < 0, -1, rows["eaidx"])
+    rows["eaidx"] = np.where((rows["gt_row"] < 0) & (rows["kind"] != 3), -1, rows["eaidx"])
     rows["beta"] = np.round(rng.normal(0, 0.05, size=n_rows), 4)
     rows["eaf"] = np.round(rng.uniform(0.01, 0.5, size=n_rows), 4)
     rows["eaf"][rng.random(n_rows) < nan_eaf_rate] = np.nan
