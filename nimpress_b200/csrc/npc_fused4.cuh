@@ -124,27 +124,42 @@ k_fused_tile4(const FusedParams P) {
 
     if (warp == NC) {
         // ================= producer ============================================================
+        // Row metadata is read 32 rows (8 tiles) at a time, one row per lane, and the NEXT group is
+        // already in flight while this one is issued: a dependent global load per tile would cap the
+        // producer at one tile per memory round trip, far below the ring's appetite.
         const uint64_t pol = l2_evict_first_policy();
+        constexpr int G = 32 / R;                                    // tiles per metadata group
         int s = 0; uint32_t ph = 0;
-        for (int64_t t = 0; t < n_tiles; t++) {
-            mbar_wait(bar_rempty + 8u * s, ph ^ 1u);
-            const int nr = (int)min((int64_t)R, P.n_rows - t * R);
-            npc_row row;
-            bool is_gt = false;
-            if (lane < nr) {
-                row = P.rows[t * R + lane];
-                is_gt = row.kind == NPC_KIND_GT && row.gt_row >= 0;
+        npc_row nxt;
+        {
+            const int64_t r = lane;
+            if (r < P.n_rows) nxt = P.rows[r];
+        }
+        for (int64_t t0 = 0; t0 < n_tiles; t0 += G) {
+            const npc_row cur = nxt;
+            const int64_t my_row = t0 * R + lane;
+            const bool have = my_row < P.n_rows;
+            {
+                const int64_t r = my_row + 32;
+                if (r < P.n_rows) nxt = P.rows[r];
             }
-            if (lane < R) s_reaidx[s * R + lane] = is_gt ? row.eaidx : 0;
-            const uint32_t gt_mask = __ballot_sync(0xffffffffu, is_gt);
-            if (lane == 0) s_risgt[s] = gt_mask;
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)__popc(gt_mask) * slab_bytes);
-            __syncwarp();
-            if (is_gt)
-                tma_load_1d(sb + M.data + (uint32_t)(s * R + lane) * (uint32_t)P.slab_stride,
-                            P.gt + (int64_t)row.gt_row * P.row_stride + c0 * 16, slab_bytes, bar_full + 8u * s, pol);
-            if (++s == Sr) { s = 0; ph ^= 1u; }
+            const bool is_gt = have && cur.kind == NPC_KIND_GT && cur.gt_row >= 0;
+            const uint32_t gt_all = __ballot_sync(0xffffffffu, is_gt);
+            const int ng = (int)min((int64_t)G, n_tiles - t0);
+            for (int j = 0; j < ng; j++) {
+                mbar_wait(bar_rempty + 8u * s, ph ^ 1u);
+                const uint32_t gt_mask = (gt_all >> (R * j)) & ((1u << R) - 1u);
+                const bool mine = (lane / R) == j;                   // lanes R*j .. R*j+R-1 own this tile's rows
+                if (mine) s_reaidx[s * R + (lane % R)] = is_gt ? cur.eaidx : 0;
+                if (lane == 0) s_risgt[s] = gt_mask;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)__popc(gt_mask) * slab_bytes);
+                __syncwarp();
+                if (mine && is_gt)
+                    tma_load_1d(sb + M.data + (uint32_t)(s * R + (lane % R)) * (uint32_t)P.slab_stride,
+                                P.gt + (int64_t)cur.gt_row * P.row_stride + c0 * 16, slab_bytes, bar_full + 8u * s, pol);
+                if (++s == Sr) { s = 0; ph ^= 1u; }
+            }
         }
     } else if (warp == NC + 1) {
         // ================= publisher ===========================================================
@@ -171,13 +186,16 @@ k_fused_tile4(const FusedParams P) {
             const int s = (int)(t % Sc);
             const int nr = (int)min((int64_t)R, P.n_rows - t * R);
             int used = 0;
+            npc_row row;
+            if (lane < nr) row = P.rows[t * R + lane];                   // in flight while we wait
+            // the grid cannot have arrived before this CTA has: sleep on the local barrier first
+            mbar_wait(bar_cnt + 8u * s, (uint32_t)((t / Sc) & 1));
             if (lane < R) {
                 double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;             // a dropped row adds +0.0: the identity
                 if (lane < nr) {
-                    const npc_row row = P.rows[t * R + lane];            // in flight while we poll
                     const ull *word = P.counts + t * R + lane;
                     ull v = ld_relaxed_gpu_u64(word);
-                    while ((v >> 56) != (ull)gridDim.x) { __nanosleep(200); v = ld_relaxed_gpu_u64(word); }
+                    while ((v >> 56) != (ull)gridDim.x) { __nanosleep(500); v = ld_relaxed_gpu_u64(word); }
                     RowP rp; npc_locus rec;
                     decide_row(P.pol, row, (v >> FUSED_CNT_BITS) & FUSED_CNT_MASK, v & FUSED_CNT_MASK, P.n, rp, rec);
                     used = rec.used;

@@ -315,3 +315,53 @@ def test_kernel_paths_agree(nb, env, monkeypatch):
         got = eng.finish(offset=0.5)
         eng.close()
         assert_parity(got, want, exact=exact)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_full_sample_width_500k(nb, mode):
+    """BASELINE.json configs[2] at its full sample width (500,000 samples, the launch shape bench.py
+    times: 148 CTAs x 14 consumer warps) on 1,024 variants of the synthetic cohort generated ON THE
+    DEVICE (npc_synth_fill_device), against the oracle on the host-generated copy of the same cohort."""
+    import torch
+    n, V, seed = 500_000, 1024, 0x6E696D70
+    rng = np.random.default_rng(seed)
+    af = rng.uniform(0.01, 0.5, size=V)
+    af_thr = (af * 65536).astype(np.uint32)
+    ms_thr = (rng.uniform(0, 0.1, size=V) * (1 << 24)).astype(np.uint32)      # per-locus missing rate U(0, 10%): half exceed --maxmis
+    alt = np.ones(V, np.int32)
+    stride = -(-2 * n // 128) * 128
+    host = np.zeros((V, stride), np.int8)
+    orc.synth_fill(host, n, 0, seed, af_thr, ms_thr, alt)
+    rows = random_rows(rng, V, n_rows=V, kinds=(0.85, 0.05, 0.05, 0.05), shuffle_gt=False)
+    want = oracle(host, n, rows, offset=0.0)
+    eng = nb.Engine(n, max_rows_per_block=V)
+    eng.set_policy(); eng.set_exact_order(mode == "exact"); eng.reset()
+    d = torch.empty((V, stride), dtype=torch.uint8, device="cuda")
+    eng.synth_fill_device(d, stride, 0, V, seed, torch.from_numpy(af_thr.view(np.int32)).cuda(),
+                          torch.from_numpy(ms_thr.view(np.int32)).cuda(), torch.from_numpy(alt).cuda())
+    eng.score_block_device(d, stride, V, rows)
+    got = eng.finish()
+    shape = eng.kernel_shape
+    eng.close()
+    assert shape["grid"] == 148 and shape["fused"] == (1 if mode == "exact" else 2)
+    assert (want["loci"]["klass"] == orc.CLASS_MAXMIS).sum() > 100 and (want["loci"]["klass"] == orc.CLASS_OK).sum() > 100
+    assert_parity(got, want, exact=mode == "exact")
+
+
+@pytest.mark.parametrize("imp_locus,maxmis", [("ps", 0.05), ("homref", 0.02), ("fail", 1.0)])
+def test_config5_policies_50k(nb, imp_locus, maxmis):
+    """BASELINE.json configs[4]: 50,000 samples x 10,000 loci, per-locus missing rate U(0, 10%), 10% of
+    records FILTER-failed, 5% of score rows absent, 30% not covered; --imp-locus x --maxmis with the
+    default --imp-sample int_ps.  Per-locus records bit-equal, scores within 1e-12 (default kernel)."""
+    n, V, seed = 50_000, 10_000, 0x6E696D70
+    rng = np.random.default_rng(seed + 5)
+    af = rng.uniform(0.01, 0.5, size=V)
+    stride = -(-2 * n // 128) * 128
+    host = np.zeros((V, stride), np.int8)
+    orc.synth_fill(host, n, 0, seed, (af * 65536).astype(np.uint32), (rng.uniform(0, 0.1, size=V) * (1 << 24)).astype(np.uint32),
+                   np.ones(V, np.int32))
+    rows = random_rows(rng, V, n_rows=V, kinds=(0.55, 0.30, 0.05, 0.10), shuffle_gt=False)
+    pol = dict(imp_locus=imp_locus, maxmis=maxmis)
+    want = oracle(host, n, rows, policy=pol)
+    got = run_engine(nb, host, n, rows, policy=pol, staged=False, mode="tile4")
+    assert_parity(got, want, exact=False)

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest -m gpu" ; timeout 1800 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+B="python bench.py --variants 32768 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --brief"
+echo "== default (tile4)"; timeout 200 $B 2>&1 | tail -1 | tee gpurun_out/sweep7.log
+echo "== exact"; NPC_EXACT=1 timeout 200 $B 2>&1 | tail -1 | tee -a gpurun_out/sweep7.log
+for cfg in "2 0 0 4" "3 0 0 4" "4 12 0 4" "4 0 0 2" "4 0 0 1" "6 8 0 3"; do set -- $cfg
+  echo "== FAST SR=$1 SC=$2 L=$3 A=$4"; NPC_FAST_SR=$1 NPC_FAST_SC=$2 NPC_FAST_L=$3 NPC_FAST_A=$4 timeout 200 $B 2>&1 | tail -1
+done 2>&1 | tee -a gpurun_out/sweep7.log
+echo "== ncu full tile4"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_fused_tile4' -s 2 -c 1 -o gpurun_out/prof_tile4_r3 -f \
+    python bench.py --variants 8192 --steps 1 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/ncu_fused.log 2>&1
+tail -1 gpurun_out/ncu_fused.log
