@@ -138,15 +138,16 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     c->fused_ok = true;
     // 4-row-tile kernel: raw ring ~80 KB, the rest of shared memory is index-ring slots
     {
-        int qSr = env_int("NPC_FAST_SR", 0), qSc = env_int("NPC_FAST_SC", 0), qL = env_int("NPC_FAST_L", 0), qA = env_int("NPC_FAST_A", 4);
+        int qSr = env_int("NPC_FAST_SR", 0), qSc = env_int("NPC_FAST_SC", 0), qL = env_int("NPC_FAST_L", 0), qA = env_int("NPC_FAST_A", 2);
         if (qSr <= 0) qSr = std::max(2, std::min(8, (112 * 1024) / (F4_R * c->f_slab)));
         if (qSc <= 0) {
             qSc = 32;
             while (qSc > 2 && (int)Fused4Smem::make(qSr, qSc, c->f_slab).total > max_smem) qSc--;
         }
         while (qSr > 2 && (int)Fused4Smem::make(qSr, qSc, c->f_slab).total > max_smem) qSr--;
-        if ((int)Fused4Smem::make(qSr, qSc, c->f_slab).total <= max_smem && qSc >= 2 && env_int("NPC_FAST", 1) != 0) {
-            if (qL <= 0 || qL > qSc - 1) qL = qSc - 1;
+        // deciders work on groups of 8 tiles: the lag must cover a whole group
+        if ((int)Fused4Smem::make(qSr, qSc, c->f_slab).total <= max_smem && qSc >= 10 && env_int("NPC_FAST", 1) != 0) {
+            if (qL <= 8 || qL > qSc - 1) qL = qSc - 1;
             c->q_Sr = qSr; c->q_Sc = qSc; c->q_L = qL; c->q_A = std::max(1, std::min(6, qA));
             c->q_smem = Fused4Smem::make(qSr, qSc, c->f_slab).total;
             const void *fn = K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;

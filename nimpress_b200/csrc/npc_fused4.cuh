@@ -41,7 +41,7 @@ struct Fused4Smem {
         m.code = o;   o += F4_CODE_TABLES * 256u;                        // first: 256-byte aligned
         m.tt = o;     o += 256u * 4u;
         m.vtab = o;   o += (uint32_t)Sc * 256u;                          // 256-byte aligned: T01 at +0, T23 at +128
-        m.vrow = o;   o += 8u * 16u * 8u;                                // per decider warp: 4 rows x 4 values
+        m.vrow = o;   o += 6u * 128u * 8u;                               // per decider warp: 32 rows x 4 values
         m.bars = o;   o += (2u * Sr + 2u * Sc) * 8u;            o = (o + 127u) & ~127u;
         m.cntacc = o; o += (uint32_t)Sc * F4_R * 16u * 4u;      o = (o + 127u) & ~127u;
         m.cisgt = o;  o += (uint32_t)Sc * 4u;                   o = (o + 127u) & ~127u;
@@ -180,43 +180,56 @@ k_fused_tile4(const FusedParams P) {
         }
     } else if (warp > NC + 1) {
         // ================= deciders ============================================================
+        // One pass decides a GROUP of 8 tiles = 32 rows, one row per lane: the global round trip of
+        // the tally word (microseconds under load) is paid once per 8 tiles, not once per tile.
+        // Groups rotate over the A decider warps.
         const int a = warp - NC - 2;
-        double *vrow = reinterpret_cast<double *>(smem + M.vrow) + a * 16;      // [row][code]
-        for (int64_t t = a; t < n_tiles; t += A) {
-            const int s = (int)(t % Sc);
-            const int nr = (int)min((int64_t)R, P.n_rows - t * R);
-            int used = 0;
+        constexpr int GD = 32 / R;                                   // tiles per group
+        double *vrow = reinterpret_cast<double *>(smem + M.vrow) + a * 128;      // [row in group][code]
+        const int64_t n_groups = (n_tiles + GD - 1) / GD;
+        for (int64_t g = a; g < n_groups; g += A) {
+            const int64_t t0 = g * GD;
+            const int ng = (int)min((int64_t)GD, n_tiles - t0);
+            const int64_t my_row = t0 * R + lane;
+            const bool have = my_row < P.n_rows;
             npc_row row;
-            if (lane < nr) row = P.rows[t * R + lane];                   // in flight while we wait
-            // the grid cannot have arrived before this CTA has: sleep on the local barrier first
-            mbar_wait(bar_cnt + 8u * s, (uint32_t)((t / Sc) & 1));
-            if (lane < R) {
-                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;             // a dropped row adds +0.0: the identity
-                if (lane < nr) {
-                    const ull *word = P.counts + t * R + lane;
-                    ull v = ld_relaxed_gpu_u64(word);
-                    while ((v >> 56) != (ull)gridDim.x) { __nanosleep(500); v = ld_relaxed_gpu_u64(word); }
-                    RowP rp; npc_locus rec;
-                    decide_row(P.pol, row, (v >> FUSED_CNT_BITS) & FUSED_CNT_MASK, v & FUSED_CNT_MASK, P.n, rp, rec);
-                    used = rec.used;
-                    if (blockIdx.x == 0) P.log[t * R + lane] = rec;
-                    if (rp.mode == MODE_DECODE) { v0 = rp.c0; v1 = rp.c1; v2 = rp.c2; v3 = rp.cm; }
-                    else if (rp.mode == MODE_CONST) { v0 = v1 = v2 = v3 = rp.c0; }
-                }
-                vrow[lane * 4 + 0] = v0; vrow[lane * 4 + 1] = v1; vrow[lane * 4 + 2] = v2; vrow[lane * 4 + 3] = v3;
+            if (have) row = P.rows[my_row];                          // in flight while we wait
+            // the grid cannot have arrived before this CTA has: sleep on the local barrier of the
+            // group's last tile first (tiles are counted in order)
+            {
+                const int64_t tl = t0 + ng - 1;
+                mbar_wait(bar_cnt + 8u * (uint32_t)(tl % Sc), (uint32_t)((tl / Sc) & 1));
             }
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // a dropped row adds +0.0: the identity
+            int used = 0;
+            if (have) {
+                const ull *word = P.counts + my_row;
+                ull v = ld_relaxed_gpu_u64(word);
+                while ((v >> 56) != (ull)gridDim.x) { __nanosleep(500); v = ld_relaxed_gpu_u64(word); }
+                RowP rp; npc_locus rec;
+                decide_row(P.pol, row, (v >> FUSED_CNT_BITS) & FUSED_CNT_MASK, v & FUSED_CNT_MASK, P.n, rp, rec);
+                used = rec.used;
+                if (blockIdx.x == 0) P.log[my_row] = rec;
+                if (rp.mode == MODE_DECODE) { v0 = rp.c0; v1 = rp.c1; v2 = rp.c2; v3 = rp.cm; }
+                else if (rp.mode == MODE_CONST) { v0 = v1 = v2 = v3 = rp.c0; }
+            }
+            vrow[lane * 4 + 0] = v0; vrow[lane * 4 + 1] = v1; vrow[lane * 4 + 2] = v2; vrow[lane * 4 + 3] = v3;
             if (blockIdx.x == 0) {
                 used = __reduce_add_sync(0xffffffffu, used);
                 if (lane == 0 && used) atomicAdd(P.nloci, (ull)used);
             }
             __syncwarp();
-            {   // lanes 0..15: T01[lane] = v0[lane&3] + v1[lane>>2]; lanes 16..31: T23 likewise from rows 2, 3
+            // per tile: lanes 0..15 build T01[lane] = v0[lane&3] + v1[lane>>2], lanes 16..31 T23 from rows 2, 3
+            const int h = lane >> 4, e = lane & 15;
+            for (int j = 0; j < ng; j++) {
+                const int s = (int)((t0 + j) % Sc);
                 double *tab = reinterpret_cast<double *>(smem + M.vtab) + s * 32;
-                const int h = lane >> 4, e = lane & 15;
-                tab[lane] = __dadd_rn(vrow[8 * h + (e & 3)], vrow[8 * h + 4 + (e >> 2)]);
+                const double *vr = vrow + (j * R + 2 * h) * 4;
+                tab[lane] = __dadd_rn(vr[e & 3], vr[4 + (e >> 2)]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_lut + 8u * s);
+            if (lane < ng) mbar_arrive(bar_lut + 8u * (uint32_t)((t0 + lane) % Sc));
+            __syncwarp();
         }
     } else {
         // ================= consumers ===========================================================

@@ -62,6 +62,8 @@ def main():
             if not s:
                 continue
             op = s.split()[1] if s.startswith("@") and len(s.split()) > 1 else s.split()[0]
+            if not (r[iex] or "0").isdigit():
+                continue                                  # repeated header of the next kernel's listing
             ex = int(r[iex] or 0)
             mix[op.split(".")[0]] += ex
             if iw is not None and r[iw]:
@@ -69,7 +71,7 @@ def main():
         tot = sum(mix.values())
         div = base or 1.0
         unit = "per unit (--base)" if base else "total"
-        print(f"\n## executed warp-instructions, last kernel, {unit}: {tot / div:.1f}")
+        print(f"\n## executed warp-instructions (all kernels of the report), {unit}: {tot / div:.1f}")
         print(", ".join(f"{k} {v / div:.2f}" for k, v in mix.most_common(24)))
         if wf:
             print(f"## shared-memory wavefronts {unit} (actual / ideal): total {sum(wf.values()) / div:.2f} / {sum(wfi.values()) / div:.2f}")
