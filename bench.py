@@ -239,11 +239,19 @@ def b200_arm(args):
     t_sums = torch.as_tensor(_Wrap(sums_ptr, (n,), "<f8"), device=dev)
     t_nloci = torch.as_tensor(_Wrap(nloci_ptr, (1,), "<i8"), device=dev)
 
-    def step():
+    launch_events = []                                  # (start, end, rows) of every scoring launch of the timed steps
+
+    def step(timed=False):
         eng.reset()
         for r0 in range(0, V, block_rows):
             nr = min(block_rows, V - r0)
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
             eng.score_block_device(gt[r0], stride, nr, d_rows[r0], n_rows=nr)
+            if timed:
+                e1.record(stream)
+                launch_events.append((e0, e1, nr))
         if world > 1:                                  # combine: gather partials, add in rank order (NCCL over NVLink)
             return shard.combine_partials(t_sums, t_nloci)
         return t_sums, t_nloci
@@ -264,7 +272,7 @@ def b200_arm(args):
     barrier()
     ev[0].record(stream)
     for i in range(args.steps):
-        total, nl = step()
+        total, nl = step(timed=True)
         ev[i + 1].record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -279,20 +287,32 @@ def b200_arm(args):
     value = genotypes_step / (ms_step * 1e-3)
     assert int(nl.item()) == V * world, (int(nl.item()), V * world)
 
-    # roofline of the scoring kernels of one rank: algorithmic bytes
-    n_blocks = -(-V // block_rows)
-    alg_bytes = 2.0 * n * V + 32.0 * V + 16.0 * n * n_blocks
+    # roofline of the dominant kernel on this rank: algorithmic bytes per launch (SURVEY.md 8d:
+    # 2 B per genotype + 32 B per row + 16 B per sample per launch) / mean duration of the full-size
+    # launches, measured with CUDA events on the launching stream inside the timed region
+    full = [(a.elapsed_time(b), r) for a, b, r in launch_events if r == min(block_rows, V)]
+    launch_ms = float(np.mean([t for t, _ in full]))
+    launch_rows = full[0][1]
+    alg_bytes = 2.0 * n * launch_rows + 32.0 * launch_rows + 16.0 * n
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")          # dram bytes of one ncu --set full capture of this launch shape
+    if os.path.exists(tpath):
+        for t in json.load(open(tpath)):
+            if t["samples"] == n and t["rows"] == launch_rows and t["fused"] == shape["fused"]:
+                traffic, traffic_src = t["dram_bytes"], t["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "kernel": ("k_fused_i8x2 (count+decide+accumulate, one persistent launch per block)" if shape["fused"]
-                           else "k_count_i8x2 + k_decide + k_accum_i8x2 sequence (all launches of a step)"),
-                "algorithmic_bytes_per_step": alg_bytes}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "launch_ms": launch_ms, "rows_per_launch": launch_rows, "launches_per_step": len(launch_events) // args.steps,
+                "kernel": {2: "k_fused_tile4 (count+decide+accumulate, one persistent launch per block)",
+                           1: "k_fused_i8x2 (exact-order fused kernel, one persistent launch per block)",
+                           0: "k_count_i8x2 + k_decide + k_accum_i8x2 sequence"}[shape["fused"]],
+                "algorithmic_bytes_per_launch": alg_bytes}
 
     # end to end through the staged C-ABI call with host buffers
     e2e = None
@@ -358,7 +378,7 @@ def b200_arm(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if args.brief:
-            print(f"{value:.4e} genotypes/s  frac={roofline['frac']:.3f}  ms={ms_step:.3f}  {shape}")
+            print(f"{value:.4e} genotypes/s  frac={roofline['frac']:.3f}  ms={ms_step:.3f} launch_ms={launch_ms:.3f}  {shape}")
         else:
             print(json.dumps(line))
     eng.close()

@@ -262,28 +262,53 @@ k_fused_tile4(const FusedParams P) {
                 for (int k = 0; k < K; k++)
 #pragma unroll
                     for (int e = 0; e < 8; e++) B[k][e] = 0;
+                // bits 8.. of each row's (T, r) code table address; a PRMT puts the folded sample byte below it
+                int ea4[R];
+                uint32_t thi4[R];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    if (!((gt_mask >> r) & 1u)) continue;
-                    const int ea = s_reaidx[sr * R + r];
-                    // bits 8.. of the (T, r) code table's address; a PRMT puts the folded sample byte below it
-                    const uint32_t thi = code_hi + (uint32_t)min(ea, (int)FUSED_CNT_TABLES - 1) * R + r;
+                    ea4[r] = s_reaidx[sr * R + r];
+                    thi4[r] = code_hi + (uint32_t)min(ea4[r], (int)FUSED_CNT_TABLES - 1) * R + r;
+                }
 #pragma unroll
-                    for (int k = 0; k < K; k++) {
-                        const uint4 w = lds_v4(d0 + r * slab + cell[k] * 16u);
-                        if (((((w.x | w.y) | (w.z | w.w)) & 0xF0F0F0F0u) | tailor[k]) == 0u) {
-                            const uint32_t f[4] = { fold_nibbles(w.x), fold_nibbles(w.y), fold_nibbles(w.z), fold_nibbles(w.w) };
+                for (int k = 0; k < K; k++) {
+                    uint4 w[R];
+                    uint32_t hi_bits = tailor[k];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {                // all loads of the tile first: 4 independent LDS.128
+                        w[r] = lds_v4(d0 + r * slab + cell[k] * 16u);
+                        hi_bits |= ((w[r].x | w[r].y) | (w[r].z | w[r].w)) & 0xF0F0F0F0u;
+                    }
+                    if (gt_mask == (1u << R) - 1u && hi_bits == 0u) {
+                        // common case, straight line: every row has genotypes and all 64 bytes are < 16:
+                        // 16 folds, 32 PRMT-composed addresses, 32 independent one-byte lookups
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const uint32_t f[4] = { fold_nibbles(w[r].x), fold_nibbles(w[r].y), fold_nibbles(w[r].z), fold_nibbles(w[r].w) };
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                B[k][2 * e] |= lds_u8(__byte_perm(f[e], thi, 0x6540));
-                                B[k][2 * e + 1] |= lds_u8(__byte_perm(f[e], thi, 0x6542));
+                                B[k][2 * e] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6540));
+                                B[k][2 * e + 1] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6542));
                             }
-                        } else {
-                            const int vk = own[k] ? valid[k] : 8;
-                            const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+                        }
+                    } else {
 #pragma unroll
-                            for (int e = 0; e < 8; e++)
-                                if (e < vk) B[k][e] |= f4_slow_code((ww[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu, ea) << (2 * r);
+                        for (int r = 0; r < R; r++) {
+                            if (!((gt_mask >> r) & 1u)) continue;
+                            if (((((w[r].x | w[r].y) | (w[r].z | w[r].w)) & 0xF0F0F0F0u) | tailor[k]) == 0u) {
+                                const uint32_t f[4] = { fold_nibbles(w[r].x), fold_nibbles(w[r].y), fold_nibbles(w[r].z), fold_nibbles(w[r].w) };
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    B[k][2 * e] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6540));
+                                    B[k][2 * e + 1] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6542));
+                                }
+                            } else {
+                                const int vk = own[k] ? valid[k] : 8;
+                                const uint32_t ww[4] = { w[r].x, w[r].y, w[r].z, w[r].w };
+#pragma unroll
+                                for (int e = 0; e < 8; e++)
+                                    if (e < vk) B[k][e] |= f4_slow_code((ww[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu, ea4[r]) << (2 * r);
+                            }
                         }
                     }
                 }
