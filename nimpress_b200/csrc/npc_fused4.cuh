@@ -3,13 +3,13 @@
 // byte read from HBM once) restructured around TILES OF FOUR SCORE ROWS so that the per-genotype
 // instruction and shared-memory cost drops by about 40%:
 //
-//  * COUNT.  A sample's two raw GT bytes (both < 16 on the fast path) are folded into one byte
-//    b0 | b1<<4 with a single IMAD.HI per word, and a PRMT composes that byte with the
-//    (effect allele, row-in-tile) table number into a complete shared-memory address: one
-//    LDS.U8 returns the sample's 2-bit dosage code {0,1,2,3=missing} already shifted to the row's
-//    position.  OR-ing the four rows gives ONE byte per sample per tile.
-//  * The tile's tallies come from that byte through a row-independent 256-entry table
-//    (per row: dosage | missing<<4, summed over 4 samples per register), once per tile.
+//  * COUNT.  A sample's two raw GT bytes (both < 8 on the fast path: alleles REF, ALT1, ALT2 or
+//    missing) are folded into one byte 2*(b0 | b1<<3) with two integer ops per word, and a PRMT
+//    composes that byte with the (effect allele, row-in-tile) table number into a complete
+//    shared-memory address: one LDS.U16 returns BOTH the sample's 2-bit dosage code
+//    {0,1,2,3=missing}, already shifted to the row's position (high byte), AND its tally
+//    contribution dosage | missing<<4 (low byte).  OR-ing the four rows gives ONE code byte per
+//    sample per tile; adding the entries of 4 samples gives the row's tallies -- no second table.
 //  * The index ring therefore holds 1 byte per sample per 4 rows (1/8 of the raw data): the
 //    grid-wide dependency (see npc_fused.cuh) can lag by dozens of rows at no cost.
 //  * DECIDE builds, per tile, two 16-entry fp64 tables T01[b0|b1<<2] = v0[b0]+v1[b1] and
@@ -31,15 +31,14 @@
 namespace npc {
 
 constexpr int F4_R = 4;                                  // rows per tile
-constexpr uint32_t F4_CODE_TABLES = FUSED_CNT_TABLES * F4_R;   // (T, row-in-tile) -> 256 one-byte entries
+constexpr uint32_t F4_CODE_TABLES = FUSED_CNT_TABLES * F4_R;   // (T, row-in-tile) -> 64 two-byte entries in a 256-byte slot
 
 struct Fused4Smem {
-    uint32_t code, tt, vrow, bars, cntacc, cisgt, risgt, reaidx, vtab, idx, data, total;
+    uint32_t code, vrow, bars, cntacc, cisgt, risgt, reaidx, vtab, idx, data, total;
     __host__ __device__ static Fused4Smem make(int Sr, int Sc, int slab_stride) {
         Fused4Smem m;
         uint32_t o = 0;
         m.code = o;   o += F4_CODE_TABLES * 256u;                        // first: 256-byte aligned
-        m.tt = o;     o += 256u * 4u;
         m.vtab = o;   o += (uint32_t)Sc * 256u;                          // 256-byte aligned: T01 at +0, T23 at +128
         m.vrow = o;   o += 6u * 128u * 8u;                               // per decider warp: 32 rows x 4 values
         m.bars = o;   o += (2u * Sr + 2u * Sc) * 8u;            o = (o + 127u) & ~127u;
@@ -72,8 +71,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-// w + (w >> 4) in one FMA-pipe op: byte 0 = b0 | b1<<4, byte 2 = b2 | b3<<4 when every byte < 16
-__device__ __forceinline__ uint32_t fold_nibbles(uint32_t w) { return __umulhi(w, 0x10000000u) + w; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// (w << 1) + (w >> 4): byte 0 = 2*(b0 | b1<<3), byte 2 = 2*(b2 | b3<<3) when every byte < 8 -- the
+// byte offset of the sample's two-byte table entry
+__device__ __forceinline__ uint32_t fold_offsets(uint32_t w) { return (w << 1) + (w >> 4); }
 
 template <int K>
 __global__ void __launch_bounds__(768, 1)
@@ -103,19 +108,11 @@ k_fused_tile4(const FusedParams P) {
         for (int s = 0; s < Sc; s++) { mbar_init(bar_cnt + 8u * s, NC); mbar_init(bar_lut + 8u * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // code tables: [T-1][row r][byte b0 | b1<<4] = dosage code << 2r
-    for (uint32_t i = threadIdx.x; i < F4_CODE_TABLES * 256u; i += blockDim.x) {
-        const int b = i & 255, r = (i >> 8) & 3, T = (int)(i >> 10) + 1;
-        smem[M.code + i] = (uint8_t)(f4_code_from_nibbles(b & 15, b >> 4, T) << (2 * r));
-    }
-    // tally table: byte of four codes -> per row (dosage | missing << 4) in byte r
-    for (uint32_t b = threadIdx.x; b < 256u; b += blockDim.x) {
-        uint32_t v = 0;
-        for (int r = 0; r < 4; r++) {
-            const uint32_t c = (b >> (2 * r)) & 3u;
-            v |= (c == 3u ? 16u : c) << (8 * r);
-        }
-        reinterpret_cast<uint32_t *>(smem + M.tt)[b] = v;
+    // tables: [T-1][row r][b0 | b1<<3] (two bytes each) = dosage code << (8 + 2r) | dosage | missing << 4
+    for (uint32_t i = threadIdx.x; i < F4_CODE_TABLES * 64u; i += blockDim.x) {
+        const int idx = i & 63, r = (i >> 6) & 3, T = (int)(i >> 8) + 1;
+        const int c = f4_code_from_nibbles(idx & 7, idx >> 3, T);
+        reinterpret_cast<uint16_t *>(smem + M.code)[(i >> 6) * 128 + idx] = (uint16_t)((c << (8 + 2 * r)) | (c == 3 ? 16 : c));
     }
     for (uint32_t i = threadIdx.x; i < (uint32_t)Sr * R * (uint32_t)P.slab_stride / 16u; i += blockDim.x)
         reinterpret_cast<uint4 *>(smem + M.data)[i] = make_uint4(0, 0, 0, 0);
@@ -248,7 +245,7 @@ k_fused_tile4(const FusedParams P) {
             for (int e = 0; e < 8; e++) acc[k][e] = e < valid[k] ? P.sums[g * 8 + e] : 0.0;
         }
         const uint32_t slab = (uint32_t)P.slab_stride, islab = slab >> 1;
-        const uint32_t code_hi = (sb + M.code) >> 8, tt0 = sb + M.tt;
+        const uint32_t code_hi = (sb + M.code) >> 8;
         const int nt = (int)n_tiles;
         int sr = 0, sc = 0, sa = 0;
         uint32_t ph_r = 0, ph_a = 0;
@@ -257,12 +254,7 @@ k_fused_tile4(const FusedParams P) {
                 mbar_wait(bar_full + 8u * sr, ph_r);
                 const uint32_t gt_mask = s_risgt[sr];
                 const uint32_t d0 = sb + M.data + (uint32_t)(sr * R) * slab;
-                uint32_t B[K][8];                                // per sample: the four rows' codes, 2 bits each
-#pragma unroll
-                for (int k = 0; k < K; k++)
-#pragma unroll
-                    for (int e = 0; e < 8; e++) B[k][e] = 0;
-                // bits 8.. of each row's (T, r) code table address; a PRMT puts the folded sample byte below it
+                // bits 8.. of each row's (T, r) table address; a PRMT puts the sample's entry offset below it
                 int ea4[R];
                 uint32_t thi4[R];
 #pragma unroll
@@ -270,70 +262,85 @@ k_fused_tile4(const FusedParams P) {
                     ea4[r] = s_reaidx[sr * R + r];
                     thi4[r] = code_hi + (uint32_t)min(ea4[r], (int)FUSED_CNT_TABLES - 1) * R + r;
                 }
+                uint32_t d02 = 0, d13 = 0, m02 = 0, m13 = 0;     // tallies: rows (0,2) / (1,3) in 16-bit halves
 #pragma unroll
                 for (int k = 0; k < K; k++) {
+                    uint32_t B[8];                               // per sample: OR of the rows' entries; byte 1 = four 2-bit codes
+                    uint32_t TA[R], TB[R];                       // per row: sum of the entries of samples 0-3 / 4-7;
+                                                                 // bits 0-3 = effect alleles, bits 4-6 = missing samples
+#pragma unroll
+                    for (int e = 0; e < 8; e++) B[e] = 0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) TA[r] = TB[r] = 0;
                     uint4 w[R];
                     uint32_t hi_bits = tailor[k];
 #pragma unroll
                     for (int r = 0; r < R; r++) {                // all loads of the tile first: 4 independent LDS.128
                         w[r] = lds_v4(d0 + r * slab + cell[k] * 16u);
-                        hi_bits |= ((w[r].x | w[r].y) | (w[r].z | w[r].w)) & 0xF0F0F0F0u;
+                        hi_bits |= ((w[r].x | w[r].y) | (w[r].z | w[r].w)) & 0xF8F8F8F8u;
                     }
                     if (gt_mask == (1u << R) - 1u && hi_bits == 0u) {
-                        // common case, straight line: every row has genotypes and all 64 bytes are < 16:
-                        // 16 folds, 32 PRMT-composed addresses, 32 independent one-byte lookups
+                        // common case, straight line: every row has genotypes and all 64 bytes are < 8:
+                        // 16 folds, 32 PRMT-composed addresses, 32 independent two-byte lookups
 #pragma unroll
                         for (int r = 0; r < R; r++) {
-                            const uint32_t f[4] = { fold_nibbles(w[r].x), fold_nibbles(w[r].y), fold_nibbles(w[r].z), fold_nibbles(w[r].w) };
+                            const uint32_t f[4] = { fold_offsets(w[r].x), fold_offsets(w[r].y), fold_offsets(w[r].z), fold_offsets(w[r].w) };
+                            uint32_t v[8];
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                B[k][2 * e] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6540));
-                                B[k][2 * e + 1] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6542));
+                                v[2 * e] = lds_u16(__byte_perm(f[e], thi4[r], 0x6540));
+                                v[2 * e + 1] = lds_u16(__byte_perm(f[e], thi4[r], 0x6542));
                             }
+#pragma unroll
+                            for (int e = 0; e < 8; e++) B[e] |= v[e];
+                            TA[r] = (v[0] + v[1]) + (v[2] + v[3]);
+                            TB[r] = (v[4] + v[5]) + (v[6] + v[7]);
                         }
                     } else {
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             if (!((gt_mask >> r) & 1u)) continue;
-                            if (((((w[r].x | w[r].y) | (w[r].z | w[r].w)) & 0xF0F0F0F0u) | tailor[k]) == 0u) {
-                                const uint32_t f[4] = { fold_nibbles(w[r].x), fold_nibbles(w[r].y), fold_nibbles(w[r].z), fold_nibbles(w[r].w) };
+                            uint32_t v[8];
+                            if (((((w[r].x | w[r].y) | (w[r].z | w[r].w)) & 0xF8F8F8F8u) | tailor[k]) == 0u) {
+                                const uint32_t f[4] = { fold_offsets(w[r].x), fold_offsets(w[r].y), fold_offsets(w[r].z), fold_offsets(w[r].w) };
 #pragma unroll
                                 for (int e = 0; e < 4; e++) {
-                                    B[k][2 * e] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6540));
-                                    B[k][2 * e + 1] |= lds_u8(__byte_perm(f[e], thi4[r], 0x6542));
+                                    v[2 * e] = lds_u16(__byte_perm(f[e], thi4[r], 0x6540));
+                                    v[2 * e + 1] = lds_u16(__byte_perm(f[e], thi4[r], 0x6542));
                                 }
-                            } else {
+                            } else {                             // exact decode, same entry format
                                 const int vk = own[k] ? valid[k] : 8;
                                 const uint32_t ww[4] = { w[r].x, w[r].y, w[r].z, w[r].w };
 #pragma unroll
-                                for (int e = 0; e < 8; e++)
-                                    if (e < vk) B[k][e] |= f4_slow_code((ww[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu, ea4[r]) << (2 * r);
+                                for (int e = 0; e < 8; e++) {
+                                    const uint32_t c = e < vk ? f4_slow_code((ww[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu, ea4[r]) : 0u;
+                                    v[e] = (c << (8 + 2 * r)) | (c == 3u ? 16u : c);
+                                }
                             }
+#pragma unroll
+                            for (int e = 0; e < 8; e++) B[e] |= v[e];
+                            TA[r] = (v[0] + v[1]) + (v[2] + v[3]);
+                            TB[r] = (v[4] + v[5]) + (v[6] + v[7]);
                         }
                     }
+                    // the tile's code bytes (byte 1 of each B) -> index ring
+                    const uint32_t x = __byte_perm(__byte_perm(B[0], B[1], 0x0051), __byte_perm(B[2], B[3], 0x0051), 0x5410);
+                    const uint32_t y = __byte_perm(__byte_perm(B[4], B[5], 0x0051), __byte_perm(B[6], B[7], 0x0051), 0x5410);
+                    sts_v2(sb + M.idx + (uint32_t)sc * islab + cell[k] * 8u, x, y);
+                    // tallies: byte 0 of each sum is clean (<= 72), byte 3 is zero: PRMT pairs rows into 16-bit halves
+                    const uint32_t a02 = __byte_perm(TA[0], TA[2], 0x7430), b02 = __byte_perm(TB[0], TB[2], 0x7430);
+                    const uint32_t a13 = __byte_perm(TA[1], TA[3], 0x7430), b13 = __byte_perm(TB[1], TB[3], 0x7430);
+                    d02 += ((a02 & 0x000F000Fu) + (b02 & 0x000F000Fu)) & own[k];
+                    d13 += ((a13 & 0x000F000Fu) + (b13 & 0x000F000Fu)) & own[k];
+                    m02 += (((a02 >> 4) & 0x00070007u) + ((b02 >> 4) & 0x00070007u)) & own[k];
+                    m13 += (((a13 >> 4) & 0x00070007u) + ((b13 >> 4) & 0x00070007u)) & own[k];
                 }
                 // raw stage fully read
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_rempty + 8u * sr);
-                // tile tallies from the code bytes (row-independent table), then one store of the bytes
-                uint32_t dd = 0, mm = 0;                         // per row in byte r: effect alleles / missing samples
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    uint32_t ta = 0, tb = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        ta += lds_u32(tt0 + (B[k][e] << 2));
-                        tb += lds_u32(tt0 + (B[k][4 + e] << 2));
-                    }
-                    dd += ((ta & 0x0F0F0F0Fu) + (tb & 0x0F0F0F0Fu)) & own[k];
-                    mm += (((ta >> 4) & 0x07070707u) + ((tb >> 4) & 0x07070707u)) & own[k];
-                    const uint32_t x = B[k][0] | (B[k][1] << 8) | (B[k][2] << 16) | (B[k][3] << 24);
-                    const uint32_t y = B[k][4] | (B[k][5] << 8) | (B[k][6] << 16) | (B[k][7] << 24);
-                    sts_v2(sb + M.idx + (uint32_t)sc * islab + cell[k] * 8u, x, y);
-                }
-                {   // rows (0,2) and (1,3) share a register as 16-bit halves: sums over the warp stay below 2^16
-                    const uint32_t d02 = __reduce_add_sync(0xffffffffu, dd & 0x00FF00FFu), d13 = __reduce_add_sync(0xffffffffu, (dd >> 8) & 0x00FF00FFu);
-                    const uint32_t m02 = __reduce_add_sync(0xffffffffu, mm & 0x00FF00FFu), m13 = __reduce_add_sync(0xffffffffu, (mm >> 8) & 0x00FF00FFu);
+                {   // sums over the warp stay below 2^16 per half
+                    d02 = __reduce_add_sync(0xffffffffu, d02); d13 = __reduce_add_sync(0xffffffffu, d13);
+                    m02 = __reduce_add_sync(0xffffffffu, m02); m13 = __reduce_add_sync(0xffffffffu, m13);
                     if (lane == 0) {
                         uint32_t *p = &s_cntacc[(sc * R) * 16 + warp];
                         p[0] = (d02 & 0xFFFFu) | (m02 << 16);
