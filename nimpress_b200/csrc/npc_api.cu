@@ -148,7 +148,7 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         // deciders work on groups of 8 tiles: the lag must cover a whole group
         if ((int)Fused4Smem::make(qSr, qSc, c->f_slab).total <= max_smem && qSc >= 10 && env_int("NPC_FAST", 1) != 0) {
             if (qL <= 8 || qL > qSc - 1) qL = qSc - 1;
-            c->q_Sr = qSr; c->q_Sc = qSc; c->q_L = qL; c->q_A = std::max(1, std::min(6, qA));
+            c->q_Sr = qSr; c->q_Sc = qSc; c->q_L = qL; c->q_A = std::max(1, std::min(2, qA));
             c->q_smem = Fused4Smem::make(qSr, qSc, c->f_slab).total;
             const void *fn = K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
             cudaError_t e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem);

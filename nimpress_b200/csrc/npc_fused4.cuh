@@ -78,10 +78,15 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 }
 // (w << 1) + (w >> 4): byte 0 = 2*(b0 | b1<<3), byte 2 = 2*(b2 | b3<<3) when every byte < 8 -- the
 // byte offset of the sample's two-byte table entry
-__device__ __forceinline__ uint32_t fold_offsets(uint32_t w) { return (w << 1) + (w >> 4); }
+__device__ __forceinline__ uint32_t fold_offsets(uint32_t w) {
+    uint32_t t, f;                                   // both on the FMA pipe (the ALU pipe is the busy one)
+    asm("mad.hi.u32 %0, %1, 0x10000000, 0;" : "=r"(t) : "r"(w));
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(f) : "r"(w), "r"(t));
+    return f;
+}
 
 template <int K>
-__global__ void __launch_bounds__(768, 1)
+__global__ void __launch_bounds__(640, 1)         // <= 16 consumer warps + producer + publisher + <= 2 deciders
 k_fused_tile4(const FusedParams P) {
     constexpr int R = F4_R;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -281,20 +286,26 @@ k_fused_tile4(const FusedParams P) {
                     }
                     if (gt_mask == (1u << R) - 1u && hi_bits == 0u) {
                         // common case, straight line: every row has genotypes and all 64 bytes are < 8:
-                        // 16 folds, 32 PRMT-composed addresses, 32 independent two-byte lookups
+                        // 16 folds, 32 PRMT-composed addresses, 32 independent two-byte lookups.  Entries
+                        // of different rows are merged by ADDITION, two rows per IADD3: code bits are
+                        // disjoint and the tally bytes (<= 16 each) cannot carry into them.
 #pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const uint32_t f[4] = { fold_offsets(w[r].x), fold_offsets(w[r].y), fold_offsets(w[r].z), fold_offsets(w[r].w) };
-                            uint32_t v[8];
+                        for (int p2 = 0; p2 < R; p2 += 2) {
+                            uint32_t v[2][8];
 #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                v[2 * e] = lds_u16(__byte_perm(f[e], thi4[r], 0x6540));
-                                v[2 * e + 1] = lds_u16(__byte_perm(f[e], thi4[r], 0x6542));
+                            for (int q = 0; q < 2; q++) {
+                                const int r = p2 + q;
+                                const uint32_t f[4] = { fold_offsets(w[r].x), fold_offsets(w[r].y), fold_offsets(w[r].z), fold_offsets(w[r].w) };
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    v[q][2 * e] = lds_u16(__byte_perm(f[e], thi4[r], 0x6540));
+                                    v[q][2 * e + 1] = lds_u16(__byte_perm(f[e], thi4[r], 0x6542));
+                                }
+                                TA[r] = (v[q][0] + v[q][1]) + (v[q][2] + v[q][3]);
+                                TB[r] = (v[q][4] + v[q][5]) + (v[q][6] + v[q][7]);
                             }
 #pragma unroll
-                            for (int e = 0; e < 8; e++) B[e] |= v[e];
-                            TA[r] = (v[0] + v[1]) + (v[2] + v[3]);
-                            TB[r] = (v[4] + v[5]) + (v[6] + v[7]);
+                            for (int e = 0; e < 8; e++) B[e] = B[e] + v[0][e] + v[1][e];
                         }
                     } else {
 #pragma unroll

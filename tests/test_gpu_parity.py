@@ -282,7 +282,7 @@ def test_config2_shape_wood_100k(nb, mode):
                                  dict(NPC_EXACT="1", NPC_FUSED_R="8", NPC_FUSED_SR="3", NPC_FUSED_SC="5", NPC_FUSED_L="3"),
                                  dict(NPC_EXACT="1", NPC_FUSED_K="2", NPC_FUSED_R="3", NPC_FUSED_A="6"),
                                  dict(NPC_FAST="0"), dict(NPC_FAST_SR="2", NPC_FAST_SC="10", NPC_FAST_A="1"),
-                                 dict(NPC_FAST_SR="5", NPC_FAST_SC="13", NPC_FAST_L="9", NPC_FAST_A="6"), dict(NPC_FUSED_K="2")],
+                                 dict(NPC_FAST_SR="5", NPC_FAST_SC="13", NPC_FAST_L="9", NPC_FAST_A="2"), dict(NPC_FUSED_K="2")],
                          ids=lambda e: ",".join(f"{k[4:]}={v}" for k, v in e.items()))
 def test_kernel_paths_agree(nb, env, monkeypatch):
     """Every kernel path and launch shape gives the oracle's per-locus records; the exact-order
