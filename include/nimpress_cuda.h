@@ -198,7 +198,8 @@ int npc_set_exact_order(npc_ctx *ctx, int32_t on);
 
 /* Which kernels npc_score_block* uses for this context: shape[0] = 2 for the 4-row-tile fused
  * kernel, 1 for the exact-order fused kernel (int8 diploid cohorts that fit one resident pass),
- * 0 for the count/decide/accumulate sequence; then grid, consumer warps, chunks per thread, rows
+ * 0 for the count/decide/accumulate sequence; then grid (tile kernel: sample slabs * 1000 + row
+ * groups), consumer warps, chunks per thread, rows
  * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + decider warps, dynamic
  * shared-memory bytes. */
 int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);

@@ -41,8 +41,10 @@ struct npc_ctx {
     bool exact = false;                     // npc_set_exact_order
     int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 2, f_Sr = 4, f_Sc = 8, f_L = 7, f_A = 4, f_slab = 0;
     uint32_t f_smem = 0;
-    int q_Sr = 3, q_Sc = 16, q_L = 15, q_A = 4;   // launch shape of the 4-row-tile kernel
+    int q_Sr = 3, q_Sc = 16, q_L = 15, q_A = 2;   // launch shape of the 4-row-tile kernel
+    int q_Gs = 1, q_Gr = 1, q_K = 1, q_nc = 1, q_slab = 0;   // its grid: sample slabs x (max) row groups
     uint32_t q_smem = 0;
+    double *d_partials = nullptr;           // [q_Gr - 1][n] partial sums of row groups 1..
     uint8_t *d_slab = nullptr;              // resident slab (npc_resident_reserve)
     int64_t slab_rows = 0;
     cudaEvent_t ev_slab = nullptr;          // last scoring launch that read the slab
@@ -78,7 +80,7 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_slab);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_slab); cudaFree(ctx->d_partials);
     if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -136,23 +138,46 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
     c->fused_ok = true;
-    // 4-row-tile kernel: raw ring ~80 KB, the rest of shared memory is index-ring slots
+    // 4-row-tile kernel.  Grid = Gs sample slabs x Gr row groups: a cohort too small to give every SM
+    // ~14 consumer warps from the sample axis alone (< ~500k samples) also splits the rows into
+    // contiguous groups whose partial sums are added in group order afterwards.
     {
+        int best_gr = 1; double best = -1.0;
+        const int force_gr = env_int("NPC_FAST_GR", 0);
+        for (int gr = 1; gr <= 16; gr++) {
+            const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
+            if (gs < 1) break;
+            const int64_t nchq = (C + gs - 1) / gs;
+            const int kq = nchq <= 512 ? 1 : 2;
+            const int64_t ncq = (nchq + 32 * kq - 1) / (32 * kq);
+            if (ncq > 16) continue;
+            const double score = (double)gs * gr * std::min<int64_t>(ncq * kq, 14) * ((double)nchq / (double)(ncq * 32 * kq));
+            if (force_gr ? gr == force_gr : score > best * 1.08) { best = score; best_gr = gr; }
+        }
+        const int gr = best_gr;
+        const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
+        const int64_t nchq = (C + gs - 1) / gs;
+        int kq = env_int("NPC_FUSED_K", 0);
+        if (kq != 1 && kq != 2) kq = nchq <= 512 ? 1 : 2;
+        const int64_t ncq = (nchq + 32 * kq - 1) / (32 * kq);
+        const int slabq = (int)(ncq * 32 * kq * 16);
         int qSr = env_int("NPC_FAST_SR", 0), qSc = env_int("NPC_FAST_SC", 0), qL = env_int("NPC_FAST_L", 0), qA = env_int("NPC_FAST_A", 2);
-        if (qSr <= 0) qSr = std::max(2, std::min(8, (112 * 1024) / (F4_R * c->f_slab)));
+        if (qSr <= 0) qSr = std::max(2, std::min(8, (112 * 1024) / (F4_R * slabq)));
         if (qSc <= 0) {
             qSc = 32;
-            while (qSc > 2 && (int)Fused4Smem::make(qSr, qSc, c->f_slab).total > max_smem) qSc--;
+            while (qSc > 2 && (int)Fused4Smem::make(qSr, qSc, slabq).total > max_smem) qSc--;
         }
-        while (qSr > 2 && (int)Fused4Smem::make(qSr, qSc, c->f_slab).total > max_smem) qSr--;
+        while (qSr > 2 && (int)Fused4Smem::make(qSr, qSc, slabq).total > max_smem) qSr--;
         // deciders work on groups of 8 tiles: the lag must cover a whole group
-        if ((int)Fused4Smem::make(qSr, qSc, c->f_slab).total <= max_smem && qSc >= 10 && env_int("NPC_FAST", 1) != 0) {
+        if (ncq <= 16 && (int)Fused4Smem::make(qSr, qSc, slabq).total <= max_smem && qSc >= 10 && env_int("NPC_FAST", 1) != 0) {
             if (qL <= 8 || qL > qSc - 1) qL = qSc - 1;
             c->q_Sr = qSr; c->q_Sc = qSc; c->q_L = qL; c->q_A = std::max(1, std::min(2, qA));
-            c->q_smem = Fused4Smem::make(qSr, qSc, c->f_slab).total;
-            const void *fn = K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
+            c->q_Gs = gs; c->q_Gr = gr; c->q_K = kq; c->q_nc = (int)ncq; c->q_slab = slabq;
+            c->q_smem = Fused4Smem::make(qSr, qSc, slabq).total;
+            const void *fn = kq == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
             cudaError_t e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem);
             if (e2 != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e2); return NPC_ECUDA; }
+            if (gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(gr - 1) * (size_t)c->n * sizeof(double)));
             c->fast_ok = true;
         }
     }
@@ -262,6 +287,7 @@ extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     const bool fast = ctx->fused_ok && ctx->fast_ok && !ctx->exact;
     shape[0] = !ctx->fused_ok ? 0 : fast ? 2 : 1; shape[1] = ctx->f_grid; shape[2] = ctx->f_nc; shape[3] = ctx->f_K;
     if (fast) {
+        shape[1] = ctx->q_Gs * 1000 + ctx->q_Gr; shape[2] = ctx->q_nc; shape[3] = ctx->q_K;
         shape[4] = F4_R; shape[5] = ctx->q_Sr * 1000 + ctx->q_Sc; shape[6] = ctx->q_L * 100 + ctx->q_A; shape[7] = (int32_t)ctx->q_smem;
     } else {
         shape[4] = ctx->f_R; shape[5] = ctx->f_Sr * 1000 + ctx->f_Sc; shape[6] = ctx->f_L * 100 + ctx->f_A; shape[7] = (int32_t)ctx->f_smem;
@@ -364,14 +390,22 @@ static int launch_fused(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
     P.sums = c->d_sums; P.counts = c->d_fcounts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
-    P.nc = c->f_nc; P.slab_stride = c->f_slab;
     void *args[] = { &P };
-    const dim3 grid(c->f_grid);
     if (c->fast_ok && !c->exact) {
+        const int64_t tiles = (n_rows + F4_R - 1) / F4_R;
+        const int gr = (int)std::max<int64_t>(1, std::min<int64_t>(c->q_Gr, tiles / 16));   // >= 16 tiles per row group
+        P.nc = c->q_nc; P.slab_stride = c->q_slab; P.Gs = c->q_Gs; P.Gr = gr; P.partials = c->d_partials;
         P.Sr = c->q_Sr; P.Sc = c->q_Sc; P.L = c->q_L; P.A = c->q_A;
-        const void *fn = c->f_K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
-        NPC_CUDA(c, cudaLaunchCooperativeKernel(fn, grid, dim3((c->f_nc + 2 + c->q_A) * 32), args, c->q_smem, c->stream));
+        const void *fn = c->q_K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
+        NPC_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->q_Gs * gr), dim3((c->q_nc + 2 + c->q_A) * 32), args, c->q_smem, c->stream));
+        if (gr > 1) {
+            k_add_partials<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_sums, c->d_partials, c->n, gr - 1);
+            c->launches++;
+            NPC_CUDA(c, cudaGetLastError());
+        }
     } else {
+        const dim3 grid(c->f_grid);
+        P.nc = c->f_nc; P.slab_stride = c->f_slab; P.Gs = c->f_grid; P.Gr = 1; P.partials = nullptr;
         P.Sr = c->f_Sr; P.Sc = c->f_Sc; P.L = c->f_L; P.A = c->f_A;
         NPC_CUDA(c, cudaLaunchCooperativeKernel((const void *)fused_kernel(c->f_K, c->f_R), grid, dim3((c->f_nc + 2 + c->f_A) * 32), args,
                                                 c->f_smem, c->stream));

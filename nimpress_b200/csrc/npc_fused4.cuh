@@ -100,12 +100,17 @@ k_fused_tile4(const FusedParams P) {
     int32_t *s_reaidx = reinterpret_cast<int32_t *>(smem + M.reaidx);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles = (P.n_rows + R - 1) / R;
+    // grid = Gs sample slabs x Gr row groups: this CTA owns chunk range `slab` of the sample axis and
+    // the contiguous tile range [tile_lo, tile_lo + n_tiles) of the rows
+    const int Gs = P.Gs, slab_id = (int)blockIdx.x % Gs, grp = (int)blockIdx.x / Gs;
+    const int64_t all_tiles = (P.n_rows + R - 1) / R;
+    const int64_t tile_lo = all_tiles * grp / P.Gr, n_tiles = all_tiles * (grp + 1) / P.Gr - tile_lo;
+    const int64_t row_lo = tile_lo * R;
 
     const int64_t C = (P.n + 7) >> 3;
-    const int64_t q = C / gridDim.x, rem = C % gridDim.x;
-    const int64_t c0 = (int64_t)blockIdx.x * q + min((int64_t)blockIdx.x, rem);
-    const int nch = (int)(q + ((int64_t)blockIdx.x < rem ? 1 : 0));
+    const int64_t q = C / Gs, rem = C % Gs;
+    const int64_t c0 = (int64_t)slab_id * q + min((int64_t)slab_id, rem);
+    const int nch = (int)(q + ((int64_t)slab_id < rem ? 1 : 0));
     const uint32_t slab_bytes = (uint32_t)nch * 16u;
 
     if (threadIdx.x == 0) {
@@ -132,18 +137,19 @@ k_fused_tile4(const FusedParams P) {
         const uint64_t pol = l2_evict_first_policy();
         constexpr int G = 32 / R;                                    // tiles per metadata group
         int s = 0; uint32_t ph = 0;
+        const int64_t row_hi = min(P.n_rows, (tile_lo + n_tiles) * R);      // this group's rows: [row_lo, row_hi)
         npc_row nxt;
         {
-            const int64_t r = lane;
-            if (r < P.n_rows) nxt = P.rows[r];
+            const int64_t r = row_lo + lane;
+            if (r < row_hi) nxt = P.rows[r];
         }
         for (int64_t t0 = 0; t0 < n_tiles; t0 += G) {
             const npc_row cur = nxt;
-            const int64_t my_row = t0 * R + lane;
-            const bool have = my_row < P.n_rows;
+            const int64_t my_row = row_lo + t0 * R + lane;
+            const bool have = my_row < row_hi;
             {
                 const int64_t r = my_row + 32;
-                if (r < P.n_rows) nxt = P.rows[r];
+                if (r < row_hi) nxt = P.rows[r];
             }
             const bool is_gt = have && cur.kind == NPC_KIND_GT && cur.gt_row >= 0;
             const uint32_t gt_all = __ballot_sync(0xffffffffu, is_gt);
@@ -168,7 +174,7 @@ k_fused_tile4(const FusedParams P) {
         int s = 0; uint32_t ph = 0;
         for (int64_t t = 0; t < n_tiles; t++) {
             mbar_wait(bar_cnt + 8u * s, ph);
-            const int nr = (int)min((int64_t)R, P.n_rows - t * R);
+            const int nr = (int)min((int64_t)R, P.n_rows - (tile_lo + t) * R);
             if (lane < nr) {
                 ull miss = 0, eff = 0;
                 if ((s_cisgt[s] >> lane) & 1u)
@@ -176,7 +182,7 @@ k_fused_tile4(const FusedParams P) {
                         const uint32_t v = s_cntacc[(s * R + lane) * 16 + w];
                         miss += v >> 16; eff += v & 0xFFFFu;
                     }
-                red_relaxed_gpu_add_u64(P.counts + t * R + lane, (1ull << 56) | (miss << FUSED_CNT_BITS) | eff);
+                red_relaxed_gpu_add_u64(P.counts + (tile_lo + t) * R + lane, (1ull << 56) | (miss << FUSED_CNT_BITS) | eff);
             }
             if (++s == Sc) { s = 0; ph ^= 1u; }
         }
@@ -192,8 +198,8 @@ k_fused_tile4(const FusedParams P) {
         for (int64_t g = a; g < n_groups; g += A) {
             const int64_t t0 = g * GD;
             const int ng = (int)min((int64_t)GD, n_tiles - t0);
-            const int64_t my_row = t0 * R + lane;
-            const bool have = my_row < P.n_rows;
+            const int64_t my_row = (tile_lo + t0) * R + lane;
+            const bool have = lane < ng * R && my_row < P.n_rows;
             npc_row row;
             if (have) row = P.rows[my_row];                          // in flight while we wait
             // the grid cannot have arrived before this CTA has: sleep on the local barrier of the
@@ -207,16 +213,16 @@ k_fused_tile4(const FusedParams P) {
             if (have) {
                 const ull *word = P.counts + my_row;
                 ull v = ld_relaxed_gpu_u64(word);
-                while ((v >> 56) != (ull)gridDim.x) { __nanosleep(500); v = ld_relaxed_gpu_u64(word); }
+                while ((v >> 56) != (ull)Gs) { __nanosleep(500); v = ld_relaxed_gpu_u64(word); }      // all slabs of this row group
                 RowP rp; npc_locus rec;
                 decide_row(P.pol, row, (v >> FUSED_CNT_BITS) & FUSED_CNT_MASK, v & FUSED_CNT_MASK, P.n, rp, rec);
                 used = rec.used;
-                if (blockIdx.x == 0) P.log[my_row] = rec;
+                if (slab_id == 0) P.log[my_row] = rec;
                 if (rp.mode == MODE_DECODE) { v0 = rp.c0; v1 = rp.c1; v2 = rp.c2; v3 = rp.cm; }
                 else if (rp.mode == MODE_CONST) { v0 = v1 = v2 = v3 = rp.c0; }
             }
             vrow[lane * 4 + 0] = v0; vrow[lane * 4 + 1] = v1; vrow[lane * 4 + 2] = v2; vrow[lane * 4 + 3] = v3;
-            if (blockIdx.x == 0) {
+            if (slab_id == 0) {
                 used = __reduce_add_sync(0xffffffffu, used);
                 if (lane == 0 && used) atomicAdd(P.nloci, (ull)used);
             }
@@ -247,8 +253,9 @@ k_fused_tile4(const FusedParams P) {
             own[k] = jc < nch ? 0xFFFFFFFFu : 0u;
             tailor[k] = (jc < nch && valid[k] < 8) ? 0xF0u : 0u;
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[k][e] = e < valid[k] ? P.sums[g * 8 + e] : 0.0;
+            for (int e = 0; e < 8; e++) acc[k][e] = (e < valid[k] && grp == 0) ? P.sums[g * 8 + e] : 0.0;
         }
+        double *sums_out = grp == 0 ? P.sums : P.partials + (int64_t)(grp - 1) * P.n;
         const uint32_t slab = (uint32_t)P.slab_stride, islab = slab >> 1;
         const uint32_t code_hi = (sb + M.code) >> 8;
         const int nt = (int)n_tiles;
@@ -394,9 +401,18 @@ k_fused_tile4(const FusedParams P) {
             const int64_t g = c0 + cell[k];
 #pragma unroll
             for (int e = 0; e < 8; e++)
-                if (e < valid[k]) P.sums[g * 8 + e] = acc[k][e];
+                if (e < valid[k]) sums_out[g * 8 + e] = acc[k][e];
         }
     }
+}
+
+// sums[s] = ((sums[s] + p0[s]) + p1[s]) + ...: the row groups' partial sums, in group (= row) order
+__global__ void k_add_partials(double *__restrict__ sums, const double *__restrict__ partials, int64_t n, int n_partials) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double a = sums[s];
+    for (int g = 0; g < n_partials; g++) a = __dadd_rn(a, partials[(int64_t)g * n + s]);
+    sums[s] = a;
 }
 
 }  // namespace npc
