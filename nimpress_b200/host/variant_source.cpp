@@ -1,9 +1,13 @@
 #include "variant_source.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
+#include <condition_variable>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace nph {
@@ -12,7 +16,137 @@ namespace nph {
 // InflateStream
 // ------------------------------------------------------------------------------------------
 
+// ------------------------------------------------------------------------------------------
+// BgzfPool: a reader thread cuts the file into BGZF blocks (18-byte header, BSIZE in the `BC`
+// extra field), worker threads inflate them (raw deflate, independent streams), the consumer takes
+// them in file order from a ring of slots.
+// ------------------------------------------------------------------------------------------
+
+class BgzfPool {
+public:
+    BgzfPool(FILE *fp, int n_workers) : fp_(fp), ring_((size_t)n_workers * 4) {
+        reader_ = std::thread([this] { read_loop(); });
+        for (int i = 0; i < n_workers; i++) workers_.emplace_back([this] { work_loop(); });
+    }
+    ~BgzfPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_job_.notify_all(); cv_free_.notify_all(); cv_done_.notify_all();
+        reader_.join();
+        for (auto &t : workers_) t.join();
+    }
+    // next inflated block, in order; false at end of file.  The returned buffer stays valid until the next call.
+    bool next(const uint8_t *&data, size_t &len) {
+        std::unique_lock<std::mutex> g(m_);
+        if (held_) { ring_[(rd_ - 1) % ring_.size()].state = FREE; held_ = false; cv_free_.notify_all(); }
+        for (;;) {
+            Slot &s = ring_[rd_ % ring_.size()];
+            if (rd_ < wr_ && s.state == DONE) {
+                if (!s.error.empty()) throw InputError(s.error);
+                data = s.out.data(); len = s.out_len; rd_++; held_ = true;
+                return true;
+            }
+            if (eof_ && rd_ == wr_) { if (!error_.empty()) throw InputError(error_); return false; }
+            cv_done_.wait(g);
+        }
+    }
+private:
+    enum { FREE = 0, QUEUED = 1, BUSY = 2, DONE = 3 };
+    struct Slot { std::vector<uint8_t> in, out; size_t in_len = 0, out_len = 0; int state = FREE; std::string error; };
+    void read_loop() {
+        for (;;) {
+            size_t idx;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_free_.wait(g, [this] { return stop_ || ring_[wr_ % ring_.size()].state == FREE; });
+                if (stop_) return;
+                idx = wr_ % ring_.size();
+            }
+            Slot &s = ring_[idx];
+            uint8_t hdr[18];
+            size_t got = fread(hdr, 1, 18, fp_);
+            std::string err;
+            size_t bsize = 0;
+            if (got == 0) { finish(""); return; }
+            if (got != 18 || hdr[0] != 0x1f || hdr[1] != 0x8b || !(hdr[3] & 4) || hdr[12] != 'B' || hdr[13] != 'C')
+                err = "BGZF: malformed block header";
+            else {
+                bsize = (size_t)(hdr[16] | (hdr[17] << 8)) + 1;
+                const size_t xlen = (size_t)(hdr[10] | (hdr[11] << 8));
+                if (bsize < 12 + xlen + 8) err = "BGZF: bad block size";
+                else {
+                    const size_t rest = bsize - 18;                 // remaining extra fields + deflate data + CRC32 + ISIZE
+                    if (s.in.size() < rest) s.in.resize(std::max<size_t>(rest, 1 << 16));
+                    if (fread(s.in.data(), 1, rest, fp_) != rest) err = "BGZF: truncated block";
+                    else {
+                        const size_t skip = xlen - 6;               // extra subfields beyond BC
+                        s.in_len = rest; s.out_len = skip;          // out_len doubles as the payload offset for the worker
+                    }
+                }
+            }
+            if (!err.empty()) { finish(err); return; }
+            {
+                std::lock_guard<std::mutex> g(m_);
+                s.state = QUEUED; s.error.clear(); wr_++;
+            }
+            cv_job_.notify_one();
+        }
+    }
+    void finish(const std::string &err) {
+        std::lock_guard<std::mutex> g(m_);
+        eof_ = true; error_ = err;
+        cv_done_.notify_all(); cv_job_.notify_all();
+    }
+    void work_loop() {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        inflateInit2(&zs, -15);
+        for (;;) {
+            Slot *s = nullptr;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                for (;;) {
+                    if (stop_) { inflateEnd(&zs); return; }
+                    for (size_t k = job_; k < wr_; k++)
+                        if (ring_[k % ring_.size()].state == QUEUED) { s = &ring_[k % ring_.size()]; s->state = BUSY; if (k == job_) job_++; break; }
+                    if (s) break;
+                    while (job_ < wr_ && ring_[job_ % ring_.size()].state != QUEUED) job_++;
+                    if (job_ < wr_) continue;
+                    if (eof_) { inflateEnd(&zs); return; }
+                    cv_job_.wait(g);
+                }
+            }
+            const size_t off = s->out_len, tail = 8;
+            uint32_t isize;
+            memcpy(&isize, s->in.data() + s->in_len - 4, 4);
+            if (s->out.size() < isize) s->out.resize(std::max<size_t>(isize, 1 << 16));
+            inflateReset(&zs);
+            zs.next_in = s->in.data() + off; zs.avail_in = (uInt)(s->in_len - off - tail);
+            zs.next_out = s->out.data(); zs.avail_out = (uInt)s->out.size();
+            const int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+            std::string err;
+            if (rc != Z_STREAM_END || zs.total_out != isize) err = "BGZF: corrupt deflate data";
+            {
+                std::lock_guard<std::mutex> g(m_);
+                s->out_len = isize; s->error = err; s->state = DONE;
+            }
+            cv_done_.notify_all();
+        }
+    }
+    FILE *fp_;
+    std::vector<Slot> ring_;
+    std::mutex m_;
+    std::condition_variable cv_job_, cv_free_, cv_done_;
+    size_t wr_ = 0, rd_ = 0, job_ = 0;
+    bool eof_ = false, stop_ = false, held_ = false;
+    std::string error_;
+    std::thread reader_;
+    std::vector<std::thread> workers_;
+};
+
+InflateStream::InflateStream() = default;
+
 InflateStream::~InflateStream() {
+    pool_.reset();
     if (zinit_) inflateEnd(&zs_);
     if (fp_) fclose(fp_);
 }
@@ -20,12 +154,20 @@ InflateStream::~InflateStream() {
 bool InflateStream::open(const std::string &path) {
     fp_ = fopen(path.c_str(), "rb");
     if (!fp_) return false;
+    unsigned char magic[18] = { 0 };
+    size_t got = fread(magic, 1, 18, fp_);
+    fseek(fp_, 0, SEEK_SET);
+    compressed_ = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    const bool bgzf = got == 18 && compressed_ && (magic[3] & 4) && magic[12] == 'B' && magic[13] == 'C';
+    int want = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char *e = getenv("NIMPRESS_THREADS")) if (*e) want = std::max(1, atoi(e));
+    if (bgzf && want > 1) {
+        threads_ = want;
+        pool_ = std::make_unique<BgzfPool>(fp_, want);
+        return true;
+    }
     in_.resize(1 << 20);
     out_.resize(4 << 20);
-    unsigned char magic[2] = { 0, 0 };
-    size_t got = fread(magic, 1, 2, fp_);
-    fseek(fp_, 0, SEEK_SET);
-    compressed_ = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     if (compressed_) {
         memset(&zs_, 0, sizeof zs_);
         if (inflateInit2(&zs_, 15 + 16) != Z_OK) return false;
@@ -37,6 +179,14 @@ bool InflateStream::open(const std::string &path) {
 bool InflateStream::fill() {
     out_pos_ = out_len_ = 0;
     if (eof_) return false;
+    if (pool_) {                                      // blocks arrive inflated, in order; empty blocks (EOF marker) are skipped
+        const uint8_t *d; size_t l;
+        do {
+            if (!pool_->next(d, l)) { eof_ = true; return false; }
+        } while (l == 0);
+        pool_data_ = d; out_len_ = l;
+        return true;
+    }
     if (!compressed_) {
         out_len_ = fread(out_.data(), 1, out_.size(), fp_);
         if (out_len_ == 0) eof_ = true;
@@ -66,7 +216,7 @@ size_t InflateStream::read(void *dst, size_t n) {
     while (done < n) {
         if (out_pos_ == out_len_ && !fill()) break;
         size_t k = std::min(n - done, out_len_ - out_pos_);
-        memcpy((uint8_t *)dst + done, out_.data() + out_pos_, k);
+        memcpy((uint8_t *)dst + done, cur() + out_pos_, k);
         out_pos_ += k;
         done += k;
     }
@@ -78,7 +228,7 @@ bool InflateStream::read_exact(void *dst, size_t n) { return read(dst, n) == n; 
 bool InflateStream::peek(void *dst, size_t n) {
     if (out_pos_ == out_len_ && !fill()) return false;
     if (out_len_ - out_pos_ < n) return false;        // only used at the very start of the stream
-    memcpy(dst, out_.data() + out_pos_, n);
+    memcpy(dst, cur() + out_pos_, n);
     return true;
 }
 
@@ -88,7 +238,7 @@ bool InflateStream::getline(std::string &line) {
     for (;;) {
         if (out_pos_ == out_len_ && !fill()) break;
         any = true;
-        const uint8_t *b = out_.data() + out_pos_;
+        const uint8_t *b = cur() + out_pos_;
         const uint8_t *nl = (const uint8_t *)memchr(b, '\n', out_len_ - out_pos_);
         if (nl) {
             line.append((const char *)b, nl - b);

@@ -17,15 +17,23 @@
 
 namespace nph {
 
-// Sequential byte stream over a plain / gzip / BGZF file (BGZF = concatenated gzip members).
+class BgzfPool;                                      // multi-threaded BGZF block inflater (variant_source.cpp)
+
+// Byte stream over a plain / gzip / BGZF file.  BGZF (concatenated <= 64 KiB gzip members with a
+// `BC` extra field giving each member's size) is inflated by a pool of worker threads, blocks
+// delivered in file order; plain gzip falls back to one sequential zlib stream.  This is the
+// replacement for htslib's bgzf reader (which the reference uses single-threaded, hts-nim's
+// default threads = 0).  NIMPRESS_THREADS sets the pool size (default: min(cores, 16); 1 = sequential).
 class InflateStream {
 public:
+    InflateStream();
     ~InflateStream();
     bool open(const std::string &path);
     size_t read(void *dst, size_t n);                 // up to n bytes; 0 at end of stream
     bool read_exact(void *dst, size_t n);
     bool getline(std::string &line);                  // strips \n and a preceding \r
     bool peek(void *dst, size_t n);                   // look ahead without consuming (n <= 64)
+    int threads() const { return threads_; }
 private:
     bool fill();
     FILE *fp_ = nullptr;
@@ -33,6 +41,10 @@ private:
     z_stream zs_{};
     std::vector<uint8_t> in_, out_;
     size_t out_pos_ = 0, out_len_ = 0;
+    const uint8_t *cur() const { return pool_ ? pool_data_ : out_.data(); }
+    std::unique_ptr<BgzfPool> pool_;
+    const uint8_t *pool_data_ = nullptr;
+    int threads_ = 1;
 };
 
 struct VariantRecord {

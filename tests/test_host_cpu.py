@@ -184,3 +184,31 @@ def test_input_errors(api, tmp_path):
     notvcf = os.path.join(str(tmp_path), "not.vcf")
     open(notvcf, "w").write("hello\n")
     assert plan(api, os.path.join(S1, "set1.score"), notvcf)[0] == -1
+
+
+def test_bgzf_thread_pool_equals_sequential(api, tmp_path, monkeypatch):
+    """Multi-block BGZF files (dozens of 64 KiB blocks) through the worker-pool inflater give the same
+    bytes as the sequential zlib stream, for BCF payloads and for VCF text."""
+    rng = np.random.default_rng(4)
+    d = make_dataset(str(tmp_path), rng, n=3000, V=240, with_traps=False)
+    assert os.path.getsize(d["bcf"]) > 300_000
+    outs = {}
+    for th in ("1", "2", "7"):
+        monkeypatch.setenv("NIMPRESS_THREADS", th)
+        a, n1, w1, p1 = read_gt(api, d["bcf"], 6016, max_records=400)
+        b, n2, w2, p2 = read_gt(api, d["vcf"], 6016, max_records=400)
+        assert np.array_equal(a, b) and len(a) == len(d["records"])
+        outs[th] = a
+        rc, kind, ea, n = plan(api, d["score"], d["bcf"])
+        assert rc == 0 and n == 3000
+    assert np.array_equal(outs["1"], outs["2"]) and np.array_equal(outs["1"], outs["7"])
+    want = np.stack([r["gt"].reshape(-1).view(np.uint8) for r in d["records"]])
+    assert np.array_equal(outs["7"][:, :6000], want)
+    # a truncated file is an input error, not a hang
+    bad = os.path.join(str(tmp_path), "trunc.bcf")
+    open(bad, "wb").write(open(d["bcf"], "rb").read()[:200_000])
+    monkeypatch.setenv("NIMPRESS_THREADS", "4")
+    L = api.load_host_library()
+    out = np.zeros((400, 6016), np.uint8)
+    nrec, ns, w, pl = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    assert L.nph_read_gt(os.fsencode(bad), out.ctypes.data, 6016, 400, C.byref(nrec), C.byref(ns), C.byref(w), C.byref(pl)) == -3
