@@ -1,7 +1,9 @@
 #include "driver.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <unordered_map>
@@ -89,6 +91,17 @@ void Matcher::finish() {
 
 namespace {
 
+// NIMPRESS_TIMING=1: phase wall times on stderr
+struct PhaseTimer {
+    bool on = getenv("NIMPRESS_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        auto now = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[nimpress timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 struct LayoutOverflow { int width, ploidy; };      // a matched record does not fit the context's GT layout
 
 // One pass over the genotype file with a fixed GT layout.  Throws LayoutOverflow when a matched
@@ -100,13 +113,19 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
     out = ScoreResult();
     out.samples = vcf.samples();
 
+    PhaseTimer timer;
     Matcher M(score, cov, p);
+    timer.mark("coverage + entry index");
     std::vector<int32_t> &kind = M.kind, &eaidx = M.eaidx;
     std::vector<int64_t> slab_row(nE, -1);
     std::vector<uint8_t> done(nE, 0);
     const int64_t n_lookup = M.n_lookup();
 
-    const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(4096, std::max<int64_t>(n_lookup, 1)));
+    // staging slots of ~32 MB: big enough for efficient H2D copies, small enough that pinning three
+    // of them does not dominate a short run (pinning costs ~1 ms per MB)
+    const int64_t row_bytes = std::max<int64_t>(16, n * ploidy * gt_width);
+    const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(4096, (32ll << 20) / row_bytes + 1),
+                                                                     std::max<int64_t>(n_lookup, 1)));
     Ctx ctx;
     npc_policy pol = { p.imp_locus, p.imp_missing, p.imp_sample, 0, p.mincs, p.maxmis };
     ctx.ck(npc_create(&ctx.h, p.device, n, ploidy, gt_width, block_rows, 3), "npc_create");
@@ -115,6 +134,7 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
     ctx.ck(npc_reset(ctx.h), "npc_reset");
     int64_t slab_cap = 0;
     ctx.ck(npc_resident_reserve(ctx.h, std::max<int64_t>(n_lookup, 1), &slab_cap), "npc_resident_reserve");
+    timer.mark("GPU context + buffers");
 
     std::vector<int64_t> submitted;                 // entry index of every row sent to the GPU, in order
     submitted.reserve(nE);
@@ -178,6 +198,7 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
         if (staged == block_rows) flush_stage();
     }
     M.finish();
+    timer.mark("stream + match + upload");
     score_round(true);
 
     // ---- results ------------------------------------------------------------------------------
@@ -188,6 +209,7 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
     if (nlog != (int64_t)submitted.size()) throw std::runtime_error("locus log length mismatch");
     out.loci.assign(nE, npc_locus());
     for (size_t k = 0; k < submitted.size(); k++) out.loci[submitted[k]] = log[k];
+    timer.mark("score + finish (GPU)");
 
     // ---- WARN lines, in the reference's order (:326, :527-530, :538-541, :554-557, :567-570, :575-579)
     std::string &w = out.warnings;
@@ -214,6 +236,7 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
                  std::to_string(n) + " samples.  This is highly unlikely given polygenic score EAF of " + format_float_nim(e.eaf) + "\n";
         }
     }
+    timer.mark("WARN lines (binomial tests)");
 }
 
 }  // namespace

@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=100_000)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "cli_config2.json"))
+    ap.add_argument("--timing", action="store_true", help="also print the CLI's phase timing (NIMPRESS_TIMING=1) for one run of each mode")
     args = ap.parse_args()
     n = args.samples
     score = os.path.join(ROOT, "tests", "golden", "scores", "wood-25282103-height.scores")
@@ -91,6 +92,12 @@ def main():
         res["runs"].append({"inflate_threads": threads or "default (min(cores,16))", "mode": "exact-order" if extra else "tile4 (default)",
                             "wall_s_best_of_3": best, "genotypes_per_s_from_disk": len(ents) * n / best,
                             "scores_match_oracle": True})
+    if args.timing:
+        for extra in (["--exact-order"], []):
+            for th in ("1", "16"):
+                env = dict(os.environ, NIMPRESS_TIMING="1", NIMPRESS_THREADS=th)
+                p = subprocess.run([exe, "--afmisp=0", *extra, score, bcf], capture_output=True, text=True, env=env)
+                print(f"--- {extra} threads={th}\n" + p.stderr, file=sys.stderr)
     res["bcf_write_s_python"] = t_write
     res["host_cores"] = os.cpu_count()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
