@@ -35,16 +35,17 @@ struct npc_ctx {
     Policy pol{};
     int64_t launches = 0;
     std::string err;
-    // fused persistent kernel (int8 diploid): launch shape fixed per context
-    bool fused_ok = false;                  // exact-order kernel (npc_fused.cuh) usable
-    bool fast_ok = false;                   // 4-row-tile kernel (npc_fused4.cuh) usable
-    bool exact = false;                     // npc_set_exact_order
-    int num_sms = 0, f_grid = 0, f_K = 1, f_nc = 0, f_R = 2, f_Sr = 4, f_Sc = 8, f_L = 7, f_A = 4, f_slab = 0;
-    uint32_t f_smem = 0;
-    int q_Sr = 3, q_Sc = 16, q_L = 15, q_A = 2;   // launch shape of the 4-row-tile kernel
-    int q_Gs = 1, q_Gr = 1, q_K = 1, q_nc = 1, q_slab = 0;   // its grid: sample slabs x (max) row groups
-    uint32_t q_smem = 0;
-    double *d_partials = nullptr;           // [q_Gr - 1][n] partial sums of row groups 1..
+    // fused tile kernel (int8 diploid): launch shapes fixed per context
+    struct TileCfg {
+        bool ok = false;
+        int Gs = 1, Gr = 1, K = 1, nc = 1, slab = 0, Sr = 3, Sc = 16, L = 15, A = 2;
+        uint32_t smem = 0;
+    };
+    TileCfg fast;                           // default: sample slabs x row groups, tile-wise summation
+    TileCfg exact_cfg;                      // npc_set_exact_order: 1-D grid, reference summation order
+    bool exact = false;
+    int num_sms = 0;
+    double *d_partials = nullptr;           // [fast.Gr - 1][n] partial sums of row groups 1..
     uint8_t *d_slab = nullptr;              // resident slab (npc_resident_reserve)
     int64_t slab_rows = 0;
     cudaEvent_t ev_slab = nullptr;          // last scoring launch that read the slab
@@ -92,95 +93,73 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-typedef void (*fused_fn)(const FusedParams);
-static fused_fn fused_kernel(int K, int R) {
-#define NPC_F(k, r) if (K == k && R == r) return k_fused_i8x2<k, r>;
-    NPC_F(1, 1) NPC_F(1, 2) NPC_F(1, 3) NPC_F(1, 4) NPC_F(1, 8)
-    NPC_F(2, 1) NPC_F(2, 2) NPC_F(2, 3) NPC_F(2, 4) NPC_F(2, 8)
-#undef NPC_F
-    return nullptr;
+static const void *tile_kernel(int K, bool exact) {
+    if (K == 1) return exact ? (const void *)k_fused_tile4<1, true> : (const void *)k_fused_tile4<1, false>;
+    return exact ? (const void *)k_fused_tile4<2, true> : (const void *)k_fused_tile4<2, false>;
 }
 
-// Launch shape of the fused kernel: one CTA per SM, each owning a contiguous range of 16-byte
-// chunks; K chunks per consumer thread; R rows per tile; a raw ring of Sr stages (prefetch) and
-// an index ring of Sc tiles (rows counted but not yet decided) sized to fill shared memory; the
-// accumulate phase runs L tiles behind the count phase; A decider warps.
-// NPC_FUSED_{K,R,SR,SC,L,A} override for tuning; NPC_FUSED=0 forces the two-kernel path.
-static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
-    c->fused_ok = false;
-    if (c->width != 1 || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
+// Launch shape of the tile kernel for `gr` row groups: Gs sample slabs (one CTA each), K chunks per
+// consumer thread, a raw ring of Sr stages (~110 KB of loads in flight per SM), the rest of shared
+// memory as index-ring slots, lag L = Sc - 1 tiles, A decider warps.
+static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg &t) {
     const int64_t C = (c->n + 7) / 8;
-    c->num_sms = prop.multiProcessorCount;
-    c->f_grid = (int)std::min<int64_t>(c->num_sms, std::max<int64_t>(1, C / 32));
-    const int64_t nch = (C + c->f_grid - 1) / c->f_grid;
-    int K = env_int("NPC_FUSED_K", 0);
+    const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
+    if (gs < 1) return false;
+    const int64_t nch = (C + gs - 1) / gs;
+    int K = env_int("NPC_TILE_K", 0);
     if (K != 1 && K != 2) K = nch <= 512 ? 1 : 2;
     const int64_t nc = (nch + 32 * K - 1) / (32 * K);
-    if (nc > 16) return NPC_OK;                       // cohort too wide for one resident pass: two-kernel path
-    c->f_K = K; c->f_nc = (int)nc; c->f_slab = (int)(nc * 32 * K * 16);
-    const int max_smem = (int)prop.sharedMemPerBlockOptin;
-    int R = env_int("NPC_FUSED_R", 4), Sr = env_int("NPC_FUSED_SR", 0), Sc = env_int("NPC_FUSED_SC", 0);
-    int L = env_int("NPC_FUSED_L", 0), A = env_int("NPC_FUSED_A", 4);
-    if (!fused_kernel(K, R)) R = 4;
-    // raw ring: about 70 KB of loads in flight per SM (HBM latency x per-SM bandwidth, with margin)
-    if (Sr <= 0) Sr = std::max(2, std::min(16, (80 * 1024) / (R * c->f_slab)));
+    if (nc > 16) return false;                        // cohort too wide for one resident pass
+    const int slab = (int)(nc * 32 * K * 16);
+    int Sr = env_int("NPC_TILE_SR", 0), Sc = env_int("NPC_TILE_SC", 0), L = env_int("NPC_TILE_L", 0), A = env_int("NPC_TILE_A", 2);
+    if (Sr <= 0) Sr = std::max(2, std::min(8, (112 * 1024) / (F4_R * slab)));
     if (Sc <= 0) {
-        Sc = 64;
-        while (Sc > 2 && (int)FusedSmem::make(R, Sr, Sc, c->f_slab).total > max_smem) Sc--;
+        Sc = 32;
+        while (Sc > 2 && (int)Fused4Smem::make(Sr, Sc, slab).total > max_smem) Sc--;
     }
-    while (Sr > 2 && (int)FusedSmem::make(R, Sr, Sc, c->f_slab).total > max_smem) Sr--;
-    if ((int)FusedSmem::make(R, Sr, Sc, c->f_slab).total > max_smem || Sc < 2) return NPC_OK;
-    if (L <= 0 || L > Sc - 1) L = Sc - 1;
-    A = std::max(1, std::min(6, A));
-    FusedSmem m = FusedSmem::make(R, Sr, Sc, c->f_slab);
-    c->f_R = R; c->f_Sr = Sr; c->f_Sc = Sc; c->f_L = L; c->f_A = A; c->f_smem = m.total;
-    cudaError_t e = cudaFuncSetAttribute(fused_kernel(K, R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.total);
-    if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
-    NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
-    c->fused_ok = true;
-    // 4-row-tile kernel.  Grid = Gs sample slabs x Gr row groups: a cohort too small to give every SM
-    // ~14 consumer warps from the sample axis alone (< ~500k samples) also splits the rows into
-    // contiguous groups whose partial sums are added in group order afterwards.
-    {
-        int best_gr = 1; double best = -1.0;
-        const int force_gr = env_int("NPC_FAST_GR", 0);
-        for (int gr = 1; gr <= 16; gr++) {
-            const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
-            if (gs < 1) break;
-            const int64_t nchq = (C + gs - 1) / gs;
-            const int kq = nchq <= 512 ? 1 : 2;
-            const int64_t ncq = (nchq + 32 * kq - 1) / (32 * kq);
-            if (ncq > 16) continue;
-            const double score = (double)gs * gr * std::min<int64_t>(ncq * kq, 14) * ((double)nchq / (double)(ncq * 32 * kq));
-            if (force_gr ? gr == force_gr : score > best * 1.08) { best = score; best_gr = gr; }
-        }
-        const int gr = best_gr;
+    while (Sr > 2 && (int)Fused4Smem::make(Sr, Sc, slab).total > max_smem) Sr--;
+    // deciders work on groups of 8 tiles: the lag must cover a whole group
+    if ((int)Fused4Smem::make(Sr, Sc, slab).total > max_smem || Sc < 10) return false;
+    if (L <= 8 || L > Sc - 1) L = Sc - 1;
+    t.Gs = gs; t.Gr = gr; t.K = K; t.nc = (int)nc; t.slab = slab; t.Sr = Sr; t.Sc = Sc; t.L = L;
+    t.A = std::max(1, std::min(2, A));
+    t.smem = Fused4Smem::make(Sr, Sc, slab).total;
+    t.ok = true;
+    return true;
+}
+
+// Choose the grids of the tile kernel.  Default mode: Gs sample slabs x Gr row groups -- a cohort too
+// small to give every SM ~14 consumer warps from the sample axis alone (< ~500k samples) also splits
+// the rows into contiguous groups whose partial sums are added in group order afterwards.  Exact
+// order: Gr = 1.  NPC_TILE_{K,SR,SC,L,A,GR} override for tuning; NPC_FUSED=0 forces the two-kernel path.
+static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
+    c->fast.ok = c->exact_cfg.ok = false;
+    if (c->width != 1 || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
+    c->num_sms = prop.multiProcessorCount;
+    const int max_smem = (int)prop.sharedMemPerBlockOptin;
+    const int64_t C = (c->n + 7) / 8;
+    int best_gr = 1; double best = -1.0;
+    const int force_gr = env_int("NPC_TILE_GR", 0);
+    for (int gr = 1; gr <= 16; gr++) {
         const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
-        const int64_t nchq = (C + gs - 1) / gs;
-        int kq = env_int("NPC_FUSED_K", 0);
-        if (kq != 1 && kq != 2) kq = nchq <= 512 ? 1 : 2;
-        const int64_t ncq = (nchq + 32 * kq - 1) / (32 * kq);
-        const int slabq = (int)(ncq * 32 * kq * 16);
-        int qSr = env_int("NPC_FAST_SR", 0), qSc = env_int("NPC_FAST_SC", 0), qL = env_int("NPC_FAST_L", 0), qA = env_int("NPC_FAST_A", 2);
-        if (qSr <= 0) qSr = std::max(2, std::min(8, (112 * 1024) / (F4_R * slabq)));
-        if (qSc <= 0) {
-            qSc = 32;
-            while (qSc > 2 && (int)Fused4Smem::make(qSr, qSc, slabq).total > max_smem) qSc--;
-        }
-        while (qSr > 2 && (int)Fused4Smem::make(qSr, qSc, slabq).total > max_smem) qSr--;
-        // deciders work on groups of 8 tiles: the lag must cover a whole group
-        if (ncq <= 16 && (int)Fused4Smem::make(qSr, qSc, slabq).total <= max_smem && qSc >= 10 && env_int("NPC_FAST", 1) != 0) {
-            if (qL <= 8 || qL > qSc - 1) qL = qSc - 1;
-            c->q_Sr = qSr; c->q_Sc = qSc; c->q_L = qL; c->q_A = std::max(1, std::min(2, qA));
-            c->q_Gs = gs; c->q_Gr = gr; c->q_K = kq; c->q_nc = (int)ncq; c->q_slab = slabq;
-            c->q_smem = Fused4Smem::make(qSr, qSc, slabq).total;
-            const void *fn = kq == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
-            cudaError_t e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem);
-            if (e2 != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e2); return NPC_ECUDA; }
-            if (gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(gr - 1) * (size_t)c->n * sizeof(double)));
-            c->fast_ok = true;
-        }
+        if (gs < 1) break;
+        const int64_t nch = (C + gs - 1) / gs;
+        const int k = nch <= 512 ? 1 : 2;
+        const int64_t nc = (nch + 32 * k - 1) / (32 * k);
+        if (nc > 16) continue;
+        const double score = (double)gs * gr * std::min<int64_t>(nc * k, 14) * ((double)nch / (double)(nc * 32 * k));
+        if (force_gr ? gr == force_gr : score > best * 1.08) { best = score; best_gr = gr; }
     }
+    tile_config(c, best_gr, max_smem, c->fast);
+    tile_config(c, 1, max_smem, c->exact_cfg);
+    for (int ex = 0; ex < 2; ex++) {
+        const npc_ctx::TileCfg &t = ex ? c->exact_cfg : c->fast;
+        if (!t.ok) continue;
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.K, ex != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+        if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
+    }
+    if (c->fast.ok || c->exact_cfg.ok) NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
+    if (c->fast.ok && c->fast.Gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(c->fast.Gr - 1) * (size_t)c->n * sizeof(double)));
     c->exact = env_int("NPC_EXACT", 0) != 0;
     return NPC_OK;
 }
@@ -284,14 +263,11 @@ extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->laun
 
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!ctx || !shape) return NPC_EINVAL;
-    const bool fast = ctx->fused_ok && ctx->fast_ok && !ctx->exact;
-    shape[0] = !ctx->fused_ok ? 0 : fast ? 2 : 1; shape[1] = ctx->f_grid; shape[2] = ctx->f_nc; shape[3] = ctx->f_K;
-    if (fast) {
-        shape[1] = ctx->q_Gs * 1000 + ctx->q_Gr; shape[2] = ctx->q_nc; shape[3] = ctx->q_K;
-        shape[4] = F4_R; shape[5] = ctx->q_Sr * 1000 + ctx->q_Sc; shape[6] = ctx->q_L * 100 + ctx->q_A; shape[7] = (int32_t)ctx->q_smem;
-    } else {
-        shape[4] = ctx->f_R; shape[5] = ctx->f_Sr * 1000 + ctx->f_Sc; shape[6] = ctx->f_L * 100 + ctx->f_A; shape[7] = (int32_t)ctx->f_smem;
-    }
+    const npc_ctx::TileCfg &t = ctx->exact ? ctx->exact_cfg : ctx->fast;
+    memset(shape, 0, 8 * sizeof(int32_t));
+    if (!t.ok) return NPC_OK;
+    shape[0] = ctx->exact ? 1 : 2; shape[1] = t.Gs * 1000 + (ctx->exact ? 1 : t.Gr); shape[2] = t.nc; shape[3] = t.K;
+    shape[4] = F4_R; shape[5] = t.Sr * 1000 + t.Sc; shape[6] = t.L * 100 + t.A; shape[7] = (int32_t)t.smem;
     return NPC_OK;
 }
 
@@ -381,42 +357,34 @@ static int launch_decide_accum(npc_ctx *c, const uint8_t *gt, int64_t row_stride
     return NPC_OK;
 }
 
-// count -> decide -> accumulate in one persistent cooperative launch (npc_fused.cuh)
-static int launch_fused(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
+// count -> decide -> accumulate in one persistent cooperative launch (npc_fused4.cuh)
+static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const uint8_t *gt, int64_t row_stride,
+                        const npc_row *d_rows, int64_t n_rows) {
     if (n_rows == 0) return NPC_OK;
     int rc = ensure_log(c, n_rows);
     if (rc) return rc;
     NPC_CUDA(c, cudaMemsetAsync(c->d_fcounts, 0, n_rows * sizeof(ull), c->stream));
+    const int64_t tiles = (n_rows + F4_R - 1) / F4_R;
+    const int gr = exact ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(t.Gr, tiles / 16));   // >= 16 tiles per row group
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
     P.sums = c->d_sums; P.counts = c->d_fcounts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
+    P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
+    P.Gs = t.Gs; P.Gr = gr; P.partials = c->d_partials;
     void *args[] = { &P };
-    if (c->fast_ok && !c->exact) {
-        const int64_t tiles = (n_rows + F4_R - 1) / F4_R;
-        const int gr = (int)std::max<int64_t>(1, std::min<int64_t>(c->q_Gr, tiles / 16));   // >= 16 tiles per row group
-        P.nc = c->q_nc; P.slab_stride = c->q_slab; P.Gs = c->q_Gs; P.Gr = gr; P.partials = c->d_partials;
-        P.Sr = c->q_Sr; P.Sc = c->q_Sc; P.L = c->q_L; P.A = c->q_A;
-        const void *fn = c->q_K == 1 ? (const void *)k_fused_tile4<1> : (const void *)k_fused_tile4<2>;
-        NPC_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->q_Gs * gr), dim3((c->q_nc + 2 + c->q_A) * 32), args, c->q_smem, c->stream));
-        if (gr > 1) {
-            k_add_partials<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_sums, c->d_partials, c->n, gr - 1);
-            c->launches++;
-            NPC_CUDA(c, cudaGetLastError());
-        }
-    } else {
-        const dim3 grid(c->f_grid);
-        P.nc = c->f_nc; P.slab_stride = c->f_slab; P.Gs = c->f_grid; P.Gr = 1; P.partials = nullptr;
-        P.Sr = c->f_Sr; P.Sc = c->f_Sc; P.L = c->f_L; P.A = c->f_A;
-        NPC_CUDA(c, cudaLaunchCooperativeKernel((const void *)fused_kernel(c->f_K, c->f_R), grid, dim3((c->f_nc + 2 + c->f_A) * 32), args,
-                                                c->f_smem, c->stream));
-    }
+    NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.K, exact), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
     c->launches++;
+    if (gr > 1) {
+        k_add_partials<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_sums, c->d_partials, c->n, gr - 1);
+        c->launches++;
+        NPC_CUDA(c, cudaGetLastError());
+    }
     c->log_len += n_rows;
     return NPC_OK;
 }
 
 static int launch_block(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
-    if (c->fused_ok) return launch_fused(c, gt, row_stride, d_rows, n_rows);
+    if (c->exact ? c->exact_cfg.ok : c->fast.ok) return launch_fused(c, c->exact ? c->exact_cfg : c->fast, c->exact, gt, row_stride, d_rows, n_rows);
     int rc = launch_count(c, gt, row_stride, d_rows, n_rows, c->d_counts);
     if (rc) return rc;
     return launch_decide_accum(c, gt, row_stride, d_rows, n_rows, c->d_counts);

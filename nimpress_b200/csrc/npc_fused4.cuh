@@ -23,8 +23,13 @@
 // first and then, in that order, to the running sum.  Every addend is still the reference's rounded product fl(dosage*beta); only the
 // association differs from the reference's left-to-right chain (src/nimpress.nim:639-640), so
 // scores agree to a few ulp of the running sum (tests assert <= 1e-12 relative; the contract is
-// 1e-9).  The result is deterministic and independent of the launch shape.  npc_set_exact_order
-// selects the bit-for-bit kernel of npc_fused.cuh instead.
+// 1e-9).  The result is deterministic and independent of the launch shape.
+//
+// EXACT = true (npc_set_exact_order) keeps everything above except the pre-summing: the tile's
+// block holds the four rows' 4-entry tables and ACCUMULATE does one lookup and one DADD per
+// genotype, rows in order -- the same rounded products and the same rounded adds as
+// `scores[i] += dosages[i]*beta` (src/nimpress.nim:640), bit for bit.  It runs on a 1-D grid (every
+// CTA sees every row) so that the per-sample chain is the reference's.
 #pragma once
 #include "npc_fused.cuh"
 
@@ -85,7 +90,7 @@ __device__ __forceinline__ uint32_t fold_offsets(uint32_t w) {
     return f;
 }
 
-template <int K>
+template <int K, bool EXACT>
 __global__ void __launch_bounds__(640, 1)         // <= 16 consumer warps + producer + publisher + <= 2 deciders
 k_fused_tile4(const FusedParams P) {
     constexpr int R = F4_R;
@@ -227,13 +232,19 @@ k_fused_tile4(const FusedParams P) {
                 if (lane == 0 && used) atomicAdd(P.nloci, (ull)used);
             }
             __syncwarp();
-            // per tile: lanes 0..15 build T01[lane] = v0[lane&3] + v1[lane>>2], lanes 16..31 T23 from rows 2, 3
+            // per tile, default order: lanes 0..15 build T01[lane] = v0[lane&3] + v1[lane>>2], lanes 16..31
+            // T23 from rows 2, 3.  Exact order: no pre-summing -- lanes 0..15 copy row (lane>>2)'s four
+            // contributions to bytes 32*row + 8*code of the tile's block.
             const int h = lane >> 4, e = lane & 15;
             for (int j = 0; j < ng; j++) {
                 const int s = (int)((t0 + j) % Sc);
                 double *tab = reinterpret_cast<double *>(smem + M.vtab) + s * 32;
-                const double *vr = vrow + (j * R + 2 * h) * 4;
-                tab[lane] = __dadd_rn(vr[e & 3], vr[4 + (e >> 2)]);
+                if (EXACT) {
+                    if (lane < 16) tab[lane] = vrow[j * R * 4 + lane];
+                } else {
+                    const double *vr = vrow + (j * R + 2 * h) * 4;
+                    tab[lane] = __dadd_rn(vr[e & 3], vr[4 + (e >> 2)]);
+                }
             }
             __syncwarp();
             if (lane < ng) mbar_arrive(bar_lut + 8u * (uint32_t)((t0 + lane) % Sc));
@@ -380,16 +391,31 @@ k_fused_tile4(const FusedParams P) {
                 for (int k = 0; k < K; k++) {
                     const uint2 v = lds_v2(sb + M.idx + (uint32_t)sa * islab + cell[k] * 8u);
                     const uint32_t vv[2] = { v.x, v.y };
+                    if (EXACT) {
+                        // the reference's chain: one rounded add per row, rows in order.  Row r's table holds
+                        // its 4 contributions at bytes 32r + 8*code; a dropped row adds +0.0 (the identity)
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        // byte offsets of 4 samples at once: T01 entry (b & 15) * 8, T23 entry 128 + (b >> 4) * 8
-                        const uint32_t lo = (vv[h] & 0x0F0F0F0Fu) << 3;
-                        const uint32_t hi = ((vv[h] >> 1) & 0x78787878u) | 0x80808080u;
+                        for (int r = 0; r < R; r++)
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const double x01 = lds_f64(__byte_perm(lo, thi, 0x6540 + e));
-                            const double x23 = lds_f64(__byte_perm(hi, thi, 0x6540 + e));
-                            acc[k][4 * h + e] = __dadd_rn(__dadd_rn(acc[k][4 * h + e], x01), x23);
+                            for (int h = 0; h < 2; h++) {
+                                const uint32_t sh = r == 0 ? vv[h] << 3 : r == 1 ? vv[h] << 1 : r == 2 ? vv[h] >> 1 : vv[h] >> 3;
+                                const uint32_t off = (sh & 0x18181818u) | (0x20202020u * (uint32_t)r);
+#pragma unroll
+                                for (int e = 0; e < 4; e++)
+                                    acc[k][4 * h + e] = __dadd_rn(acc[k][4 * h + e], lds_f64(__byte_perm(off, thi, 0x6540 + e)));
+                            }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            // byte offsets of 4 samples at once: T01 entry (b & 15) * 8, T23 entry 128 + (b >> 4) * 8
+                            const uint32_t lo = (vv[h] & 0x0F0F0F0Fu) << 3;
+                            const uint32_t hi = ((vv[h] >> 1) & 0x78787878u) | 0x80808080u;
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const double x01 = lds_f64(__byte_perm(lo, thi, 0x6540 + e));
+                                const double x23 = lds_f64(__byte_perm(hi, thi, 0x6540 + e));
+                                acc[k][4 * h + e] = __dadd_rn(__dadd_rn(acc[k][4 * h + e], x01), x23);
+                            }
                         }
                     }
                 }

@@ -277,17 +277,17 @@ def test_config2_shape_wood_100k(nb, mode):
                   exact=mode == "exact")
 
 
-@pytest.mark.parametrize("env", [dict(NPC_FUSED="0"),
-                                 dict(NPC_EXACT="1", NPC_FUSED_R="1", NPC_FUSED_SR="2", NPC_FUSED_SC="2", NPC_FUSED_A="1"),
-                                 dict(NPC_EXACT="1", NPC_FUSED_R="8", NPC_FUSED_SR="3", NPC_FUSED_SC="5", NPC_FUSED_L="3"),
-                                 dict(NPC_EXACT="1", NPC_FUSED_K="2", NPC_FUSED_R="3", NPC_FUSED_A="6"),
-                                 dict(NPC_FAST="0"), dict(NPC_FAST_SR="2", NPC_FAST_SC="10", NPC_FAST_A="1"),
-                                 dict(NPC_FAST_SR="5", NPC_FAST_SC="13", NPC_FAST_L="9", NPC_FAST_A="2"), dict(NPC_FUSED_K="2")],
+@pytest.mark.parametrize("env", [dict(NPC_FUSED="0"), dict(NPC_EXACT="1"),
+                                 dict(NPC_EXACT="1", NPC_TILE_SR="2", NPC_TILE_SC="10", NPC_TILE_A="1"),
+                                 dict(NPC_EXACT="1", NPC_TILE_K="2", NPC_TILE_SR="5", NPC_TILE_SC="13", NPC_TILE_L="9"),
+                                 dict(NPC_TILE_SR="2", NPC_TILE_SC="10", NPC_TILE_A="1"),
+                                 dict(NPC_TILE_SR="5", NPC_TILE_SC="13", NPC_TILE_L="9", NPC_TILE_A="2"), dict(NPC_TILE_K="2"),
+                                 dict(NPC_TILE_GR="1"), dict(NPC_TILE_GR="3"), dict(NPC_TILE_GR="4", NPC_TILE_K="2")],
                          ids=lambda e: ",".join(f"{k[4:]}={v}" for k, v in e.items()))
 def test_kernel_paths_agree(nb, env, monkeypatch):
-    """Every kernel path and launch shape gives the oracle's per-locus records; the exact-order
-    kernels (two-kernel sequence, exact fused kernel under several ring shapes) give its bits, the
-    4-row-tile kernel agrees to 1e-12 under every ring shape."""
+    """Every kernel path and launch shape gives the oracle's per-locus records; the exact-order paths
+    (two-kernel sequence, tile kernel in exact mode under several ring shapes) give its bits, the
+    default tile kernel agrees to 1e-12 under every ring shape and every sample-slab x row-group grid."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     rng = np.random.default_rng(77)
@@ -298,7 +298,7 @@ def test_kernel_paths_agree(nb, env, monkeypatch):
     eng = nb.Engine(n, max_rows_per_block=512)
     kind = eng.kernel_shape["fused"]
     eng.close()
-    exact = "NPC_EXACT" in env or env.get("NPC_FUSED") == "0" or env.get("NPC_FAST") == "0"
+    exact = "NPC_EXACT" in env or env.get("NPC_FUSED") == "0"
     assert kind == (0 if env.get("NPC_FUSED") == "0" else 1 if exact else 2)
     mode = None                                        # leave the context's default (set by the environment)
     for kw in (dict(staged=False, max_rows=512), dict(staged=True, block_rows=37, max_rows=512)):
