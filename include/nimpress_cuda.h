@@ -192,12 +192,12 @@ int64_t npc_launch_count(const npc_ctx *ctx);
  * fl(dosage*beta) as the reference, different association, scores within a few ulp of the running
  * sum (<= 1e-12 relative in the tests; contract 1e-9).  on = 1: every product is added in
  * score-row order like `scores[i] += dosages[i]*beta` (src/nimpress.nim:639-640): bit-identical
- * to the reference's chain, at a lower speed.  The generic (int16/int32/other ploidy) kernels
- * and the split count/accumulate calls are always exact. */
+ * to the reference's chain, at about 85% of the default mode's speed.  The generic (int16/int32/
+ * other ploidy) kernels and the split count/accumulate calls are always exact. */
 int npc_set_exact_order(npc_ctx *ctx, int32_t on);
 
-/* Which kernels npc_score_block* uses for this context: shape[0] = 2 for the 4-row-tile fused
- * kernel, 1 for the exact-order fused kernel (int8 diploid cohorts that fit one resident pass),
+/* Which kernels npc_score_block* uses for this context: shape[0] = 2 for the fused tile kernel in
+ * its default mode, 1 in exact-order mode (int8 diploid cohorts that fit one resident pass),
  * 0 for the count/decide/accumulate sequence; then grid (tile kernel: sample slabs * 1000 + row
  * groups), consumer warps, chunks per thread, rows
  * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + decider warps, dynamic
