@@ -132,8 +132,9 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
     ctx.ck(npc_set_policy(ctx.h, &pol), "npc_set_policy");
     if (p.exact_order) ctx.ck(npc_set_exact_order(ctx.h, 1), "npc_set_exact_order");
     ctx.ck(npc_reset(ctx.h), "npc_reset");
-    int64_t slab_cap = 0;
-    ctx.ck(npc_resident_reserve(ctx.h, std::max<int64_t>(n_lookup, 1), &slab_cap), "npc_resident_reserve");
+    int64_t slab_cap = 0, slab_want = std::max<int64_t>(n_lookup, 1);
+    if (const char *e = getenv("NIMPRESS_SLAB_ROWS")) if (*e) slab_want = std::max<int64_t>(1, std::min<int64_t>(slab_want, atoll(e)));   // tests: force rounds
+    ctx.ck(npc_resident_reserve(ctx.h, slab_want, &slab_cap), "npc_resident_reserve");
     timer.mark("GPU context + buffers");
 
     std::vector<int64_t> submitted;                 // entry index of every row sent to the GPU, in order

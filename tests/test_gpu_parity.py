@@ -365,3 +365,37 @@ def test_config5_policies_50k(nb, imp_locus, maxmis):
     want = oracle(host, n, rows, policy=pol)
     got = run_engine(nb, host, n, rows, policy=pol, staged=False, mode="tile4")
     assert_parity(got, want, exact=False)
+
+
+def test_c_abi_error_paths(nb):
+    """The C ABI refuses bad calls with the documented codes instead of computing something."""
+    import ctypes as C
+    import torch
+    L = nb.load_library()
+    h = C.c_void_p()
+    assert L.npc_create(C.byref(h), 0, 100, 2, 3, 16, 2) == -1 and b"invalid" in L.npc_last_error(None)      # gt_width 3
+    assert L.npc_create(C.byref(h), 0, 100, 2, 1, 16, 1) == -1                                                # one staging slot
+    assert L.npc_create(C.byref(h), 99, 100, 2, 1, 16, 2) == -1                                               # no such device
+    eng = nb.Engine(100, max_rows_per_block=16, n_slots=2)
+    rows = np.zeros(4, dtype=nb.ROW_DTYPE)
+    assert L.npc_score_block(eng.h, 0, 1, rows.ctypes.data, 4) == -4                                          # slot not acquired
+    slot, view = eng.stage_acquire()
+    assert L.npc_score_block(eng.h, slot, 17, rows.ctypes.data, 4) == -1                                      # more rows than the block holds
+    big = np.zeros(17, dtype=nb.ROW_DTYPE)
+    assert L.npc_score_block(eng.h, slot, 1, big.ctypes.data, 17) == -1
+    eng.score_block(slot, 1, rows[:1])
+    s2, _ = eng.stage_acquire()
+    with pytest.raises(nb.NpcError):                                                                         # ring exhausted: both lent / in flight
+        eng.stage_acquire(); eng.stage_acquire()
+    d = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    assert L.npc_score_block_device(eng.h, d.data_ptr() + 1, 208, 1, rows.ctypes.data, 1, 0) == -1            # misaligned slab
+    assert L.npc_score_block_device(eng.h, d.data_ptr(), 100, 1, rows.ctypes.data, 1, 0) == -1                # stride % 16
+    assert L.npc_score_block_device(eng.h, d.data_ptr(), 64, 1, rows.ctypes.data, 1, 0) == -1                 # stride < row bytes
+    assert L.npc_stage_upload(eng.h, s2, 1, 0) == -1                                                          # no resident slab reserved
+    bad = nb.cuda._Policy(7, 0, 0, 0, 0, 0.0)
+    assert L.npc_set_policy(eng.h, C.byref(bad)) == -1
+    eng.close()
+    e0 = nb.Engine(100, max_rows_per_block=16, n_slots=0)
+    with pytest.raises(nb.NpcError, match="staging ring"):
+        e0.stage_acquire()
+    e0.close()

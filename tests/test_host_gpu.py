@@ -103,3 +103,24 @@ def test_cli_stdout_matches_oracle_cli(api, tmp_path):
     assert subprocess.run([exe, "--imp-locus=bogus", sc, vc], capture_output=True, text=True).returncode == 1
     v = subprocess.run([exe, "--version"], capture_output=True, text=True)
     assert v.stdout.strip() == "nimpress 1.0.0"
+
+
+def test_rounds_when_slab_is_too_small(api, tmp_path, monkeypatch):
+    """Matched genotype rows exceeding the resident slab are scored in rounds (NIMPRESS_SLAB_ROWS forces
+    it): per-locus records still bit-equal, scores within 1e-12 (terms are added in a different order),
+    WARN text unchanged; nph_result_rounds reports the rounds."""
+    rng = np.random.default_rng(31)
+    d = make_dataset(str(tmp_path), rng, n=1500, V=300, sorted_scores=False)
+    want = orc.compute_scores_files(d["score"], d["vcf"], d["bed"])
+    for cap in ("7", "64"):
+        monkeypatch.setenv("NIMPRESS_SLAB_ROWS", cap)
+        got = api.run(d["score"], d["bcf"], d["bed"], exact_order=True)
+        assert got.rounds > 2 and got.nloci == want["nloci"] and got.warnings == want["warn"]
+        assert_loci_equal(got.loci, want["loci"])
+        a, b = got.scores, want["scores"]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        ok = np.isfinite(b)
+        assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(np.abs(b[ok]), 1e-3))
+    monkeypatch.delenv("NIMPRESS_SLAB_ROWS")
+    got = api.run(d["score"], d["bcf"], d["bed"], exact_order=True)
+    assert got.rounds == 1 and np.array_equal(bits(got.scores[np.isfinite(got.scores)]), bits(want["scores"][np.isfinite(want["scores"])]))
