@@ -168,6 +168,17 @@ int npc_stage_upload(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, int64_t dst_
  * (any n_rows: split internally into launches of at most max_rows_per_block rows). */
 int npc_score_resident(npc_ctx *ctx, const npc_row *rows, int64_t n_rows);
 
+/* Several score definitions over the same resident slab in one call (BASELINE config 4; the
+ * reference runs its whole pipeline once per score file, src/nimpress.nim:652-753 per process).
+ * For each k < n_scores the outcome is exactly what npc_reset; npc_score_resident(rows[k],
+ * n_rows[k]); npc_finish(offsets[k], scores_out[k], &nloci_out[k], loci_out[k], n_rows[k]) gives:
+ * scores_out[k][n_samples] normalised, loci_out[k][n_rows[k]] in row order (loci_out or
+ * loci_out[k] may be NULL).  Synchronous; the context's own running sums and locus log are
+ * overwritten. */
+int npc_score_resident_multi(npc_ctx *ctx, int32_t n_scores, const npc_row *const *rows, const int64_t *n_rows,
+                             const double *offsets, double *const *scores_out, int64_t *nloci_out,
+                             npc_locus *const *loci_out);
+
 /* ---- results ---------------------------------------------------------------------------- */
 
 /* Waits for all submitted blocks.  scores_out[n_samples] = sum / (2*nloci) + offset

@@ -53,6 +53,11 @@ typedef struct nph_result nph_result;
  * score_path; bed_path may be NULL.  On NPH_OK *out owns the result. */
 int nph_compute_polygenic_scores(const char *score_path, const char *genotype_path, const char *bed_path,
                                  const nph_params *p, nph_result **out);
+/* Several score files over ONE pass of the genotype file (BASELINE config 4).  out[k] is what
+ * nph_compute_polygenic_scores returns for score_paths[k] alone -- the reference's way to get it
+ * is one nimpress process per score file.  On failure nothing is returned in out. */
+int nph_compute_polygenic_scores_multi(const char *const *score_paths, int32_t n_scores, const char *genotype_path,
+                                       const char *bed_path, const nph_params *p, nph_result **out);
 int64_t nph_result_n_samples(const nph_result *r);
 int64_t nph_result_n_loci(const nph_result *r);          /* score rows                      */
 int64_t nph_result_nloci_used(const nph_result *r);      /* loci in the sum (the divisor/2) */

@@ -73,6 +73,7 @@ def load_host_library():
     vp, i32, i64, f64, cp = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_char_p
     sig = {
         "nph_compute_polygenic_scores": (C.c_int, [cp, cp, cp, C.POINTER(_Params), C.POINTER(vp)]),
+        "nph_compute_polygenic_scores_multi": (C.c_int, [C.POINTER(cp), C.c_int32, cp, cp, C.POINTER(_Params), C.POINTER(vp)]),
         "nph_result_n_samples": (i64, [vp]), "nph_result_n_loci": (i64, [vp]), "nph_result_nloci_used": (i64, [vp]),
         "nph_result_rounds": (i64, [vp]), "nph_result_scores": (vp, [vp]), "nph_result_loci": (vp, [vp]),
         "nph_result_sample": (cp, [vp, i64]), "nph_result_warnings": (cp, [vp]), "nph_result_free": (None, [vp]),
@@ -145,12 +146,36 @@ def run(score_path, genotype_path, bed_path=None, imp_locus=ImputeMethodLocus.ps
     h = C.c_void_p()
     rc = L.nph_compute_polygenic_scores(os.fsencode(score_path), os.fsencode(genotype_path),
                                         os.fsencode(bed_path) if bed_path else None, C.byref(p), C.byref(h))
+    _check(L, rc)
+    return _take_result(L, h)
+
+
+def run_multi(score_paths, genotype_path, bed_path=None, imp_locus=ImputeMethodLocus.ps, imp_missing=ImputeMethodMissing.homref,
+              imp_sample=ImputeMethodSample.int_ps, maxmis=0.05, afmisp=0.001, mincs=100, ignorefilt=False, device=0,
+              exact_order=False):
+    """nph_compute_polygenic_scores_multi: several score files over one pass of the genotype file
+    -> [Result], each equal to run() on that file alone."""
+    L = load_host_library()
+    p = _Params(int(imp_locus), int(imp_missing), int(imp_sample), int(ignorefilt), int(bed_path is not None), device,
+                int(bool(exact_order)), 0, int(mincs), float(maxmis), float(afmisp))
+    paths = (C.c_char_p * len(score_paths))(*[os.fsencode(s) for s in score_paths])
+    hs = (C.c_void_p * len(score_paths))()
+    rc = L.nph_compute_polygenic_scores_multi(paths, len(score_paths), os.fsencode(genotype_path),
+                                              os.fsencode(bed_path) if bed_path else None, C.byref(p), hs)
+    _check(L, rc)
+    return [_take_result(L, C.c_void_p(h)) for h in hs]
+
+
+def _check(L, rc):
     if rc == -3:
         raise NimpressInputError(L.nph_last_error().decode())
     if rc in (-1, -2):
         raise FileNotFoundError(L.nph_last_error().decode())
     if rc:
         raise NpcError(f"rc={rc}: {L.nph_last_error().decode()}")
+
+
+def _take_result(L, h):
     try:
         n, nl = L.nph_result_n_samples(h), L.nph_result_n_loci(h)
         scores = np.ctypeslib.as_array(C.cast(L.nph_result_scores(h), C.POINTER(C.c_double)), (n,)).copy() if n else np.zeros(0)

@@ -551,6 +551,24 @@ extern "C" int npc_finish(npc_ctx *ctx, double offset, double *scores_out, int64
     return NPC_OK;
 }
 
+// Several score definitions over the resident slab.  Each is scored exactly as
+// npc_reset + npc_score_resident + npc_finish would score it alone.
+extern "C" int npc_score_resident_multi(npc_ctx *ctx, int32_t n_scores, const npc_row *const *rows, const int64_t *n_rows,
+                                        const double *offsets, double *const *scores_out, int64_t *nloci_out,
+                                        npc_locus *const *loci_out) {
+    if (!ctx || n_scores < 0 || (n_scores && (!rows || !n_rows || !offsets || !scores_out))) return NPC_EINVAL;
+    for (int32_t k = 0; k < n_scores; k++) if (n_rows[k] < 0 || (n_rows[k] && !rows[k]) || !scores_out[k]) return NPC_EINVAL;
+    for (int32_t k = 0; k < n_scores; k++) {
+        int rc = npc_reset(ctx);
+        if (rc) return rc;
+        if ((rc = npc_score_resident(ctx, rows[k], n_rows[k]))) return rc;
+        int64_t nlog = 0;
+        if ((rc = npc_finish(ctx, offsets[k], scores_out[k], nloci_out ? &nloci_out[k] : nullptr,
+                             loci_out ? loci_out[k] : nullptr, loci_out && loci_out[k] ? n_rows[k] : 0, &nlog))) return rc;
+    }
+    return NPC_OK;
+}
+
 extern "C" int npc_partial(npc_ctx *ctx, double *sums_out, int64_t *nloci_out, npc_locus *loci_out, int64_t loci_cap,
                            int64_t *n_loci_out) {
     if (!ctx || !sums_out) return NPC_EINVAL;

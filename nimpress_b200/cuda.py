@@ -65,6 +65,7 @@ def load_library():
         "npc_resident_reserve": (C.c_int, [vp, i64, pi64]),
         "npc_stage_upload": (C.c_int, [vp, i32, i64, i64]),
         "npc_score_resident": (C.c_int, [vp, vp, i64]),
+        "npc_score_resident_multi": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "npc_finish": (C.c_int, [vp, f64, vp, pi64, vp, i64, pi64]),
         "npc_partial": (C.c_int, [vp, vp, pi64, vp, i64, pi64]),
         "npc_partial_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
@@ -168,6 +169,21 @@ class Engine:
     def score_resident(self, rows):
         rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
         self._ck(self.L.npc_score_resident(self.h, rows.ctypes.data, len(rows)))
+
+    def score_resident_multi(self, rows_list, offsets):
+        """npc_score_resident_multi -> [(scores, nloci, loci)] per score definition."""
+        S = len(rows_list)
+        rows_list = [np.ascontiguousarray(r, dtype=ROW_DTYPE) for r in rows_list]
+        rp = (C.c_void_p * S)(*[r.ctypes.data for r in rows_list])
+        nr = np.array([len(r) for r in rows_list], dtype=np.int64)
+        off = np.array(offsets, dtype=np.float64)
+        scores = [np.zeros(self.n, dtype=np.float64) for _ in range(S)]
+        loci = [np.zeros(len(r), dtype=LOCUS_DTYPE) for r in rows_list]
+        sp = (C.c_void_p * S)(*[a.ctypes.data for a in scores])
+        lp = (C.c_void_p * S)(*[a.ctypes.data for a in loci])
+        nloci = np.zeros(S, dtype=np.int64)
+        self._ck(self.L.npc_score_resident_multi(self.h, S, rp, nr.ctypes.data, off.ctypes.data, sp, nloci.ctypes.data, lp))
+        return [(scores[k], int(nloci[k]), loci[k]) for k in range(S)]
 
     # -- device-resident blocks
     def score_block_device(self, gt_dev, row_stride, n_gt_rows, rows, n_rows=None):

@@ -103,120 +103,15 @@ struct PhaseTimer {
 };
 
 struct LayoutOverflow { int width, ploidy; };      // a matched record does not fit the context's GT layout
+struct SlabOverflow {};                            // several score files, and their matched rows exceed device memory
 
-// One pass over the genotype file with a fixed GT layout.  Throws LayoutOverflow when a matched
-// record needs a wider layout (the caller restarts the pass with it).
-void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals &cov, const ScoreParams &p,
-              int gt_width, int ploidy, ScoreResult &out) {
+// WARN lines of one score file, in the reference's order (:326, :527-530, :538-541, :554-557, :567-570, :575-579)
+std::string make_warnings(const ScoreFile &score, const Matcher &M, const std::vector<npc_locus> &loci, int64_t n, const ScoreParams &p) {
+    std::string w;
     const std::vector<ScoreEntry> &E = score.entries;
-    const int64_t nE = (int64_t)E.size(), n = vcf.n_samples();
-    out = ScoreResult();
-    out.samples = vcf.samples();
-
-    PhaseTimer timer;
-    Matcher M(score, cov, p);
-    timer.mark("coverage + entry index");
-    std::vector<int32_t> &kind = M.kind, &eaidx = M.eaidx;
-    std::vector<int64_t> slab_row(nE, -1);
-    std::vector<uint8_t> done(nE, 0);
-    const int64_t n_lookup = M.n_lookup();
-
-    // staging slots of ~32 MB: big enough for efficient H2D copies, small enough that pinning three
-    // of them does not dominate a short run (pinning costs ~1 ms per MB)
-    const int64_t row_bytes = std::max<int64_t>(16, n * ploidy * gt_width);
-    const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(4096, (32ll << 20) / row_bytes + 1),
-                                                                     std::max<int64_t>(n_lookup, 1)));
-    Ctx ctx;
-    npc_policy pol = { p.imp_locus, p.imp_missing, p.imp_sample, 0, p.mincs, p.maxmis };
-    ctx.ck(npc_create(&ctx.h, p.device, n, ploidy, gt_width, block_rows, 3), "npc_create");
-    ctx.ck(npc_set_policy(ctx.h, &pol), "npc_set_policy");
-    if (p.exact_order) ctx.ck(npc_set_exact_order(ctx.h, 1), "npc_set_exact_order");
-    ctx.ck(npc_reset(ctx.h), "npc_reset");
-    int64_t slab_cap = 0, slab_want = std::max<int64_t>(n_lookup, 1);
-    if (const char *e = getenv("NIMPRESS_SLAB_ROWS")) if (*e) slab_want = std::max<int64_t>(1, std::min<int64_t>(slab_want, atoll(e)));   // tests: force rounds
-    ctx.ck(npc_resident_reserve(ctx.h, slab_want, &slab_cap), "npc_resident_reserve");
-    timer.mark("GPU context + buffers");
-
-    std::vector<int64_t> submitted;                 // entry index of every row sent to the GPU, in order
-    submitted.reserve(nE);
-    std::vector<npc_row> rows;
-    int32_t slot = -1; uint8_t *stage = nullptr; int64_t stride = 0, staged = 0, slab_base = 0;
-    auto flush_stage = [&]() {
-        if (slot < 0) return;
-        ctx.ck(npc_stage_upload(ctx.h, slot, staged, slab_base), "npc_stage_upload");
-        slab_base += staged; staged = 0; slot = -1;
-    };
-    // A round scores rows over the resident slab in score-file order.  The normal case is ONE
-    // final round holding every row: exactly the reference's loop order (:634-641).  Only when the
-    // matched genotype rows exceed device memory are there earlier rounds; those take the rows
-    // whose genotypes sit in the slab, and the summation order then differs from the reference's
-    // by a reordering of terms (scores agree to ~1 ulp of the partial sums, not bit for bit).
-    auto score_round = [&](bool final_round) {
-        flush_stage();
-        rows.clear();
-        for (int64_t i = 0; i < nE; i++) {
-            if (done[i]) continue;
-            if (!final_round && !(kind[i] == NPC_KIND_GT && slab_row[i] >= 0)) continue;
-            npc_row r;
-            r.gt_row = kind[i] == NPC_KIND_GT ? (int32_t)slab_row[i] : -1;
-            r.eaidx = eaidx[i]; r.beta = E[i].beta; r.eaf = E[i].eaf;
-            r.ref_is_ea = E[i].ref_is_ea() ? 1 : 0; r.kind = kind[i];
-            rows.push_back(r);
-            submitted.push_back(i);
-            done[i] = 1;
-        }
-        if (!rows.empty()) ctx.ck(npc_score_resident(ctx.h, rows.data(), (int64_t)rows.size()), "npc_score_resident");
-        out.rounds++;
-    };
-
-    // ---- one streaming pass over the genotype file (findVariant :353-364, eaidx :375-379) ---
-    VariantRecord rec;
-    while (vcf.next(rec)) {
-        out.records_read++;
-        const std::vector<int64_t> &hits = M.match(rec);
-        if (hits.empty()) continue;
-        out.records_matched++;
-        bool need_gt = false;
-        for (int64_t i : hits) need_gt |= kind[i] == NPC_KIND_GT;
-        if (!need_gt) continue;                                     // FILTER-failed: never decoded (:553-558)
-        if (!rec.has_gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
-        if (rec.ploidy > ploidy || rec.gt_width > gt_width)
-            throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
-        if (slab_base + staged >= slab_cap) {                       // slab full: score its rows, start over
-            score_round(false);
-            slab_base = 0;
-        }
-        if (slot < 0) {
-            void *ptr;
-            ctx.ck(npc_stage_acquire(ctx.h, &slot, &ptr, &stride), "npc_stage_acquire");
-            stage = (uint8_t *)ptr; staged = 0;
-        }
-        uint8_t *dst = stage + staged * stride;
-        if (rec.gt_width == gt_width && rec.ploidy == ploidy) memcpy(dst, rec.gt, (size_t)n * ploidy * gt_width);
-        else convert_gt(rec, n, gt_width, ploidy, dst);
-        for (int64_t i : hits) if (kind[i] == NPC_KIND_GT) slab_row[i] = slab_base + staged;
-        staged++;
-        if (staged == block_rows) flush_stage();
-    }
-    M.finish();
-    timer.mark("stream + match + upload");
-    score_round(true);
-
-    // ---- results ------------------------------------------------------------------------------
-    out.scores.assign(n, 0.0);
-    std::vector<npc_locus> log(submitted.size());
-    int64_t nlog = 0;
-    ctx.ck(npc_finish(ctx.h, score.offset, out.scores.data(), &out.nloci, log.data(), (int64_t)log.size(), &nlog), "npc_finish");
-    if (nlog != (int64_t)submitted.size()) throw std::runtime_error("locus log length mismatch");
-    out.loci.assign(nE, npc_locus());
-    for (size_t k = 0; k < submitted.size(); k++) out.loci[submitted[k]] = log[k];
-    timer.mark("score + finish (GPU)");
-
-    // ---- WARN lines, in the reference's order (:326, :527-530, :538-541, :554-557, :567-570, :575-579)
-    std::string &w = out.warnings;
-    for (int64_t i = 0; i < nE; i++) {
+    for (int64_t i = 0; i < (int64_t)E.size(); i++) {
         const ScoreEntry &e = E[i];
-        const npc_locus &L = out.loci[i];
+        const npc_locus &L = loci[i];
         const std::string id = e.contig + ":" + std::to_string(e.pos) + ":" + e.refseq + ":" + e.easeq;
         const std::string span = e.contig + ":" + std::to_string(e.pos) + "-" + std::to_string(e.stop());
         if (L.klass == NPC_KIND_NOTCOV) {
@@ -237,25 +132,199 @@ void run_pass(const ScoreFile &score, VariantSource &vcf, const GenomeIntervals 
                  std::to_string(n) + " samples.  This is highly unlikely given polygenic score EAF of " + format_float_nim(e.eaf) + "\n";
         }
     }
+    return w;
+}
+
+// One pass over the genotype file with a fixed GT layout, for one score file or several at once
+// (BASELINE config 4: every score file sees the same record stream, a record any of them matches
+// is uploaded once, and the resident slab is then scored for each file).  Throws LayoutOverflow
+// when a matched record needs a wider layout (the caller restarts the pass with it) and
+// SlabOverflow when several files are given and their rows do not fit device memory.
+void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, const GenomeIntervals &cov, const ScoreParams &p,
+              int gt_width, int ploidy, std::vector<ScoreResult> &outs) {
+    const int S = (int)scores.size();
+    const int64_t n = vcf.n_samples();
+    struct PerScore {
+        std::unique_ptr<Matcher> M;
+        std::vector<int64_t> slab_row, submitted;   // submitted: entry index of every row sent to the GPU, in order
+        std::vector<uint8_t> done;
+        std::vector<npc_row> rows;
+    };
+    std::vector<PerScore> ps(S);
+    outs.assign(S, ScoreResult());
+
+    PhaseTimer timer;
+    int64_t n_lookup = 0;
+    {   // entries with the same (contig, pos, ref, ea) settle on the same record: count keys once
+        std::unordered_map<std::string, int> keys;
+        for (int k = 0; k < S; k++) {
+            outs[k].samples = vcf.samples();
+            ps[k].M.reset(new Matcher(*scores[k], cov, p));
+            const int64_t nE = (int64_t)scores[k]->entries.size();
+            ps[k].slab_row.assign(nE, -1); ps[k].done.assign(nE, 0); ps[k].submitted.reserve(nE);
+            if (S == 1) { n_lookup = ps[k].M->n_lookup(); break; }
+            for (int64_t i = 0; i < nE; i++) if (ps[k].M->kind[i] == Matcher::PENDING) {
+                const ScoreEntry &e = scores[k]->entries[i];
+                keys.emplace(e.contig + "\t" + std::to_string(e.pos) + "\t" + e.refseq + "\t" + e.easeq, 0);
+            }
+        }
+        if (S > 1) n_lookup = (int64_t)keys.size();
+    }
+    timer.mark("coverage + entry index");
+
+    // staging slots of ~32 MB: big enough for efficient H2D copies, small enough that pinning three
+    // of them does not dominate a short run (pinning costs ~1 ms per MB)
+    const int64_t row_bytes = std::max<int64_t>(16, n * ploidy * gt_width);
+    const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(4096, (32ll << 20) / row_bytes + 1),
+                                                                     std::max<int64_t>(n_lookup, 1)));
+    Ctx ctx;
+    npc_policy pol = { p.imp_locus, p.imp_missing, p.imp_sample, 0, p.mincs, p.maxmis };
+    ctx.ck(npc_create(&ctx.h, p.device, n, ploidy, gt_width, block_rows, 3), "npc_create");
+    ctx.ck(npc_set_policy(ctx.h, &pol), "npc_set_policy");
+    if (p.exact_order) ctx.ck(npc_set_exact_order(ctx.h, 1), "npc_set_exact_order");
+    ctx.ck(npc_reset(ctx.h), "npc_reset");
+    int64_t slab_cap = 0, slab_want = std::max<int64_t>(n_lookup, 1);
+    if (const char *e = getenv("NIMPRESS_SLAB_ROWS")) if (*e) slab_want = std::max<int64_t>(1, std::min<int64_t>(slab_want, atoll(e)));   // tests: force rounds
+    ctx.ck(npc_resident_reserve(ctx.h, slab_want, &slab_cap), "npc_resident_reserve");
+    timer.mark("GPU context + buffers");
+
+    int32_t slot = -1; uint8_t *stage = nullptr; int64_t stride = 0, staged = 0, slab_base = 0;
+    auto flush_stage = [&]() {
+        if (slot < 0) return;
+        ctx.ck(npc_stage_upload(ctx.h, slot, staged, slab_base), "npc_stage_upload");
+        slab_base += staged; staged = 0; slot = -1;
+    };
+    // the rows of score k that a round takes, in score-file order
+    auto collect_rows = [&](int k, bool final_round) {
+        PerScore &q = ps[k];
+        const std::vector<ScoreEntry> &E = scores[k]->entries;
+        q.rows.clear();
+        for (int64_t i = 0; i < (int64_t)E.size(); i++) {
+            if (q.done[i]) continue;
+            const int32_t kind = q.M->kind[i];
+            if (!final_round && !(kind == NPC_KIND_GT && q.slab_row[i] >= 0)) continue;
+            npc_row r;
+            r.gt_row = kind == NPC_KIND_GT ? (int32_t)q.slab_row[i] : -1;
+            r.eaidx = q.M->eaidx[i]; r.beta = E[i].beta; r.eaf = E[i].eaf;
+            r.ref_is_ea = E[i].ref_is_ea() ? 1 : 0; r.kind = kind;
+            q.rows.push_back(r);
+            q.submitted.push_back(i);
+            q.done[i] = 1;
+        }
+    };
+    // A round scores rows over the resident slab in score-file order.  The normal case is ONE
+    // final round holding every row: exactly the reference's loop order (:634-641).  Only when the
+    // matched genotype rows exceed device memory are there earlier rounds; those take the rows
+    // whose genotypes sit in the slab, and the summation order then differs from the reference's
+    // by a reordering of terms (scores agree to ~1 ulp of the partial sums, not bit for bit).
+    auto score_round = [&](bool final_round) {     // one score file only
+        flush_stage();
+        collect_rows(0, final_round);
+        if (!ps[0].rows.empty()) ctx.ck(npc_score_resident(ctx.h, ps[0].rows.data(), (int64_t)ps[0].rows.size()), "npc_score_resident");
+        outs[0].rounds++;
+    };
+
+    // ---- one streaming pass over the genotype file (findVariant :353-364, eaidx :375-379) ---
+    VariantRecord rec;
+    int64_t records_read = 0, records_matched = 0;
+    while (vcf.next(rec)) {
+        records_read++;
+        bool any = false, need_gt = false;
+        for (int k = 0; k < S; k++) {
+            const std::vector<int64_t> &hits = ps[k].M->match(rec);
+            for (int64_t i : hits) { any = true; need_gt |= ps[k].M->kind[i] == NPC_KIND_GT; }
+        }
+        if (!any) continue;
+        records_matched++;
+        if (!need_gt) continue;                                     // FILTER-failed: never decoded (:553-558)
+        if (!rec.has_gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
+        if (rec.ploidy > ploidy || rec.gt_width > gt_width)
+            throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
+        if (slab_base + staged >= slab_cap) {                       // slab full: score its rows, start over
+            if (S > 1) throw SlabOverflow();
+            score_round(false);
+            slab_base = 0;
+        }
+        if (slot < 0) {
+            void *ptr;
+            ctx.ck(npc_stage_acquire(ctx.h, &slot, &ptr, &stride), "npc_stage_acquire");
+            stage = (uint8_t *)ptr; staged = 0;
+        }
+        uint8_t *dst = stage + staged * stride;
+        if (rec.gt_width == gt_width && rec.ploidy == ploidy) memcpy(dst, rec.gt, (size_t)n * ploidy * gt_width);
+        else convert_gt(rec, n, gt_width, ploidy, dst);
+        for (int k = 0; k < S; k++) for (int64_t i : ps[k].M->match_last()) if (ps[k].M->kind[i] == NPC_KIND_GT) ps[k].slab_row[i] = slab_base + staged;
+        staged++;
+        if (staged == block_rows) flush_stage();
+    }
+    for (int k = 0; k < S; k++) { ps[k].M->finish(); outs[k].records_read = records_read; outs[k].records_matched = records_matched; }
+    timer.mark("stream + match + upload");
+
+    // ---- score the slab, collect results ------------------------------------------------------
+    std::vector<std::vector<npc_locus>> logs(S);
+    if (S == 1) {
+        score_round(true);
+        outs[0].scores.assign(n, 0.0);
+        logs[0].resize(ps[0].submitted.size());
+        int64_t nlog = 0;
+        ctx.ck(npc_finish(ctx.h, scores[0]->offset, outs[0].scores.data(), &outs[0].nloci, logs[0].data(), (int64_t)logs[0].size(), &nlog), "npc_finish");
+        if (nlog != (int64_t)ps[0].submitted.size()) throw std::runtime_error("locus log length mismatch");
+    } else {
+        flush_stage();
+        std::vector<const npc_row *> rows(S);
+        std::vector<int64_t> n_rows(S), nloci(S);
+        std::vector<double> offsets(S);
+        std::vector<double *> sc(S);
+        std::vector<npc_locus *> lg(S);
+        for (int k = 0; k < S; k++) {
+            collect_rows(k, true);
+            rows[k] = ps[k].rows.data(); n_rows[k] = (int64_t)ps[k].rows.size(); offsets[k] = scores[k]->offset;
+            outs[k].scores.assign(n, 0.0); sc[k] = outs[k].scores.data();
+            logs[k].resize(ps[k].rows.size()); lg[k] = logs[k].data();
+            outs[k].rounds = 1;
+        }
+        ctx.ck(npc_score_resident_multi(ctx.h, S, rows.data(), n_rows.data(), offsets.data(), sc.data(), nloci.data(), lg.data()),
+               "npc_score_resident_multi");
+        for (int k = 0; k < S; k++) outs[k].nloci = nloci[k];
+    }
+    timer.mark("score + finish (GPU)");
+    for (int k = 0; k < S; k++) {
+        outs[k].loci.assign(scores[k]->entries.size(), npc_locus());
+        for (size_t j = 0; j < ps[k].submitted.size(); j++) outs[k].loci[ps[k].submitted[j]] = logs[k][j];
+        outs[k].warnings = make_warnings(*scores[k], *ps[k].M, outs[k].loci, n, p);
+    }
     timer.mark("WARN lines (binomial tests)");
 }
 
 }  // namespace
 
-bool compute_polygenic_scores(const ScoreFile &score, const std::string &genotype_path, const GenomeIntervals &cov,
-                              const ScoreParams &p, ScoreResult &out) {
+bool compute_polygenic_scores_multi(const std::vector<const ScoreFile *> &scores, const std::string &genotype_path,
+                                    const GenomeIntervals &cov, const ScoreParams &p, std::vector<ScoreResult> &outs) {
     int width = 1, ploidy = 2;                      // BCF's usual GT layout: int8, diploid
     for (int attempt = 0; attempt < 4; attempt++) {
         std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path);
         if (!vcf) return false;
         try {
-            run_pass(score, *vcf, cov, p, width, ploidy, out);
+            run_pass(scores, *vcf, cov, p, width, ploidy, outs);
             return true;
         } catch (const LayoutOverflow &o) {         // rare: wider integers or higher ploidy -- rerun with that layout
             width = o.width; ploidy = o.ploidy;
+        } catch (const SlabOverflow &) {            // too many rows for one resident slab: one file at a time
+            outs.assign(scores.size(), ScoreResult());
+            for (size_t k = 0; k < scores.size(); k++)
+                if (!compute_polygenic_scores(*scores[k], genotype_path, cov, p, outs[k])) return false;
+            return true;
         }
     }
     throw std::runtime_error("GT layout kept growing between passes");
+}
+
+bool compute_polygenic_scores(const ScoreFile &score, const std::string &genotype_path, const GenomeIntervals &cov,
+                              const ScoreParams &p, ScoreResult &out) {
+    std::vector<ScoreResult> outs;
+    if (!compute_polygenic_scores_multi({ &score }, genotype_path, cov, p, outs)) return false;
+    out = std::move(outs[0]);
+    return true;
 }
 
 }  // namespace nph

@@ -46,6 +46,7 @@ public:
     Matcher(const ScoreFile &score, const GenomeIntervals &cov, const ScoreParams &p);
     // entries settled by this record (their kind / eaidx / filter text are set); empty if none
     const std::vector<int64_t> &match(const VariantRecord &rec);
+    const std::vector<int64_t> &match_last() const { return hits_; }   // what the last match() returned
     void finish();                                  // everything still pending is ABSENT (:536)
     bool has_contig(const std::string &c) const { return index_.count(c) != 0; }
     int64_t n_lookup() const { return n_lookup_; }
@@ -67,5 +68,10 @@ private:
 // false: the genotype file cannot be opened (the reference: FATAL + quit(-1), :728-730).
 bool compute_polygenic_scores(const ScoreFile &score, const std::string &genotype_path, const GenomeIntervals &cov,
                               const ScoreParams &p, ScoreResult &out);
+
+// Several score files over ONE pass of the genotype file (BASELINE config 4).  Each result is what
+// compute_polygenic_scores gives for that file alone (the reference: one nimpress run per file).
+bool compute_polygenic_scores_multi(const std::vector<const ScoreFile *> &scores, const std::string &genotype_path,
+                                    const GenomeIntervals &cov, const ScoreParams &p, std::vector<ScoreResult> &outs);
 
 }  // namespace nph

@@ -2,6 +2,7 @@
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "../../include/nimpress_host.h"
 #include "driver.hpp"
@@ -56,6 +57,45 @@ int nph_compute_polygenic_scores(const char *score_path, const char *genotype_pa
         }
         res->r.warnings = fatal + res->r.warnings;
         *out = res;
+        return NPH_OK;
+    } catch (const InputError &e) {
+        g_err = e.what();
+        return NPH_EINPUT;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return NPH_EGPU;
+    }
+}
+
+int nph_compute_polygenic_scores_multi(const char *const *score_paths, int32_t n_scores, const char *genotype_path,
+                                       const char *bed_path, const nph_params *p, nph_result **out) {
+    if (!score_paths || n_scores < 1 || !genotype_path || !p || !out) return NPH_EINPUT;
+    for (int32_t k = 0; k < n_scores; k++) out[k] = nullptr;
+    try {
+        ScoreParams q = to_params(p);
+        {
+            std::unique_ptr<VariantSource> probe = open_variant_source(genotype_path);
+            if (!probe) { g_err = std::string("Could not open input VCF file ") + genotype_path; return NPH_EOPEN_VCF; }
+        }
+        std::vector<ScoreFile> files((size_t)n_scores);
+        std::vector<const ScoreFile *> ptrs;
+        GenomeIntervals cov;
+        std::string fatal;
+        for (int32_t k = 0; k < n_scores; k++) {
+            if (!files[k].load(score_paths[k])) { g_err = std::string("Could not open polygenic score file ") + score_paths[k]; return NPH_EOPEN_SCORE; }
+            ptrs.push_back(&files[k]);
+        }
+        if (q.use_cov && bed_path && !cov.load(bed_path)) fatal = std::string("FATAL Could not open coverage BED file ") + bed_path + "\n";
+        std::vector<ScoreResult> rs;
+        if (!compute_polygenic_scores_multi(ptrs, genotype_path, cov, q, rs)) {
+            g_err = std::string("Could not open input VCF file ") + genotype_path;
+            return NPH_EOPEN_VCF;
+        }
+        for (int32_t k = 0; k < n_scores; k++) {
+            out[k] = new nph_result();
+            out[k]->r = std::move(rs[k]);
+            out[k]->r.warnings = fatal + out[k]->r.warnings;
+        }
         return NPH_OK;
     } catch (const InputError &e) {
         g_err = e.what();
@@ -146,6 +186,7 @@ static const char *USAGE =
     "Compute polygenic scores from a VCF/BCF.\n\n"
     "Usage:\n"
     "  nimpress [options] <scoredef> <genotypes.vcf>\n"
+    "  nimpress [options] <scoredef1>,<scoredef2>,... <genotypes.vcf>   (one pass, a \"#score\" line per file; not in the reference)\n"
     "  nimpress (-h | --help)\n"
     "  nimpress --version\n\n"
     "Options:\n"
@@ -217,6 +258,25 @@ int nph_main(int argc, char **argv) {
     } catch (const InputError &e) {
         std::cerr << e.what() << "\n" << "Usage:\n  nimpress [options] <scoredef> <genotypes.vcf>\n";
         return 1;
+    }
+    if (pos[0].find(',') != std::string::npos) {            // several score files, one pass (not a reference feature)
+        std::vector<std::string> paths;
+        for (size_t a = 0; a <= pos[0].size();) { size_t b = pos[0].find(',', a); if (b == std::string::npos) b = pos[0].size(); if (b > a) paths.push_back(pos[0].substr(a, b - a)); a = b + 1; }
+        std::vector<const char *> cp;
+        for (auto &s : paths) cp.push_back(s.c_str());
+        std::vector<nph_result *> rs(paths.size(), nullptr);
+        int rc = nph_compute_polygenic_scores_multi(cp.data(), (int32_t)cp.size(), pos[1].c_str(), p.use_cov ? cov.c_str() : nullptr, &p, rs.data());
+        if (rc == NPH_EOPEN_VCF) { std::cout << "FATAL Could not open input VCF file " << pos[1] << "\n"; return 255; }
+        if (rc == NPH_EOPEN_SCORE) { std::cout << "FATAL " << nph_last_error() << "\n"; return 255; }
+        if (rc) { std::cerr << "nimpress: " << nph_last_error() << "\n"; return 1; }
+        for (size_t k = 0; k < rs.size(); k++) {           // per file: a "#score" line, then the reference's output for it
+            std::cout << "#score\t" << paths[k] << "\n" << nph_result_warnings(rs[k]);
+            const double *s = nph_result_scores(rs[k]);
+            for (int64_t i = 0; i < nph_result_n_samples(rs[k]); i++)
+                std::cout << nph_result_sample(rs[k], i) << "\t" << format_float_nim(s[i]) << "\n";
+            nph_result_free(rs[k]);
+        }
+        return 0;
     }
     nph_result *r = nullptr;
     int rc = nph_compute_polygenic_scores(pos[0].c_str(), pos[1].c_str(), p.use_cov ? cov.c_str() : nullptr, &p, &r);

@@ -102,3 +102,31 @@ def make_dataset(tmp, rng, n=300, V=120, miss_rate=0.03, with_traps=True, gt_dty
     bcf = os.path.join(tmp, "d.bcf")
     write_bcf(bcf, samples, records, contigs=list(contigs), filters=("FAIL", "LowQ"), compress="bgzf")
     return dict(score=score, vcf=vcf, bcf=bcf, bed=bed, samples=samples, records=records, entries=entries)
+
+
+def write_score(path, entries, offset=0.0, name="Synthetic"):
+    with open(path, "w") as fh:
+        fh.write(f"{name}\ndesc\ncite\nhs37d5\n{offset!r}\n")
+        fh.write("\n".join("\t".join(str(x) for x in e) for e in entries) + "\n")
+    return path
+
+
+def derive_scores(tmp, rng, entries, S, keep=0.7, flip=0.15):
+    """S further score files over (a subset of) the same sites: other weights, some rows with the
+    other allele as effect allele, some rows repeated, shuffled order -- what a batch of published
+    scores over one cohort looks like."""
+    paths = []
+    for k in range(S):
+        ents = []
+        for (c, pos, ref, ea, beta, eaf) in entries:
+            if rng.random() > keep:
+                continue
+            if rng.random() < flip:
+                ea = ref if ea != ref else "N"
+            ents.append((c, pos, ref, ea, round(float(rng.normal(0, 0.05)), 4), eaf))
+            if rng.random() < 0.02:
+                ents.append(ents[-1])
+        if k % 2:
+            ents = [ents[i] for i in rng.permutation(len(ents))]
+        paths.append(write_score(os.path.join(tmp, f"derived{k}.score"), ents, offset=round(float(rng.normal()), 3), name=f"derived{k}"))
+    return paths
