@@ -170,11 +170,19 @@ int npc_score_resident(npc_ctx *ctx, const npc_row *rows, int64_t n_rows);
 
 /* Several score definitions over the same resident slab in one call (BASELINE config 4; the
  * reference runs its whole pipeline once per score file, src/nimpress.nim:652-753 per process).
- * For each k < n_scores the outcome is exactly what npc_reset; npc_score_resident(rows[k],
- * n_rows[k]); npc_finish(offsets[k], scores_out[k], &nloci_out[k], loci_out[k], n_rows[k]) gives:
+ * For each k < n_scores the outcome is what npc_reset; npc_score_resident(rows[k], n_rows[k]);
+ * npc_finish(offsets[k], scores_out[k], &nloci_out[k], loci_out[k], n_rows[k]) gives:
  * scores_out[k][n_samples] normalised, loci_out[k][n_rows[k]] in row order (loci_out or
  * loci_out[k] may be NULL).  Synchronous; the context's own running sums and locus log are
- * overwritten. */
+ * overwritten.
+ *   With three or more definitions on an int8 diploid slab (and exact order off) the sums are
+ * formed as one dense contraction on the tensor cores (npc_multi.cuh): the genotypes are read
+ * once for the tallies and once per 16 definitions instead of once per definition.  Per-locus
+ * records and nloci are bit-equal to the one-by-one path; scores agree with it within 1e-9
+ * relative (exact integer arithmetic on coefficients rounded to 2^-53 of the definition's
+ * largest; measured ~1e-15).  Inputs it does not represent (effect-allele index > 62, a
+ * definition naming one slab row with one allele more than four times, infinite coefficients)
+ * take the one-by-one path.  npc_multi_contractions counts the calls the contraction served. */
 int npc_score_resident_multi(npc_ctx *ctx, int32_t n_scores, const npc_row *const *rows, const int64_t *n_rows,
                              const double *offsets, double *const *scores_out, int64_t *nloci_out,
                              npc_locus *const *loci_out);
@@ -197,6 +205,7 @@ void npc_normalise(double *sums, int64_t n, int64_t nloci, double offset);
 
 /* Kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t npc_launch_count(const npc_ctx *ctx);
+int64_t npc_multi_contractions(const npc_ctx *ctx);
 
 /* Summation order of the int8 diploid fused kernels.  on = 0 (default): a tile of four score
  * rows is summed first and then added to each sample's running sum -- same rounded products

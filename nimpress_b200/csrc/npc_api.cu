@@ -5,10 +5,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "npc_fused4.cuh"
+#include "npc_multi.cuh"
 
 using namespace npc;
 
@@ -50,6 +53,7 @@ struct npc_ctx {
     int64_t slab_rows = 0;
     cudaEvent_t ev_slab = nullptr;          // last scoring launch that read the slab
     ull *d_fcounts = nullptr;               // [max_rows] arrivals | nmiss | neff words of the fused kernel
+    int64_t multi_contractions = 0;         // npc_score_resident_multi calls served by the tensor-core contraction
 };
 
 #define NPC_CUDA(ctx, call)                                                                       \
@@ -260,6 +264,7 @@ extern "C" int npc_reset(npc_ctx *ctx) {
 }
 
 extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t npc_multi_contractions(const npc_ctx *ctx) { return ctx ? ctx->multi_contractions : 0; }
 
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!ctx || !shape) return NPC_EINVAL;
@@ -551,13 +556,11 @@ extern "C" int npc_finish(npc_ctx *ctx, double offset, double *scores_out, int64
     return NPC_OK;
 }
 
-// Several score definitions over the resident slab.  Each is scored exactly as
-// npc_reset + npc_score_resident + npc_finish would score it alone.
-extern "C" int npc_score_resident_multi(npc_ctx *ctx, int32_t n_scores, const npc_row *const *rows, const int64_t *n_rows,
-                                        const double *offsets, double *const *scores_out, int64_t *nloci_out,
-                                        npc_locus *const *loci_out) {
-    if (!ctx || n_scores < 0 || (n_scores && (!rows || !n_rows || !offsets || !scores_out))) return NPC_EINVAL;
-    for (int32_t k = 0; k < n_scores; k++) if (n_rows[k] < 0 || (n_rows[k] && !rows[k]) || !scores_out[k]) return NPC_EINVAL;
+// ---- several score definitions over the resident slab ------------------------------------------
+
+// one fused pass per definition: exactly npc_reset + npc_score_resident + npc_finish each
+static int multi_one_by_one(npc_ctx *ctx, int32_t n_scores, const npc_row *const *rows, const int64_t *n_rows, const double *offsets,
+                            double *const *scores_out, int64_t *nloci_out, npc_locus *const *loci_out) {
     for (int32_t k = 0; k < n_scores; k++) {
         int rc = npc_reset(ctx);
         if (rc) return rc;
@@ -567,6 +570,171 @@ extern "C" int npc_score_resident_multi(npc_ctx *ctx, int32_t n_scores, const np
                              loci_out ? loci_out[k] : nullptr, loci_out && loci_out[k] ? n_rows[k] : 0, &nlog))) return rc;
     }
     return NPC_OK;
+}
+
+namespace {
+struct DevBufs {                                    // scratch of one contraction call
+    std::vector<void *> p;
+    template <typename T> cudaError_t get(T **out, size_t count) {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) p.push_back(q);
+        *out = (T *)q;
+        return e;
+    }
+    ~DevBufs() { for (void *q : p) cudaFree(q); }
+};
+}  // namespace
+
+// The dense contraction (npc_multi.cuh).  Returns 1 when the input is outside what it represents
+// (the caller then scores one by one), 0 on success, < 0 on error.
+static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, const int64_t *n_rows, const double *offsets,
+                          double *const *scores_out, int64_t *nloci_out, npc_locus *const *loci_out) {
+    // ---- entries: one per (slab row, effect allele) any definition uses -------------------------
+    std::vector<int64_t> row0(S + 1, 0);
+    for (int k = 0; k < S; k++) row0[k + 1] = row0[k] + n_rows[k];
+    const int64_t R = row0[S];
+    std::vector<npc_row> all((size_t)R), erows;
+    std::vector<int32_t> ent((size_t)R, -1), score_of((size_t)R, 0);
+    std::unordered_map<uint64_t, int32_t> index;
+    std::unordered_map<uint64_t, int32_t> mult;
+    for (int k = 0; k < S; k++)
+        for (int64_t i = 0; i < n_rows[k]; i++) {
+            const npc_row &r = rows[k][i];
+            const int64_t j = row0[k] + i;
+            all[j] = r; score_of[j] = k % npc::MC_SCORES;
+            if (r.kind != NPC_KIND_GT || r.gt_row < 0) continue;
+            if (r.gt_row >= c->slab_rows) return fail(c, NPC_EINVAL, "npc_score_resident_multi: gt_row outside the resident slab");
+            if (r.eaidx < 0 || r.eaidx > 62) return 1;               // no int8 code can match: leave it to the general path
+            const uint64_t key = ((uint64_t)(uint32_t)r.gt_row << 8) | (uint32_t)r.eaidx;
+            auto it = index.find(key);
+            if (it == index.end()) {
+                it = index.emplace(key, (int32_t)erows.size()).first;
+                npc_row e = r; e.kind = NPC_KIND_GT;
+                erows.push_back(e);
+            }
+            ent[j] = it->second;
+            if (++mult[((uint64_t)k << 40) | (uint64_t)it->second] > 4) return 1;   // fixed-point headroom covers 4 repeats
+        }
+    const int64_t E = (int64_t)erows.size();
+    if (E == 0 || E > (1 << 22)) return 1;
+    const int32_t n_kb = (int32_t)((E + npc::MC_ENT - 1) / npc::MC_ENT);
+    const int64_t Ep = (int64_t)n_kb * npc::MC_ENT;
+    std::vector<int32_t> entry_row((size_t)Ep, erows[0].gt_row);
+    std::vector<uint32_t> entry_pat((size_t)Ep, 0xFEFEFEFEu);
+    for (int64_t e = 0; e < E; e++) { entry_row[e] = erows[e].gt_row; entry_pat[e] = 0x01010101u * (uint32_t)((erows[e].eaidx + 1) << 1); }
+
+    DevBufs B;
+    npc_row *d_erows, *d_all; ull *d_ecounts, *d_counts, *d_nloci; int32_t *d_entry_row, *d_ent, *d_score_of, *d_fexp; uint32_t *d_entry_pat;
+    RowP *d_rowp; npc_locus *d_log; int64_t *d_row0; MultiScale *d_scale; long long *d_coef; uint8_t *d_pois, *d_A; double *d_out;
+    const int Sg = std::min<int>(S, npc::MC_SCORES);
+    if (B.get(&d_erows, E) || B.get(&d_ecounts, 2 * E) || B.get(&d_entry_row, Ep) || B.get(&d_entry_pat, Ep) || B.get(&d_all, R) ||
+        B.get(&d_ent, R) || B.get(&d_score_of, R) || B.get(&d_counts, 2 * R) || B.get(&d_rowp, R) || B.get(&d_log, R) ||
+        B.get(&d_nloci, S) || B.get(&d_row0, S + 1) || B.get(&d_scale, S) || B.get(&d_fexp, S) || B.get(&d_coef, (size_t)Sg * 2 * Ep) ||
+        B.get(&d_pois, (size_t)Sg * Ep) || B.get(&d_A, (size_t)n_kb * npc::MC_A_STAGE) || B.get(&d_out, (size_t)Sg * c->n)) {
+        cudaGetLastError();
+        return 1;                                                    // no room for the scratch: one by one needs none
+    }
+    cudaStream_t st = c->stream;
+    NPC_CUDA(c, cudaMemcpyAsync(d_erows, erows.data(), E * sizeof(npc_row), cudaMemcpyHostToDevice, st));
+    NPC_CUDA(c, cudaMemcpyAsync(d_entry_row, entry_row.data(), Ep * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    NPC_CUDA(c, cudaMemcpyAsync(d_entry_pat, entry_pat.data(), Ep * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    NPC_CUDA(c, cudaMemcpyAsync(d_all, all.data(), R * sizeof(npc_row), cudaMemcpyHostToDevice, st));
+    NPC_CUDA(c, cudaMemcpyAsync(d_ent, ent.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    NPC_CUDA(c, cudaMemcpyAsync(d_score_of, score_of.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    NPC_CUDA(c, cudaMemcpyAsync(d_row0, row0.data(), (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    NPC_CUDA(c, cudaMemsetAsync(d_nloci, 0, S * sizeof(ull), st));
+    for (int s = 0; s < c->n_slots; s++) NPC_CUDA(c, cudaStreamWaitEvent(st, c->ev_h2d[s], 0));   // every upload has landed
+
+    // ---- tallies once per entry, decisions per definition (the same k_decide as every path) ------
+    int rc = launch_count(c, c->d_slab, c->row_stride, d_erows, E, d_ecounts);
+    if (rc) return rc;
+    if (R) {
+        k_multi_gather<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(d_ent, R, d_ecounts, d_counts);
+        c->launches++;
+    }
+    for (int k = 0; k < S; k++) if (n_rows[k]) {
+        k_decide<<<(unsigned)((n_rows[k] + 127) / 128), 128, 0, st>>>(d_all + row0[k], n_rows[k], d_counts + 2 * row0[k], c->pol, c->n,
+                                                                     d_rowp + row0[k], d_log + row0[k], d_nloci + k);
+        c->launches++;
+    }
+    k_multi_scale<<<S, 256, 0, st>>>(d_rowp, d_row0, d_scale);
+    c->launches++;
+    NPC_CUDA(c, cudaGetLastError());
+    std::vector<MultiScale> scale(S);
+    std::vector<ull> nloci(S);
+    std::vector<npc_locus> log((size_t)R);
+    NPC_CUDA(c, cudaMemcpyAsync(scale.data(), d_scale, S * sizeof(MultiScale), cudaMemcpyDeviceToHost, st));
+    NPC_CUDA(c, cudaMemcpyAsync(nloci.data(), d_nloci, S * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if (R) NPC_CUDA(c, cudaMemcpyAsync(log.data(), d_log, R * sizeof(npc_locus), cudaMemcpyDeviceToHost, st));
+    NPC_CUDA(c, cudaStreamSynchronize(st));
+    std::vector<int32_t> fexp(S, 0);
+    for (int k = 0; k < S; k++) {
+        if (scale[k].flags) return 1;
+        int ex = 0;
+        if (scale[k].maxabs > 0) { frexp(scale[k].maxabs, &ex); fexp[k] = 52 - ex; }
+        if (fexp[k] > 900 || fexp[k] < -900) return 1;
+    }
+    NPC_CUDA(c, cudaMemcpyAsync(d_fexp, fexp.data(), S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+
+    // ---- contraction, sixteen definitions per launch ------------------------------------------------
+    static bool attr_set = false;
+    if (!attr_set) {
+        NPC_CUDA(c, cudaFuncSetAttribute(k_multi_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, npc::MC_SMEM));
+        attr_set = true;
+    }
+    const int64_t n_tiles = (c->n + npc::MC_N - 1) / npc::MC_N;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, c->num_sms > 0 ? c->num_sms : 148);
+    for (int k0 = 0; k0 < S; k0 += npc::MC_SCORES) {
+        const int ng = std::min(npc::MC_SCORES, S - k0);
+        NPC_CUDA(c, cudaMemsetAsync(d_coef, 0, (size_t)ng * 2 * Ep * sizeof(long long), st));
+        NPC_CUDA(c, cudaMemsetAsync(d_pois, 0, (size_t)ng * Ep, st));
+        const int64_t ra = row0[k0], rb = row0[k0 + ng];
+        if (rb > ra) {
+            k_multi_coef<<<(unsigned)((rb - ra + 255) / 256), 256, 0, st>>>(d_rowp + ra, d_ent + ra, d_score_of + ra, rb - ra, d_fexp + k0, Ep,
+                                                                           d_coef, d_pois);
+            c->launches++;
+        }
+        k_multi_digits<<<dim3((unsigned)n_kb, npc::MC_M), 128, 0, st>>>(d_coef, d_pois, Ep, ng, d_A);
+        c->launches++;
+        MultiParams P;
+        memset(&P, 0, sizeof(P));
+        P.gt = c->d_slab; P.row_stride = c->row_stride; P.n = c->n;
+        P.entry_row = d_entry_row; P.entry_pat = d_entry_pat; P.A = d_A; P.n_kb = n_kb; P.n_scores = ng;
+        for (int k = 0; k < ng; k++) {
+            P.sc_lo[k] = ldexp(1.0, -fexp[k0 + k]); P.sc_hi[k] = ldexp(1.0, 32 - fexp[k0 + k]);
+            P.consts[k] = scale[k0 + k].consts; P.denom[k] = (double)(int64_t)nloci[k0 + k] * 2.0; P.offset[k] = offsets[k0 + k];
+            P.out[k] = d_out + (size_t)k * c->n;
+        }
+        k_multi_contract<<<grid, npc::MC_THREADS, npc::MC_SMEM, st>>>(P);
+        c->launches++;
+        NPC_CUDA(c, cudaGetLastError());
+        for (int k = 0; k < ng; k++)
+            NPC_CUDA(c, cudaMemcpyAsync(scores_out[k0 + k], d_out + (size_t)k * c->n, c->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        NPC_CUDA(c, cudaStreamSynchronize(st));
+    }
+    NPC_CUDA(c, cudaEventRecord(c->ev_slab, st));
+    for (int k = 0; k < S; k++) {
+        if (nloci_out) nloci_out[k] = (int64_t)nloci[k];
+        if (loci_out && loci_out[k] && n_rows[k]) memcpy(loci_out[k], log.data() + row0[k], n_rows[k] * sizeof(npc_locus));
+    }
+    return 0;
+}
+
+extern "C" int npc_score_resident_multi(npc_ctx *ctx, int32_t n_scores, const npc_row *const *rows, const int64_t *n_rows,
+                                        const double *offsets, double *const *scores_out, int64_t *nloci_out,
+                                        npc_locus *const *loci_out) {
+    if (!ctx || n_scores < 0 || (n_scores && (!rows || !n_rows || !offsets || !scores_out))) return NPC_EINVAL;
+    for (int32_t k = 0; k < n_scores; k++) if (n_rows[k] < 0 || (n_rows[k] && !rows[k]) || !scores_out[k]) return NPC_EINVAL;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the contraction pays one tally pass + one pass per 16 definitions; below three definitions the fused kernel is as cheap
+    const char *env = getenv("NPC_MULTI");
+    const int min_scores = env && *env ? (atoi(env) ? 1 : 1 << 30) : 3;
+    if (n_scores >= min_scores && !ctx->exact && ctx->width == 1 && ctx->ploidy == 2 && ctx->n > 0 && ctx->d_slab) {
+        const int rc = multi_contract(ctx, n_scores, rows, n_rows, offsets, scores_out, nloci_out, loci_out);
+        if (rc <= 0) { if (rc == 0) ctx->multi_contractions++; return rc; }
+    }
+    return multi_one_by_one(ctx, n_scores, rows, n_rows, offsets, scores_out, nloci_out, loci_out);
 }
 
 extern "C" int npc_partial(npc_ctx *ctx, double *sums_out, int64_t *nloci_out, npc_locus *loci_out, int64_t loci_cap,

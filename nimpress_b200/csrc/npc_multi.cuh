@@ -1,0 +1,395 @@
+// npc_multi.cuh -- several score definitions over one resident slab as ONE dense contraction
+// (BASELINE.json configs[3]; north_star: "when several score files are evaluated in one pass it
+// becomes a true dense contraction (scores x variants . variants x samples), and only then is a
+// tensor-core path used, with its tolerance stated").
+//
+// The reference scores one file per process (src/nimpress.nim:652-753); per score k, for every
+// row classed OK it adds dosage*beta, or imputed*beta for a missing sample (:639-641, :450-481).
+// With d[e,s] = called dosage (0 when missing) and m[e,s] = missing indicator of slab entry e
+// (= one genotype row decoded for one effect allele):
+//
+//     sum[k,s] = SUM_e  beta[k,e] * d[e,s] + cm[k,e] * m[e,s]            cm = fl(imputed*beta)
+//
+// is a [scores x 2E] . [2E x samples] product.  It is evaluated EXACTLY in integers on the 5th-gen
+// tensor cores: every coefficient is scaled by a per-score power of two to a 56-bit fixed-point
+// integer and split into seven balanced base-256 digits; tcgen05.mma.kind::i8 multiplies the digit
+// rows (operand A, int8) with the d / m planes (operand B, int8 values 0,1,2) into int32
+// accumulators in tensor memory; the epilogue recombines the seven digit sums as two int64 and
+// converts once.  The only approximation is the fixed-point rounding of the coefficients: at most
+// 2^-53 of the largest |coefficient| of that score per term (the reference's own fp64 chain rounds
+// every add at 2^-53 of the running sum).  Stated tolerance: scores within 1e-9 relative of the
+// reference (tests measure ~1e-15).  Per-locus records and nloci come from the same k_decide as
+// every other path: bit-equal.
+//
+// An eighth row per score counts, per sample, the missing calls at entries whose imputed
+// contribution is NaN (--imp-sample=fail / int_fail, eaf = NaN): count > 0 -> score NaN, as the
+// reference's NaN propagation gives.
+//
+// Kernel k_multi_contract: persistent, one CTA per SM, a tile = 256 samples x all entries.
+//   warp 4       producer: per k-block (64 entries) 64 TMA bulk copies of 512 B (one per genotype row
+//                segment) + the 64 effect-allele patterns into a 3-stage raw ring, and the 16 KB
+//                digit tile A (prebuilt in global memory as the smem image) into a 2-stage ring
+//   warps 6..13  converters: raw GT bytes -> d / m planes with byte-wise SWAR compares, written as
+//                operand B, K-major, 128-byte swizzle (the canonical UMMA layout), 2-stage ring
+//   warp 5       one thread issues 4 x tcgen05.mma (M=128, N=256, K=32) per k-block; tcgen05.commit
+//                releases the A / B stages and, after the last k-block, hands the accumulator over
+//   warps 0..3   epilogue: tcgen05.ld -> smem transpose -> int64 recombination -> normalise
+//                (:643-649) -> coalesced stores; two accumulators (2 x 256 TMEM columns) so the
+//                epilogue of tile t overlaps the main loop of tile t+1
+#pragma once
+#include "npc_fused4.cuh"
+
+namespace npc {
+
+constexpr int MC_M = 128;                    // UMMA M: 16 scores x 8 rows (7 digits + NaN counter)
+constexpr int MC_N = 256;                    // UMMA N: samples per tile
+constexpr int MC_ENT = 64;                   // entries per k-block -> 128 plane rows = one 128-byte swizzle row of K
+constexpr int MC_SCORES = 16;                // scores per launch
+constexpr int MC_DIGITS = 7;
+constexpr int MC_RS = 3, MC_BS = 2, MC_AS = 2, MC_TS = 2;   // ring depths: raw, B, A, accumulators
+constexpr int MC_PITCH = 528;                // raw row pitch in a stage: 512 + 16 so that rows g, g+1, .. hit distinct banks
+constexpr int MC_RAW_STAGE = MC_ENT * MC_PITCH + MC_ENT * 4;   // + the effect-allele byte patterns of the 64 entries
+constexpr int MC_A_STAGE = MC_M * 128, MC_B_STAGE = MC_N * 128;
+constexpr int MC_CW = 8;                     // converter warps
+constexpr int MC_THREADS = (4 + 2 + MC_CW) * 32;
+constexpr int MC_EPI_PITCH = 33;             // words; conflict-free transpose
+constexpr int MC_OFF_B = 0;
+constexpr int MC_OFF_A = MC_OFF_B + MC_BS * MC_B_STAGE;
+constexpr int MC_OFF_RAW = MC_OFF_A + MC_AS * MC_A_STAGE;
+constexpr int MC_OFF_EPI = MC_OFF_RAW + MC_RS * MC_RAW_STAGE;
+constexpr int MC_OFF_BAR = MC_OFF_EPI + 4 * 32 * MC_EPI_PITCH * 4;
+constexpr int MC_NBAR = 2 * MC_RS + 2 * MC_BS + 2 * MC_AS + 2 * MC_TS;
+constexpr int MC_OFF_TMEM = MC_OFF_BAR + MC_NBAR * 8;
+constexpr int MC_SMEM = MC_OFF_TMEM + 16 + 1024;          // + slack to align the base to 1024 (swizzle atom)
+
+struct MultiParams {
+    const uint8_t *gt; int64_t row_stride; int64_t n;
+    const int32_t *entry_row;                // [n_kb*64] slab row of each entry (padding entries: any valid row)
+    const uint32_t *entry_pat;               // [n_kb*64] (eaidx+1)<<1 in all four bytes
+    const uint8_t *A;                        // [n_kb][16 KB] digit tiles, already in the swizzled smem layout
+    int32_t n_kb, n_scores;
+    double sc_lo[MC_SCORES], sc_hi[MC_SCORES];   // 2^-F and 2^(32-F) of each score's fixed-point scale
+    double consts[MC_SCORES];                // sum of the constant (whole-locus) contributions, NaN if any is NaN
+    double denom[MC_SCORES];                 // 2 * nloci
+    double offset[MC_SCORES];
+    double *out[MC_SCORES];                  // device, [n] each
+};
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// K-major operand, 128-byte swizzle: row r (M or N index) at r*128, its 16-byte chunk c at ((c ^ (r&7)) << 4);
+// 8 rows = one 1024-byte atom, atoms 1024 bytes apart (stride byte offset); descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// D = S32, A = B = signed 8-bit, both K-major, N = 256, M = 128
+constexpr uint32_t MC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MC_N >> 3) << 17) | ((uint32_t)(MC_M >> 4) << 24);
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(MC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+                 "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// d and m of four samples of one genotype row.  w0, w1: the eight GT bytes (sample-major allele pairs);
+// pat: (eaidx+1)<<1 in every byte.  Returns dosage bytes (0 where the sample is missing) and missing bytes (0/1).
+// All bytes non-negative (the common case): per byte, bits 1..6 are allele+1 (0 = missing); a byte x is zero iff
+// (x + 0x7F) has bit 7 clear, carry-free since x <= 0x7E.  Otherwise (sentinels, invalid codes): decode_sample.
+__device__ __forceinline__ void convert4(uint32_t w0, uint32_t w1, uint32_t pat, int eaidx, uint32_t &d4, uint32_t &m4) {
+    if (((w0 | w1) & 0x80808080u) == 0u) {
+        const uint32_t a0 = __byte_perm(w0, w1, 0x6420), a1 = __byte_perm(w0, w1, 0x7531);   // first / second allele of the 4 samples
+        const uint32_t ne0 = (((a0 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu), ne1 = (((a1 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu);
+        const uint32_t nz0 = ((a0 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu), nz1 = ((a1 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu);
+        const uint32_t called = ((nz0 & nz1) >> 7) & 0x01010101u;                            // 1 = both alleles called
+        const uint32_t d = 0x02020202u - ((ne0 >> 7) & 0x01010101u) - ((ne1 >> 7) & 0x01010101u);
+        d4 = d & (called * 3u);
+        m4 = called ^ 0x01010101u;
+    } else {
+        d4 = 0; m4 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t h = ((i < 2 ? w0 : w1) >> ((i & 1) * 16)) & 0xFFFFu;
+            int8_t a[2] = { (int8_t)(h & 0xFF), (int8_t)(h >> 8) };
+            int d; bool miss;
+            decode_sample<int8_t>(a, 2, eaidx, d, miss);
+            d4 |= (uint32_t)(miss ? 0 : d) << (8 * i);
+            m4 |= (uint32_t)(miss ? 1 : 0) << (8 * i);
+        }
+    }
+}
+
+// 4x4 byte transpose: in r[j] byte i -> out o[i] byte j
+__device__ __forceinline__ void transpose4(const uint32_t r0, const uint32_t r1, const uint32_t r2, const uint32_t r3,
+                                           uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
+    const uint32_t t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140);
+    const uint32_t t2 = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
+    o0 = __byte_perm(t0, t1, 0x5410); o1 = __byte_perm(t0, t1, 0x7632);
+    o2 = __byte_perm(t2, t3, 0x5410); o3 = __byte_perm(t2, t3, 0x7632);
+}
+
+__global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_constant__ MultiParams P) {
+    extern __shared__ uint8_t mc_smem_raw[];
+    const uint32_t base = (smem_u32(mc_smem_raw) + 1023u) & ~1023u;
+    const uint32_t sB = base + MC_OFF_B, sA = base + MC_OFF_A, sRaw = base + MC_OFF_RAW, sEpi = base + MC_OFF_EPI;
+    const uint32_t bars = base + MC_OFF_BAR, sTmem = base + MC_OFF_TMEM;
+    // barrier map
+    const uint32_t raw_full = bars, raw_empty = raw_full + 8 * MC_RS, b_full = raw_empty + 8 * MC_RS, b_empty = b_full + 8 * MC_BS;
+    const uint32_t a_full = b_empty + 8 * MC_BS, a_empty = a_full + 8 * MC_AS, t_full = a_empty + 8 * MC_AS, t_empty = t_full + 8 * MC_TS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (P.n + MC_N - 1) / MC_N;
+
+    if (tid == 0) {
+        for (int i = 0; i < MC_RS; i++) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, MC_CW); }
+        for (int i = 0; i < MC_BS; i++) { mbar_init(b_full + 8 * i, MC_CW); mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < MC_AS; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < MC_TS; i++) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = lds_u32(sTmem);
+
+    if (warp == 4) {
+        // ===== producer =====
+        const uint64_t pol_stream = l2_evict_first_policy(), pol_keep = l2_evict_last_policy();
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t byte0 = tile * (MC_N * 2);
+            const uint32_t seg = (uint32_t)min((int64_t)(MC_N * 2), P.row_stride - byte0);      // multiple of 16: row_stride is
+            int32_t r0 = P.entry_row[lane], r1 = P.entry_row[lane + 32];
+            for (int kb = 0; kb < P.n_kb; kb++, it++) {
+                const uint32_t rs = it % MC_RS, as = it % MC_AS;
+                const uint32_t stage = sRaw + rs * MC_RAW_STAGE;
+                mbar_wait(raw_empty + 8 * rs, ((it / MC_RS) & 1) ^ 1);
+                if (lane == 0) mbar_arrive_expect_tx(raw_full + 8 * rs, seg * MC_ENT + MC_ENT * 4);
+                __syncwarp();
+                tma_load_1d(stage + lane * MC_PITCH, P.gt + (int64_t)r0 * P.row_stride + byte0, seg, raw_full + 8 * rs, pol_stream);
+                tma_load_1d(stage + (lane + 32) * MC_PITCH, P.gt + (int64_t)r1 * P.row_stride + byte0, seg, raw_full + 8 * rs, pol_stream);
+                if (lane == 0) tma_load_1d(stage + MC_ENT * MC_PITCH, P.entry_pat + (int64_t)kb * MC_ENT, MC_ENT * 4, raw_full + 8 * rs, pol_keep);
+                if (kb + 1 < P.n_kb) { r0 = P.entry_row[(kb + 1) * MC_ENT + lane]; r1 = P.entry_row[(kb + 1) * MC_ENT + lane + 32]; }
+                if (lane == 0) {
+                    mbar_wait(a_empty + 8 * as, ((it / MC_AS) & 1) ^ 1);
+                    mbar_arrive_expect_tx(a_full + 8 * as, MC_A_STAGE);
+                    tma_load_1d(sA + as * MC_A_STAGE, P.A + (int64_t)kb * MC_A_STAGE, MC_A_STAGE, a_full + 8 * as, pol_keep);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            uint32_t it = 0, tcount = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
+                const uint32_t ts = tcount % MC_TS;
+                mbar_wait(t_empty + 8 * ts, ((tcount / MC_TS) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem + ts * MC_N;
+                for (int kb = 0; kb < P.n_kb; kb++, it++) {
+                    const uint32_t bs = it % MC_BS, as = it % MC_AS;
+                    mbar_wait(a_full + 8 * as, (it / MC_AS) & 1);
+                    mbar_wait(b_full + 8 * bs, (it / MC_BS) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sA + as * MC_A_STAGE), db = umma_desc_sw128(sB + bs * MC_B_STAGE);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++)                       // K = 32 bytes per instruction: +2 in the 16-byte address field
+                        umma_i8(acc, da + 2 * ks, db + 2 * ks, (kb | ks) != 0);
+                    umma_commit(b_empty + 8 * bs);
+                    umma_commit(a_empty + 8 * as);
+                }
+                umma_commit(t_full + 8 * ts);
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== converters =====
+        const int cw = warp - 6, g = lane & 7, qsub = lane >> 3;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < P.n_kb; kb++, it++) {
+                const uint32_t rs = it % MC_RS, bs = it % MC_BS;
+                const uint32_t stage = sRaw + rs * MC_RAW_STAGE, bt = sB + bs * MC_B_STAGE;
+                mbar_wait(raw_full + 8 * rs, (it / MC_RS) & 1);
+                mbar_wait(b_empty + 8 * bs, ((it / MC_BS) & 1) ^ 1);
+                uint32_t pat[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) pat[j] = lds_u32(stage + MC_ENT * MC_PITCH + (g + 8 * j) * 4);
+#pragma unroll
+                for (int st = 0; st < 2; st++) {
+                    const int q = (cw * 2 + st) * 4 + qsub;              // sample quad 0..63 of the tile
+                    uint32_t D[8], M[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {                        // entry g + 8j of the k-block
+                        const uint2 w = lds_v2(stage + (g + 8 * j) * MC_PITCH + q * 8);
+                        convert4(w.x, w.y, pat[j], (int)((pat[j] & 0xFFu) >> 1) - 1, D[j], M[j]);
+                    }
+                    uint32_t o[4][4];                                    // [sample][word]: d of entries j=0..3, j=4..7, m of j=0..3, j=4..7
+                    transpose4(D[0], D[1], D[2], D[3], o[0][0], o[1][0], o[2][0], o[3][0]);
+                    transpose4(D[4], D[5], D[6], D[7], o[0][1], o[1][1], o[2][1], o[3][1]);
+                    transpose4(M[0], M[1], M[2], M[3], o[0][2], o[1][2], o[2][2], o[3][2]);
+                    transpose4(M[4], M[5], M[6], M[7], o[0][3], o[1][3], o[2][3], o[3][3]);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t s = (uint32_t)(4 * q + i);        // row of B = sample of the tile; chunk g of its 128 K-bytes
+                        sts_v4(bt + s * 128 + ((uint32_t)(g ^ (s & 7)) << 4), o[i][0], o[i][1], o[i][2], o[i][3]);
+                    }
+                }
+                fence_async_smem();                                      // these generic-proxy writes are read by the tensor core
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(b_full + 8 * bs); mbar_arrive(raw_empty + 8 * rs); }
+            }
+        }
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = rows of scores 4w..4w+3 =====
+        const uint32_t epi = sEpi + warp * (32 * MC_EPI_PITCH * 4);
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
+            const uint32_t ts = tcount % MC_TS;
+            mbar_wait(t_full + 8 * ts, (tcount / MC_TS) & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < MC_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ts * MC_N + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) sts_u32(epi + (lane * MC_EPI_PITCH + j) * 4, v[j]);
+                __syncwarp();
+                const int64_t s = tile * MC_N + c0 + lane;               // this lane's sample (column c0 + lane)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const int k = warp * 4 + kk;
+                    if (k < P.n_scores) {
+                        int32_t x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) x[j] = (int32_t)lds_u32(epi + ((kk * 8 + j) * MC_EPI_PITCH + lane) * 4);
+                        const long long lo = (long long)x[0] + ((long long)x[1] << 8) + ((long long)x[2] << 16) + ((long long)x[3] << 24);
+                        const long long hi = (long long)x[4] + ((long long)x[5] << 8) + ((long long)x[6] << 16);
+                        double sum = __dadd_rn(__dmul_rn((double)hi, P.sc_hi[k]), __dmul_rn((double)lo, P.sc_lo[k]));
+                        sum = __dadd_rn(sum, P.consts[k]);
+                        if (x[7] != 0) sum = __longlong_as_double(0x7FF8000000000000ll);
+                        if (s < P.n) P.out[k][s] = __dadd_rn(__ddiv_rn(sum, P.denom[k]), P.offset[k]);   // :643-649
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + 8 * ts);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---- coefficient preparation -------------------------------------------------------------------
+
+// counts of a score row = counts of its slab entry
+__global__ void k_multi_gather(const int32_t *__restrict__ ent, int64_t n_rows, const ull *__restrict__ ecounts, ull *__restrict__ counts) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int32_t e = ent[r];
+    counts[2 * r] = e >= 0 ? ecounts[2 * e] : 0;
+    counts[2 * r + 1] = e >= 0 ? ecounts[2 * e + 1] : 0;
+}
+
+struct MultiScale { double maxabs; double consts; int32_t flags; int32_t pad; };   // flags bit 0: not representable -> caller falls back
+
+// One block per score: largest |coefficient| over its OK rows, the ordered sum of its constant rows
+// (fixed order: 256 contiguous chunks, then the chunk sums left to right), and the fallback flag.
+__global__ void __launch_bounds__(256) k_multi_scale(const RowP *__restrict__ rowp, const int64_t *__restrict__ row0, MultiScale *__restrict__ out) {
+    const int k = blockIdx.x;
+    const int64_t a = row0[k], b = row0[k + 1];
+    const int64_t per = (b - a + 255) / 256;
+    const int64_t lo = a + threadIdx.x * per, hi = min(b, lo + per);
+    double mx = 0.0, cs = 0.0;
+    int flags = 0;
+    for (int64_t r = lo; r < hi; r++) {
+        const RowP rp = rowp[r];
+        if (rp.mode == MODE_CONST) cs = __dadd_rn(cs, rp.c0);
+        else if (rp.mode == MODE_DECODE) {
+            if (!(fabs(rp.c1) <= 1.79e308) || rp.c0 != 0.0) cs = __dadd_rn(cs, __longlong_as_double(0x7FF8000000000000ll));   // beta NaN / inf: every sample NaN
+            else {
+                mx = fmax(mx, fabs(rp.c1));
+                if (rp.cm == rp.cm) { if (fabs(rp.cm) > 1.79e308) flags |= 1; else mx = fmax(mx, fabs(rp.cm)); }
+            }
+        }
+    }
+    __shared__ double s_mx[256], s_cs[256];
+    __shared__ int s_fl;
+    if (threadIdx.x == 0) s_fl = 0;
+    __syncthreads();
+    s_mx[threadIdx.x] = mx; s_cs[threadIdx.x] = cs;
+    if (flags) atomicOr(&s_fl, flags);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0, c = 0.0;
+        for (int i = 0; i < 256; i++) { m = fmax(m, s_mx[i]); c = __dadd_rn(c, s_cs[i]); }
+        MultiScale o; o.maxabs = m; o.consts = c; o.flags = s_fl; o.pad = 0;
+        out[k] = o;
+    }
+}
+
+// coef[(k*2 + plane) * E + e] += round(c * 2^F_k): exact integer adds, so repeated rows of one score commute
+__global__ void k_multi_coef(const RowP *__restrict__ rowp, const int32_t *__restrict__ ent, const int32_t *__restrict__ score_of, int64_t n_rows,
+                             const int32_t *__restrict__ fexp, int64_t E, long long *__restrict__ coef, uint8_t *__restrict__ pois) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const RowP rp = rowp[r];
+    const int32_t e = ent[r];
+    if (rp.mode != MODE_DECODE || e < 0) return;
+    if (!(fabs(rp.c1) <= 1.79e308) || rp.c0 != 0.0) return;             // counted as a NaN constant by k_multi_scale
+    const int k = score_of[r];
+    const int F = fexp[k];
+    atomicAdd((ull *)&coef[((int64_t)k * 2 + 0) * E + e], (ull)__double2ll_rn(scalbn(rp.c1, F)));
+    if (rp.cm == rp.cm) atomicAdd((ull *)&coef[((int64_t)k * 2 + 1) * E + e], (ull)__double2ll_rn(scalbn(rp.cm, F)));
+    else pois[(int64_t)k * E + e] = 1;
+}
+
+// digit tiles: image kb, row R = score*8 + digit (digit 7 = NaN counter), K byte kbyte = 16*g + 8*plane + j  <->  entry kb*64 + g + 8j
+__global__ void __launch_bounds__(128) k_multi_digits(const long long *__restrict__ coef, const uint8_t *__restrict__ pois, int64_t E, int n_scores,
+                                                     uint8_t *__restrict__ A) {
+    const int kb = blockIdx.x, R = blockIdx.y, kbyte = threadIdx.x;
+    const int k = R >> 3, dg = R & 7, g = kbyte >> 4, plane = (kbyte >> 3) & 1, j = kbyte & 7;
+    const int64_t e = (int64_t)kb * MC_ENT + g + 8 * j;
+    int8_t val = 0;
+    if (k < n_scores && e < E) {
+        if (dg == 7) val = plane ? (int8_t)pois[(int64_t)k * E + e] : 0;
+        else {
+            long long v = coef[((int64_t)k * 2 + plane) * E + e];
+            int d = 0;
+            for (int i = 0; i <= dg; i++) { d = (int)(((v + 128) & 255) - 128); v = (v - d) >> 8; }   // balanced base-256 digits
+            val = (int8_t)d;
+        }
+    }
+    A[(int64_t)kb * MC_A_STAGE + R * 128 + ((g ^ (R & 7)) << 4) + (kbyte & 15)] = (uint8_t)val;
+}
+
+}  // namespace npc

@@ -65,6 +65,7 @@ def load_library():
         "npc_resident_reserve": (C.c_int, [vp, i64, pi64]),
         "npc_stage_upload": (C.c_int, [vp, i32, i64, i64]),
         "npc_score_resident": (C.c_int, [vp, vp, i64]),
+        "npc_multi_contractions": (C.c_int64, [vp]),
         "npc_score_resident_multi": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "npc_finish": (C.c_int, [vp, f64, vp, pi64, vp, i64, pi64]),
         "npc_partial": (C.c_int, [vp, vp, pi64, vp, i64, pi64]),
@@ -184,6 +185,10 @@ class Engine:
         nloci = np.zeros(S, dtype=np.int64)
         self._ck(self.L.npc_score_resident_multi(self.h, S, rp, nr.ctypes.data, off.ctypes.data, sp, nloci.ctypes.data, lp))
         return [(scores[k], int(nloci[k]), loci[k]) for k in range(S)]
+
+    @property
+    def multi_contractions(self):
+        return self.L.npc_multi_contractions(self.h)
 
     # -- device-resident blocks
     def score_block_device(self, gt_dev, row_stride, n_gt_rows, rows, n_rows=None):

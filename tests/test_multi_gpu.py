@@ -134,35 +134,121 @@ def test_cli_multi_blocks(api, tmp_path):
     assert bad.returncode == 255 and "FATAL Could not open polygenic score file" in bad.stdout
 
 
-@pytest.mark.parametrize("exact", [False, True], ids=["default", "exact-order"])
-def test_resident_multi_c_abi(nb, exact):
-    """npc_score_resident_multi over a device slab == npc_reset/score_resident/finish per definition,
-    and == the oracle: row lists of different lengths (one empty), shared and private slab rows."""
+def fill_slab(eng, gt, block=128):
+    V = gt.shape[0]
+    assert eng.resident_reserve(V) >= V
+    for r0 in range(0, V, block):
+        slot, view = eng.stage_acquire()
+        m = min(block, V - r0)
+        view[:m, :gt.shape[1]] = gt[r0:r0 + m].view(np.uint8)
+        eng.stage_upload(slot, m, r0)
+
+
+def check_lists(got, gt, n, lists, offs, exact, rtol, threads=1, **pol):
+    worst = 0.0
+    for k, rows in enumerate(lists):
+        want = orc.score_matrix(gt, n, 2, rows, offset=offs[k], threads=threads, **pol)
+        sc, nloci, loci = got[k]
+        assert nloci == want["nloci"]
+        assert_loci_equal(loci, want["loci"])
+        a, b = sc, want["scores"]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (k, np.isnan(a).sum(), np.isnan(b).sum())
+        ok = np.isfinite(b)
+        if exact:
+            assert np.array_equal(bits(a[ok]), bits(b[ok]))
+        elif ok.any():
+            dev = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-3)
+            worst = max(worst, float(dev.max()))
+            assert dev.max() <= rtol, (k, dev.max())
+    return worst
+
+
+@pytest.mark.parametrize("mode", ["contract", "one-by-one", "exact-order"])
+def test_resident_multi_c_abi(nb, mode, monkeypatch):
+    """npc_score_resident_multi over a device slab == the oracle per definition: row lists of different
+    lengths (one empty), shared and private slab rows, repeated rows, every row kind.  `contract` is the
+    tensor-core contraction (1e-9 contract, checked at 1e-12), the others the fused kernel per definition."""
     rng = np.random.default_rng(21)
     n, V = 30011, 180
     gt = random_cohort(rng, n, V, miss_rate=0.04, n_alt=3)
     lists = [random_rows(rng, V, n_rows=m, n_alt=3) for m in (200, 37, 0, 411, 1)]
     offs = [0.0, -1.5, 2.0, 0.25, 7.0]
+    if mode == "one-by-one":
+        monkeypatch.setenv("NPC_MULTI", "0")
     eng = nb.Engine(n, max_rows_per_block=128, n_slots=2)
-    eng.set_exact_order(exact)
-    cap = eng.resident_reserve(V)
-    assert cap >= V
-    for r0 in range(0, V, 128):
-        slot, view = eng.stage_acquire()
-        m = min(128, V - r0)
-        view[:m, :gt.shape[1]] = gt[r0:r0 + m].view(np.uint8)
-        eng.stage_upload(slot, m, r0)
+    eng.set_exact_order(mode == "exact-order")
+    fill_slab(eng, gt)
     got = eng.score_resident_multi(lists, offs)
-    for k, rows in enumerate(lists):
-        want = orc.score_matrix(gt, n, 2, rows, offset=offs[k])
-        sc, nloci, loci = got[k]
-        assert nloci == want["nloci"]
-        assert_loci_equal(loci, want["loci"])
-        a, b = sc, want["scores"]
-        assert np.array_equal(np.isnan(a), np.isnan(b))
-        ok = np.isfinite(b)
-        if exact:
-            assert np.array_equal(bits(a[ok]), bits(b[ok]))
-        else:
-            assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(np.abs(b[ok]), 1e-3))
+    assert eng.multi_contractions == (1 if mode == "contract" else 0)
+    check_lists(got, gt, n, lists, offs, mode == "exact-order", 1e-12)
+    eng.close()
+
+
+@pytest.mark.parametrize("pol", [dict(), dict(imp_locus="fail", imp_sample="int_fail", mincs=40000, maxmis=0.03),
+                                 dict(imp_locus="homref", imp_sample="fail"), dict(imp_locus="ignore", imp_missing="ignore", imp_sample="ps", maxmis=1.0)],
+                         ids=["default", "fail-int_fail", "homref-fail", "ignore-ps"])
+def test_contraction_policies_and_odd_bytes(nb, pol):
+    """The contraction under the policies that poison samples (NaN counter row), with sentinel / short-call /
+    invalid bytes in the slab (its scalar decode path), 20 definitions (two launches of <= 16), NaN eaf."""
+    rng = np.random.default_rng(33)
+    n, V = 7001, 150
+    gt = random_cohort(rng, n, V, miss_rate=0.03, n_alt=5, sentinel_rate=0.01, invalid_rate=0.002)
+    lists = [random_rows(rng, V, n_rows=int(rng.integers(1, 300)), n_alt=5, nan_eaf_rate=0.05) for _ in range(20)]
+    offs = [float(k) for k in range(20)]
+    eng = nb.Engine(n, max_rows_per_block=256, n_slots=2)
+    eng.set_policy(**pol)
+    fill_slab(eng, gt, 256)
+    got = eng.score_resident_multi(lists, offs)
+    assert eng.multi_contractions == 1
+    check_lists(got, gt, n, lists, offs, False, 1e-12, **pol)
+    eng.close()
+
+
+def test_contraction_falls_back_outside_its_range(nb):
+    """More than four repeats of one (row, allele) in a definition, or an effect-allele index no int8 code
+    reaches: served one by one, same results."""
+    rng = np.random.default_rng(34)
+    n, V = 3000, 40
+    gt = random_cohort(rng, n, V, n_alt=2)
+    base = random_rows(rng, V, n_rows=60, n_alt=2, kinds=(1.0, 0, 0, 0))
+    rep = base.copy(); rep["gt_row"][:6] = 3; rep["eaidx"][:6] = 1
+    far = base.copy(); far["eaidx"][5] = 63
+    for lists in ([base, rep, base], [base, far, base]):
+        eng = nb.Engine(n, max_rows_per_block=64, n_slots=2)
+        fill_slab(eng, gt, 64)
+        got = eng.score_resident_multi(lists, [0.0, 1.0, 2.0])
+        assert eng.multi_contractions == 0
+        check_lists(got, gt, n, lists, [0.0, 1.0, 2.0], False, 1e-12)
+        eng.close()
+
+
+def test_config4_contraction_200k(nb):
+    """BASELINE.json configs[3] at its size: 18 definitions (the bundled wood weights + 17 derived) x ~700 loci x
+    200,000 samples, one contraction (two launches: 16 + 2 definitions)."""
+    offset, ents = read_score(os.path.join(G, "scores", "wood-25282103-height.scores"))
+    n, V = 200_000, len(ents)
+    rng = np.random.default_rng(0x6E696D70)
+    af = np.array([e["eaf"] for e in ents])
+    stride = -(-2 * n // 128) * 128
+    gt = np.zeros((V, stride), np.int8)
+    orc.synth_fill(gt, n, 0, 0x6E696D70, (af * 65536).astype(np.uint32), np.full(V, int(0.005 * (1 << 24)), np.uint32), np.ones(V, np.int32))
+    base = np.zeros(V, dtype=orc.ROW_DTYPE)
+    base["gt_row"] = np.arange(V)
+    base["ref_is_ea"] = [int(e["ref"] == e["ea"]) for e in ents]
+    base["eaidx"] = np.where(base["ref_is_ea"] == 1, 0, 1)
+    base["beta"] = [e["beta"] for e in ents]
+    base["eaf"] = af
+    lists, offs = [base], [offset]
+    for k in range(17):
+        r = base[rng.random(V) < 0.9].copy()
+        r["beta"] = np.round(rng.normal(0, 0.05, len(r)), 4)
+        flip = rng.random(len(r)) < 0.2
+        r["eaidx"][flip] ^= 1; r["ref_is_ea"][flip] ^= 1
+        lists.append(r); offs.append(float(k))
+    eng = nb.Engine(n, max_rows_per_block=256, n_slots=2)
+    fill_slab(eng, gt, 256)
+    got = eng.score_resident_multi(lists, offs)
+    assert eng.multi_contractions == 1
+    worst = check_lists(got, gt, n, lists, offs, False, 1e-12, threads=8)
+    print(f"config 4 contraction: worst relative deviation {worst:.3e}")
     eng.close()
