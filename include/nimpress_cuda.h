@@ -163,6 +163,11 @@ int npc_accumulate_block_device(npc_ctx *ctx, const void *gt_dev, int64_t row_st
 int npc_resident_reserve(npc_ctx *ctx, int64_t capacity_rows, int64_t *granted_rows);
 /* Asynchronous: copy n_gt_rows staged rows of `slot` to slab rows dst_row.. and return the slot
  * to the ring when the copy is done. */
+/* Use caller-owned device memory as the resident slab instead (genotypes already on the GPU):
+ * n_gt_rows rows of row_stride bytes (16-byte aligned, a multiple of 16, >= a whole row).  The
+ * context never frees it; it must stay valid until the context is destroyed or another slab is
+ * reserved / adopted.  npc_stage_upload needs row_stride equal to the staging ring's. */
+int npc_resident_adopt(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows);
 int npc_stage_upload(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, int64_t dst_row);
 /* Asynchronous: count -> decide -> accumulate for n_rows score rows over the slab, in order
  * (any n_rows: split internally into launches of at most max_rows_per_block rows). */

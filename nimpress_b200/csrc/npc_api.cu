@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <cmath>
 #include <string>
 #include <unordered_map>
@@ -49,10 +50,14 @@ struct npc_ctx {
     bool exact = false;
     int num_sms = 0;
     double *d_partials = nullptr;           // [fast.Gr - 1][n] partial sums of row groups 1..
-    uint8_t *d_slab = nullptr;              // resident slab (npc_resident_reserve)
+    uint8_t *d_slab = nullptr;              // resident slab (npc_resident_reserve / npc_resident_adopt)
+    bool slab_owned = false;
+    int64_t slab_stride = 0;
     int64_t slab_rows = 0;
     cudaEvent_t ev_slab = nullptr;          // last scoring launch that read the slab
     ull *d_fcounts = nullptr;               // [max_rows] arrivals | nmiss | neff words of the fused kernel
+    uint8_t *d_multi_scratch = nullptr;     // arena of npc_score_resident_multi's contraction
+    size_t multi_scratch_bytes = 0;
     int64_t multi_contractions = 0;         // npc_score_resident_multi calls served by the tensor-core contraction
 };
 
@@ -85,7 +90,7 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_slab); cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
     if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -477,7 +482,8 @@ extern "C" int npc_resident_reserve(npc_ctx *ctx, int64_t capacity_rows, int64_t
     if (!ctx || capacity_rows < 0) return NPC_EINVAL;
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));
     NPC_CUDA(ctx, cudaDeviceSynchronize());
-    if (ctx->d_slab) { cudaFree(ctx->d_slab); ctx->d_slab = nullptr; ctx->slab_rows = 0; }
+    if (ctx->d_slab && ctx->slab_owned) cudaFree(ctx->d_slab);
+    ctx->d_slab = nullptr; ctx->slab_rows = 0; ctx->slab_owned = false;
     if (!ctx->ev_slab) NPC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_slab, cudaEventDisableTiming));
     size_t free_b = 0, total_b = 0;
     NPC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -485,8 +491,20 @@ extern "C" int npc_resident_reserve(npc_ctx *ctx, int64_t capacity_rows, int64_t
     int64_t rows = std::min(capacity_rows, budget);
     if (rows < 1 && capacity_rows > 0) return fail(ctx, NPC_ENOMEM, "no device memory for a resident slab");
     if (rows > 0) NPC_CUDA(ctx, cudaMalloc(&ctx->d_slab, (size_t)rows * ctx->row_stride));
-    ctx->slab_rows = rows;
+    ctx->slab_rows = rows; ctx->slab_owned = rows > 0; ctx->slab_stride = ctx->row_stride;
     if (granted_rows) *granted_rows = rows;
+    return NPC_OK;
+}
+
+extern "C" int npc_resident_adopt(npc_ctx *ctx, const void *gt_dev, int64_t row_stride, int64_t n_gt_rows) {
+    if (!ctx || n_gt_rows < 0 || (n_gt_rows && !gt_dev)) return NPC_EINVAL;
+    if (((uintptr_t)gt_dev & 15) || (row_stride & 15) || row_stride < ctx->n * ctx->ploidy * ctx->width)
+        return fail(ctx, NPC_EINVAL, "npc_resident_adopt: slab must be 16-byte aligned, row_stride a multiple of 16 holding a whole row");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    NPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_slab && ctx->slab_owned) cudaFree(ctx->d_slab);
+    if (!ctx->ev_slab) NPC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_slab, cudaEventDisableTiming));
+    ctx->d_slab = (uint8_t *)gt_dev; ctx->slab_rows = n_gt_rows; ctx->slab_owned = false; ctx->slab_stride = row_stride;
     return NPC_OK;
 }
 
@@ -495,6 +513,7 @@ extern "C" int npc_stage_upload(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, i
     if (slot < 0 || slot >= ctx->n_slots || ctx->slot_state[slot] != 1) return fail(ctx, NPC_ESTATE, "slot was not acquired");
     if (n_gt_rows < 0 || n_gt_rows > ctx->max_rows || dst_row < 0 || dst_row + n_gt_rows > ctx->slab_rows)
         return fail(ctx, NPC_EINVAL, "npc_stage_upload: rows outside the resident slab");
+    if (ctx->slab_stride != ctx->row_stride) return fail(ctx, NPC_ESTATE, "npc_stage_upload: the adopted slab has another row stride");
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));
     // a scoring launch may still be reading the slab rows we are about to overwrite
     NPC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_slab, 0));
@@ -520,7 +539,7 @@ extern "C" int npc_score_resident(npc_ctx *ctx, const npc_row *rows, int64_t n_r
         const npc_row *d_rows;
         int rc = upload_rows(ctx, rows + r0, nr, 0, &d_rows);
         if (rc) return rc;
-        if ((rc = launch_block(ctx, ctx->d_slab, ctx->row_stride, d_rows, nr))) return rc;
+        if ((rc = launch_block(ctx, ctx->d_slab, ctx->slab_stride, d_rows, nr))) return rc;
     }
     NPC_CUDA(ctx, cudaEventRecord(ctx->ev_slab, ctx->stream));
     return NPC_OK;
@@ -572,49 +591,46 @@ static int multi_one_by_one(npc_ctx *ctx, int32_t n_scores, const npc_row *const
     return NPC_OK;
 }
 
-namespace {
-struct DevBufs {                                    // scratch of one contraction call
-    std::vector<void *> p;
-    template <typename T> cudaError_t get(T **out, size_t count) {
-        void *q = nullptr;
-        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
-        if (e == cudaSuccess) p.push_back(q);
-        *out = (T *)q;
-        return e;
-    }
-    ~DevBufs() { for (void *q : p) cudaFree(q); }
-};
-}  // namespace
 
 // The dense contraction (npc_multi.cuh).  Returns 1 when the input is outside what it represents
 // (the caller then scores one by one), 0 on success, < 0 on error.
 static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, const int64_t *n_rows, const double *offsets,
                           double *const *scores_out, int64_t *nloci_out, npc_locus *const *loci_out) {
+    const bool timing = getenv("NPC_TIMING") != nullptr;         // phase wall times on stderr (each phase drained first)
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(c->stream);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[npc multi] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     // ---- entries: one per (slab row, effect allele) any definition uses -------------------------
     std::vector<int64_t> row0(S + 1, 0);
     for (int k = 0; k < S; k++) row0[k + 1] = row0[k] + n_rows[k];
     const int64_t R = row0[S];
-    std::vector<npc_row> all((size_t)R), erows;
+    std::vector<npc_row> erows;
     std::vector<int32_t> ent((size_t)R, -1), score_of((size_t)R, 0);
-    std::unordered_map<uint64_t, int32_t> index;
-    std::unordered_map<uint64_t, int32_t> mult;
+    std::vector<int32_t> head((size_t)c->slab_rows, -1), next, last_score, repeats;   // per slab row: chain of its entries
     for (int k = 0; k < S; k++)
         for (int64_t i = 0; i < n_rows[k]; i++) {
             const npc_row &r = rows[k][i];
             const int64_t j = row0[k] + i;
-            all[j] = r; score_of[j] = k % npc::MC_SCORES;
+            score_of[j] = k % npc::MC_SCORES;
             if (r.kind != NPC_KIND_GT || r.gt_row < 0) continue;
             if (r.gt_row >= c->slab_rows) return fail(c, NPC_EINVAL, "npc_score_resident_multi: gt_row outside the resident slab");
             if (r.eaidx < 0 || r.eaidx > 62) return 1;               // no int8 code can match: leave it to the general path
-            const uint64_t key = ((uint64_t)(uint32_t)r.gt_row << 8) | (uint32_t)r.eaidx;
-            auto it = index.find(key);
-            if (it == index.end()) {
-                it = index.emplace(key, (int32_t)erows.size()).first;
-                npc_row e = r; e.kind = NPC_KIND_GT;
-                erows.push_back(e);
+            int32_t e = head[r.gt_row];
+            while (e >= 0 && erows[e].eaidx != r.eaidx) e = next[e];
+            if (e < 0) {
+                e = (int32_t)erows.size();
+                npc_row er = r; er.kind = NPC_KIND_GT;
+                erows.push_back(er); next.push_back(head[r.gt_row]); last_score.push_back(-1); repeats.push_back(0);
+                head[r.gt_row] = e;
             }
-            ent[j] = it->second;
-            if (++mult[((uint64_t)k << 40) | (uint64_t)it->second] > 4) return 1;   // fixed-point headroom covers 4 repeats
+            ent[j] = e;
+            if (last_score[e] != k) { last_score[e] = k; repeats[e] = 0; }
+            if (++repeats[e] > 4) return 1;                          // fixed-point headroom covers 4 repeats
         }
     const int64_t E = (int64_t)erows.size();
     if (E == 0 || E > (1 << 22)) return 1;
@@ -624,22 +640,39 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     std::vector<uint32_t> entry_pat((size_t)Ep, 0xFEFEFEFEu);
     for (int64_t e = 0; e < E; e++) { entry_row[e] = erows[e].gt_row; entry_pat[e] = 0x01010101u * (uint32_t)((erows[e].eaidx + 1) << 1); }
 
-    DevBufs B;
-    npc_row *d_erows, *d_all; ull *d_ecounts, *d_counts, *d_nloci; int32_t *d_entry_row, *d_ent, *d_score_of, *d_fexp; uint32_t *d_entry_pat;
-    RowP *d_rowp; npc_locus *d_log; int64_t *d_row0; MultiScale *d_scale; long long *d_coef; uint8_t *d_pois, *d_A; double *d_out;
+    mark("entries (host)");
+    // scratch: one arena kept by the context, grown when a call needs more
     const int Sg = std::min<int>(S, npc::MC_SCORES);
-    if (B.get(&d_erows, E) || B.get(&d_ecounts, 2 * E) || B.get(&d_entry_row, Ep) || B.get(&d_entry_pat, Ep) || B.get(&d_all, R) ||
-        B.get(&d_ent, R) || B.get(&d_score_of, R) || B.get(&d_counts, 2 * R) || B.get(&d_rowp, R) || B.get(&d_log, R) ||
-        B.get(&d_nloci, S) || B.get(&d_row0, S + 1) || B.get(&d_scale, S) || B.get(&d_fexp, S) || B.get(&d_coef, (size_t)Sg * 2 * Ep) ||
-        B.get(&d_pois, (size_t)Sg * Ep) || B.get(&d_A, (size_t)n_kb * npc::MC_A_STAGE) || B.get(&d_out, (size_t)Sg * c->n)) {
-        cudaGetLastError();
-        return 1;                                                    // no room for the scratch: one by one needs none
+    size_t need = 0;
+    auto reserve = [&](size_t bytes) { size_t off = need; need += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return off; };
+    const size_t o_erows = reserve(E * sizeof(npc_row)), o_ecounts = reserve(2 * E * sizeof(ull)), o_entry_row = reserve(Ep * 4),
+                 o_entry_pat = reserve(Ep * 4), o_all = reserve(R * sizeof(npc_row)), o_ent = reserve(R * 4), o_score_of = reserve(R * 4),
+                 o_counts = reserve(2 * R * sizeof(ull)), o_rowp = reserve(R * sizeof(RowP)), o_log = reserve(R * sizeof(npc_locus)),
+                 o_nloci = reserve(S * sizeof(ull)), o_row0 = reserve((S + 1) * 8), o_scale = reserve(S * sizeof(MultiScale)),
+                 o_fexp = reserve(S * 4), o_coef = reserve((size_t)Sg * 2 * Ep * 8), o_pois = reserve((size_t)Sg * Ep),
+                 o_A = reserve((size_t)n_kb * npc::MC_A_STAGE), o_out = reserve((size_t)Sg * c->n * 8);
+    if (need > c->multi_scratch_bytes) {
+        NPC_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_multi_scratch); c->d_multi_scratch = nullptr; c->multi_scratch_bytes = 0;
+        if (cudaMalloc(&c->d_multi_scratch, need) != cudaSuccess) { cudaGetLastError(); return 1; }   // no room: one by one needs none
+        c->multi_scratch_bytes = need;
     }
+    uint8_t *base = c->d_multi_scratch;
+    npc_row *d_erows = (npc_row *)(base + o_erows), *d_all = (npc_row *)(base + o_all);
+    ull *d_ecounts = (ull *)(base + o_ecounts), *d_counts = (ull *)(base + o_counts), *d_nloci = (ull *)(base + o_nloci);
+    int32_t *d_entry_row = (int32_t *)(base + o_entry_row), *d_ent = (int32_t *)(base + o_ent), *d_score_of = (int32_t *)(base + o_score_of),
+            *d_fexp = (int32_t *)(base + o_fexp);
+    uint32_t *d_entry_pat = (uint32_t *)(base + o_entry_pat);
+    RowP *d_rowp = (RowP *)(base + o_rowp); npc_locus *d_log = (npc_locus *)(base + o_log); int64_t *d_row0 = (int64_t *)(base + o_row0);
+    MultiScale *d_scale = (MultiScale *)(base + o_scale); long long *d_coef = (long long *)(base + o_coef);
+    uint8_t *d_pois = base + o_pois, *d_A = base + o_A; double *d_out = (double *)(base + o_out);
     cudaStream_t st = c->stream;
+    mark("scratch arena");
     NPC_CUDA(c, cudaMemcpyAsync(d_erows, erows.data(), E * sizeof(npc_row), cudaMemcpyHostToDevice, st));
     NPC_CUDA(c, cudaMemcpyAsync(d_entry_row, entry_row.data(), Ep * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     NPC_CUDA(c, cudaMemcpyAsync(d_entry_pat, entry_pat.data(), Ep * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    NPC_CUDA(c, cudaMemcpyAsync(d_all, all.data(), R * sizeof(npc_row), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < S; k++) if (n_rows[k])
+        NPC_CUDA(c, cudaMemcpyAsync(d_all + row0[k], rows[k], n_rows[k] * sizeof(npc_row), cudaMemcpyHostToDevice, st));
     NPC_CUDA(c, cudaMemcpyAsync(d_ent, ent.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     NPC_CUDA(c, cudaMemcpyAsync(d_score_of, score_of.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     NPC_CUDA(c, cudaMemcpyAsync(d_row0, row0.data(), (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -647,8 +680,9 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     for (int s = 0; s < c->n_slots; s++) NPC_CUDA(c, cudaStreamWaitEvent(st, c->ev_h2d[s], 0));   // every upload has landed
 
     // ---- tallies once per entry, decisions per definition (the same k_decide as every path) ------
-    int rc = launch_count(c, c->d_slab, c->row_stride, d_erows, E, d_ecounts);
+    int rc = launch_count(c, c->d_slab, c->slab_stride, d_erows, E, d_ecounts);
     if (rc) return rc;
+    mark("tally kernel");
     if (R) {
         k_multi_gather<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(d_ent, R, d_ecounts, d_counts);
         c->launches++;
@@ -663,11 +697,12 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     NPC_CUDA(c, cudaGetLastError());
     std::vector<MultiScale> scale(S);
     std::vector<ull> nloci(S);
-    std::vector<npc_locus> log((size_t)R);
     NPC_CUDA(c, cudaMemcpyAsync(scale.data(), d_scale, S * sizeof(MultiScale), cudaMemcpyDeviceToHost, st));
     NPC_CUDA(c, cudaMemcpyAsync(nloci.data(), d_nloci, S * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    if (R) NPC_CUDA(c, cudaMemcpyAsync(log.data(), d_log, R * sizeof(npc_locus), cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < S; k++) if (loci_out && loci_out[k] && n_rows[k])
+        NPC_CUDA(c, cudaMemcpyAsync(loci_out[k], d_log + row0[k], n_rows[k] * sizeof(npc_locus), cudaMemcpyDeviceToHost, st));
     NPC_CUDA(c, cudaStreamSynchronize(st));
+    mark("decide + scale + log D2H");
     std::vector<int32_t> fexp(S, 0);
     for (int k = 0; k < S; k++) {
         if (scale[k].flags) return 1;
@@ -699,25 +734,25 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
         c->launches++;
         MultiParams P;
         memset(&P, 0, sizeof(P));
-        P.gt = c->d_slab; P.row_stride = c->row_stride; P.n = c->n;
+        P.gt = c->d_slab; P.row_stride = c->slab_stride; P.n = c->n;
         P.entry_row = d_entry_row; P.entry_pat = d_entry_pat; P.A = d_A; P.n_kb = n_kb; P.n_scores = ng;
         for (int k = 0; k < ng; k++) {
             P.sc_lo[k] = ldexp(1.0, -fexp[k0 + k]); P.sc_hi[k] = ldexp(1.0, 32 - fexp[k0 + k]);
             P.consts[k] = scale[k0 + k].consts; P.denom[k] = (double)(int64_t)nloci[k0 + k] * 2.0; P.offset[k] = offsets[k0 + k];
             P.out[k] = d_out + (size_t)k * c->n;
         }
+        mark("digit tiles");
         k_multi_contract<<<grid, npc::MC_THREADS, npc::MC_SMEM, st>>>(P);
         c->launches++;
         NPC_CUDA(c, cudaGetLastError());
+        mark("contraction kernel");
         for (int k = 0; k < ng; k++)
             NPC_CUDA(c, cudaMemcpyAsync(scores_out[k0 + k], d_out + (size_t)k * c->n, c->n * sizeof(double), cudaMemcpyDeviceToHost, st));
         NPC_CUDA(c, cudaStreamSynchronize(st));
+        mark("scores D2H");
     }
     NPC_CUDA(c, cudaEventRecord(c->ev_slab, st));
-    for (int k = 0; k < S; k++) {
-        if (nloci_out) nloci_out[k] = (int64_t)nloci[k];
-        if (loci_out && loci_out[k] && n_rows[k]) memcpy(loci_out[k], log.data() + row0[k], n_rows[k] * sizeof(npc_locus));
-    }
+    for (int k = 0; k < S; k++) if (nloci_out) nloci_out[k] = (int64_t)nloci[k];
     return 0;
 }
 

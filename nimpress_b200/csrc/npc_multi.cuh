@@ -26,12 +26,14 @@
 // reference's NaN propagation gives.
 //
 // Kernel k_multi_contract: persistent, one CTA per SM, a tile = 256 samples x all entries.
-//   warp 4       producer: per k-block (64 entries) 64 TMA bulk copies of 512 B (one per genotype row
-//                segment) + the 64 effect-allele patterns into a 3-stage raw ring, and the 16 KB
-//                digit tile A (prebuilt in global memory as the smem image) into a 2-stage ring
-//   warps 6..13  converters: raw GT bytes -> d / m planes with byte-wise SWAR compares, written as
+//   warps 4..7   producers: per k-block (64 entries) 64 TMA bulk copies of 512 B (one per genotype row
+//                segment; a warp issues one copy at a time, hence four warps) + the 64 effect-allele
+//                patterns into a 3-stage raw ring
+//   warp 9       loads the 16 KB digit tile A of the k-block (prebuilt in global memory as the smem
+//                image, L2-resident) into its own 3-stage ring
+//   warps 10..17 converters: raw GT bytes -> d / m planes with byte-wise SWAR compares, written as
 //                operand B, K-major, 128-byte swizzle (the canonical UMMA layout), 2-stage ring
-//   warp 5       one thread issues 4 x tcgen05.mma (M=128, N=256, K=32) per k-block; tcgen05.commit
+//   warp 8       one thread issues 4 x tcgen05.mma (M=128, N=256, K=32) per k-block; tcgen05.commit
 //                releases the A / B stages and, after the last k-block, hands the accumulator over
 //   warps 0..3   epilogue: tcgen05.ld -> smem transpose -> int64 recombination -> normalise
 //                (:643-649) -> coalesced stores; two accumulators (2 x 256 TMEM columns) so the
@@ -46,13 +48,16 @@ constexpr int MC_N = 256;                    // UMMA N: samples per tile
 constexpr int MC_ENT = 64;                   // entries per k-block -> 128 plane rows = one 128-byte swizzle row of K
 constexpr int MC_SCORES = 16;                // scores per launch
 constexpr int MC_DIGITS = 7;
-constexpr int MC_RS = 3, MC_BS = 2, MC_AS = 2, MC_TS = 2;   // ring depths: raw, B, A, accumulators
+constexpr int MC_RS = 3, MC_BS = 2, MC_AS = 3, MC_TS = 2;   // ring depths: raw, B, A, accumulators
 constexpr int MC_PITCH = 528;                // raw row pitch in a stage: 512 + 16 so that rows g, g+1, .. hit distinct banks
 constexpr int MC_RAW_STAGE = MC_ENT * MC_PITCH + MC_ENT * 4;   // + the effect-allele byte patterns of the 64 entries
 constexpr int MC_A_STAGE = MC_M * 128, MC_B_STAGE = MC_N * 128;
 constexpr int MC_CW = 8;                     // converter warps
-constexpr int MC_THREADS = (4 + 2 + MC_CW) * 32;
-constexpr int MC_EPI_PITCH = 33;             // words; conflict-free transpose
+constexpr int MC_PW = 4;                     // raw producer warps: a bulk copy is issued by one thread at a time per warp
+constexpr int MC_W_MMA = 4 + MC_PW, MC_W_A = MC_W_MMA + 1, MC_FIRST_CW = MC_W_A + 1;   // warps 0..3 epilogue, 4..7 producers, 8 MMA, 9 A loader, 10.. converters
+constexpr int MC_THREADS = (MC_FIRST_CW + MC_CW) * 32;
+constexpr int MC_EPI_COLS = 16;              // accumulator columns per epilogue step
+constexpr int MC_EPI_PITCH = MC_EPI_COLS + 1; // words; conflict-free transpose
 constexpr int MC_OFF_B = 0;
 constexpr int MC_OFF_A = MC_OFF_B + MC_BS * MC_B_STAGE;
 constexpr int MC_OFF_RAW = MC_OFF_A + MC_AS * MC_A_STAGE;
@@ -106,6 +111,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
                    "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
                    "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -164,13 +176,13 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
     const int64_t n_tiles = (P.n + MC_N - 1) / MC_N;
 
     if (tid == 0) {
-        for (int i = 0; i < MC_RS; i++) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, MC_CW); }
+        for (int i = 0; i < MC_RS; i++) { mbar_init(raw_full + 8 * i, MC_PW); mbar_init(raw_empty + 8 * i, MC_CW); }
         for (int i = 0; i < MC_BS; i++) { mbar_init(b_full + 8 * i, MC_CW); mbar_init(b_empty + 8 * i, 1); }
         for (int i = 0; i < MC_AS; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
         for (int i = 0; i < MC_TS; i++) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == MC_W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -179,33 +191,42 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
     tc_fence_after();
     const uint32_t tmem = lds_u32(sTmem);
 
-    if (warp == 4) {
-        // ===== producer =====
+    if (warp >= 4 && warp < 4 + MC_PW) {
+        // ===== raw producers: warp pw brings entries pw*16 .. pw*16+15 of every k-block =====
         const uint64_t pol_stream = l2_evict_first_policy(), pol_keep = l2_evict_last_policy();
+        constexpr int PER = MC_ENT / MC_PW;
+        const int pw = warp - 4, el = pw * PER + (lane % PER);
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t byte0 = tile * (MC_N * 2);
             const uint32_t seg = (uint32_t)min((int64_t)(MC_N * 2), P.row_stride - byte0);      // multiple of 16: row_stride is
-            int32_t r0 = P.entry_row[lane], r1 = P.entry_row[lane + 32];
+            int32_t r0 = P.entry_row[el];
             for (int kb = 0; kb < P.n_kb; kb++, it++) {
-                const uint32_t rs = it % MC_RS, as = it % MC_AS;
+                const uint32_t rs = it % MC_RS;
                 const uint32_t stage = sRaw + rs * MC_RAW_STAGE;
                 mbar_wait(raw_empty + 8 * rs, ((it / MC_RS) & 1) ^ 1);
-                if (lane == 0) mbar_arrive_expect_tx(raw_full + 8 * rs, seg * MC_ENT + MC_ENT * 4);
+                if (lane == 0) mbar_arrive_expect_tx(raw_full + 8 * rs, seg * PER + (pw == 0 ? MC_ENT * 4 : 0));
                 __syncwarp();
-                tma_load_1d(stage + lane * MC_PITCH, P.gt + (int64_t)r0 * P.row_stride + byte0, seg, raw_full + 8 * rs, pol_stream);
-                tma_load_1d(stage + (lane + 32) * MC_PITCH, P.gt + (int64_t)r1 * P.row_stride + byte0, seg, raw_full + 8 * rs, pol_stream);
-                if (lane == 0) tma_load_1d(stage + MC_ENT * MC_PITCH, P.entry_pat + (int64_t)kb * MC_ENT, MC_ENT * 4, raw_full + 8 * rs, pol_keep);
-                if (kb + 1 < P.n_kb) { r0 = P.entry_row[(kb + 1) * MC_ENT + lane]; r1 = P.entry_row[(kb + 1) * MC_ENT + lane + 32]; }
-                if (lane == 0) {
+                if (lane < PER) tma_load_1d(stage + el * MC_PITCH, P.gt + (int64_t)r0 * P.row_stride + byte0, seg, raw_full + 8 * rs, pol_stream);
+                if (pw == 0 && lane == 0) tma_load_1d(stage + MC_ENT * MC_PITCH, P.entry_pat + (int64_t)kb * MC_ENT, MC_ENT * 4, raw_full + 8 * rs, pol_keep);
+                if (kb + 1 < P.n_kb) r0 = P.entry_row[(kb + 1) * MC_ENT + el];
+                __syncwarp();
+            }
+        }
+    } else if (warp == MC_W_A) {
+        // ===== digit-tile loader: its own ring, so that it never holds the raw producer back =====
+        if (lane == 0) {
+            const uint64_t pol_keep = l2_evict_last_policy();
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int kb = 0; kb < P.n_kb; kb++, it++) {
+                    const uint32_t as = it % MC_AS;
                     mbar_wait(a_empty + 8 * as, ((it / MC_AS) & 1) ^ 1);
                     mbar_arrive_expect_tx(a_full + 8 * as, MC_A_STAGE);
                     tma_load_1d(sA + as * MC_A_STAGE, P.A + (int64_t)kb * MC_A_STAGE, MC_A_STAGE, a_full + 8 * as, pol_keep);
                 }
-                __syncwarp();
-            }
         }
-    } else if (warp == 5) {
+    } else if (warp == MC_W_MMA) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             uint32_t it = 0, tcount = 0;
@@ -229,9 +250,9 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                 umma_commit(t_full + 8 * ts);
             }
         }
-    } else if (warp >= 6) {
+    } else if (warp >= MC_FIRST_CW) {
         // ===== converters =====
-        const int cw = warp - 6, g = lane & 7, qsub = lane >> 3;
+        const int cw = warp - MC_FIRST_CW, g = lane & 7, qsub = lane >> 3;
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < P.n_kb; kb++, it++) {
@@ -275,20 +296,23 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
             const uint32_t ts = tcount % MC_TS;
             mbar_wait(t_full + 8 * ts, (tcount / MC_TS) & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < MC_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ts * MC_N + c0, v);
+            for (int c0 = 0; c0 < MC_N; c0 += MC_EPI_COLS) {
+                uint32_t v[MC_EPI_COLS];
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + ts * MC_N + c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; j++) sts_u32(epi + (lane * MC_EPI_PITCH + j) * 4, v[j]);
+                for (int j = 0; j < MC_EPI_COLS; j++) sts_u32(epi + (lane * MC_EPI_PITCH + j) * 4, v[j]);
                 __syncwarp();
-                const int64_t s = tile * MC_N + c0 + lane;               // this lane's sample (column c0 + lane)
+                // lane -> column c0 + (lane & 15), scores 2*(lane>>4) and 2*(lane>>4)+1 of this warp's four
+                const int col = lane & 15;
+                const int64_t s = tile * MC_N + c0 + col;
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
+                for (int kh = 0; kh < 2; kh++) {
+                    const int kk = (lane >> 4) * 2 + kh;
                     const int k = warp * 4 + kk;
                     if (k < P.n_scores) {
                         int32_t x[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) x[j] = (int32_t)lds_u32(epi + ((kk * 8 + j) * MC_EPI_PITCH + lane) * 4);
+                        for (int j = 0; j < 8; j++) x[j] = (int32_t)lds_u32(epi + ((kk * 8 + j) * MC_EPI_PITCH + col) * 4);
                         const long long lo = (long long)x[0] + ((long long)x[1] << 8) + ((long long)x[2] << 16) + ((long long)x[3] << 24);
                         const long long hi = (long long)x[4] + ((long long)x[5] << 8) + ((long long)x[6] << 16);
                         double sum = __dadd_rn(__dmul_rn((double)hi, P.sc_hi[k]), __dmul_rn((double)lo, P.sc_lo[k]));
@@ -306,7 +330,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == MC_W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 // ---- coefficient preparation -------------------------------------------------------------------

@@ -64,6 +64,7 @@ def load_library():
         "npc_accumulate_block_device": (C.c_int, [vp, vp, i64, i64, vp, i64, i32, vp]),
         "npc_resident_reserve": (C.c_int, [vp, i64, pi64]),
         "npc_stage_upload": (C.c_int, [vp, i32, i64, i64]),
+        "npc_resident_adopt": (C.c_int, [vp, vp, i64, i64]),
         "npc_score_resident": (C.c_int, [vp, vp, i64]),
         "npc_multi_contractions": (C.c_int64, [vp]),
         "npc_score_resident_multi": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
@@ -164,6 +165,9 @@ class Engine:
         self._ck(self.L.npc_resident_reserve(self.h, int(capacity_rows), C.byref(g)))
         return g.value
 
+    def resident_adopt(self, gt_dev, row_stride, n_gt_rows):
+        self._ck(self.L.npc_resident_adopt(self.h, _ptr(gt_dev), int(row_stride), int(n_gt_rows)))
+
     def stage_upload(self, slot, n_gt_rows, dst_row):
         self._ck(self.L.npc_stage_upload(self.h, slot, int(n_gt_rows), int(dst_row)))
 
@@ -171,15 +175,16 @@ class Engine:
         rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
         self._ck(self.L.npc_score_resident(self.h, rows.ctypes.data, len(rows)))
 
-    def score_resident_multi(self, rows_list, offsets):
-        """npc_score_resident_multi -> [(scores, nloci, loci)] per score definition."""
+    def score_resident_multi(self, rows_list, offsets, scores=None, loci=None):
+        """npc_score_resident_multi -> [(scores, nloci, loci)] per score definition.  scores / loci:
+        optional preallocated output arrays (e.g. views of pinned memory), one per definition."""
         S = len(rows_list)
         rows_list = [np.ascontiguousarray(r, dtype=ROW_DTYPE) for r in rows_list]
         rp = (C.c_void_p * S)(*[r.ctypes.data for r in rows_list])
         nr = np.array([len(r) for r in rows_list], dtype=np.int64)
         off = np.array(offsets, dtype=np.float64)
-        scores = [np.zeros(self.n, dtype=np.float64) for _ in range(S)]
-        loci = [np.zeros(len(r), dtype=LOCUS_DTYPE) for r in rows_list]
+        scores = scores if scores is not None else [np.zeros(self.n, dtype=np.float64) for _ in range(S)]
+        loci = loci if loci is not None else [np.zeros(len(r), dtype=LOCUS_DTYPE) for r in rows_list]
         sp = (C.c_void_p * S)(*[a.ctypes.data for a in scores])
         lp = (C.c_void_p * S)(*[a.ctypes.data for a in loci])
         nloci = np.zeros(S, dtype=np.int64)
