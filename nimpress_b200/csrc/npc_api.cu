@@ -616,7 +616,7 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
         for (int64_t i = 0; i < n_rows[k]; i++) {
             const npc_row &r = rows[k][i];
             const int64_t j = row0[k] + i;
-            score_of[j] = k % npc::MC_SCORES;
+            score_of[j] = k;
             if (r.kind != NPC_KIND_GT || r.gt_row < 0) continue;
             if (r.gt_row >= c->slab_rows) return fail(c, NPC_EINVAL, "npc_score_resident_multi: gt_row outside the resident slab");
             if (r.eaidx < 0 || r.eaidx > 62) return 1;               // no int8 code can match: leave it to the general path
@@ -704,15 +704,17 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     NPC_CUDA(c, cudaStreamSynchronize(st));
     mark("decide + scale + log D2H");
     std::vector<int32_t> fexp(S, 0);
+    int rps = npc::MC_DIGITS;
     for (int k = 0; k < S; k++) {
-        if (scale[k].flags) return 1;
+        if (scale[k].flags & 1) return 1;
+        if (scale[k].flags & 2) rps = npc::MC_DIGITS + 1;                // some imputed contribution is NaN: add the counter rows
         int ex = 0;
         if (scale[k].maxabs > 0) { frexp(scale[k].maxabs, &ex); fexp[k] = 52 - ex; }
         if (fexp[k] > 900 || fexp[k] < -900) return 1;
     }
     NPC_CUDA(c, cudaMemcpyAsync(d_fexp, fexp.data(), S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
 
-    // ---- contraction, sixteen definitions per launch ------------------------------------------------
+    // ---- contraction -------------------------------------------------------------------------------
     static bool attr_set = false;
     if (!attr_set) {
         NPC_CUDA(c, cudaFuncSetAttribute(k_multi_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, npc::MC_SMEM));
@@ -720,22 +722,23 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     }
     const int64_t n_tiles = (c->n + npc::MC_N - 1) / npc::MC_N;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, c->num_sms > 0 ? c->num_sms : 148);
-    for (int k0 = 0; k0 < S; k0 += npc::MC_SCORES) {
-        const int ng = std::min(npc::MC_SCORES, S - k0);
+    const int per_launch = npc::MC_M / rps;                             // 18 definitions of 7 rows, or 16 of 8
+    for (int k0 = 0; k0 < S; k0 += per_launch) {
+        const int ng = std::min(per_launch, S - k0);
         NPC_CUDA(c, cudaMemsetAsync(d_coef, 0, (size_t)ng * 2 * Ep * sizeof(long long), st));
         NPC_CUDA(c, cudaMemsetAsync(d_pois, 0, (size_t)ng * Ep, st));
         const int64_t ra = row0[k0], rb = row0[k0 + ng];
         if (rb > ra) {
-            k_multi_coef<<<(unsigned)((rb - ra + 255) / 256), 256, 0, st>>>(d_rowp + ra, d_ent + ra, d_score_of + ra, rb - ra, d_fexp + k0, Ep,
+            k_multi_coef<<<(unsigned)((rb - ra + 255) / 256), 256, 0, st>>>(d_rowp + ra, d_ent + ra, d_score_of + ra, rb - ra, k0, d_fexp + k0, Ep,
                                                                            d_coef, d_pois);
             c->launches++;
         }
-        k_multi_digits<<<dim3((unsigned)n_kb, npc::MC_M), 128, 0, st>>>(d_coef, d_pois, Ep, ng, d_A);
+        k_multi_digits<<<dim3((unsigned)n_kb, npc::MC_M), 128, 0, st>>>(d_coef, d_pois, Ep, ng, rps, d_A);
         c->launches++;
         MultiParams P;
         memset(&P, 0, sizeof(P));
         P.gt = c->d_slab; P.row_stride = c->slab_stride; P.n = c->n;
-        P.entry_row = d_entry_row; P.entry_pat = d_entry_pat; P.A = d_A; P.n_kb = n_kb; P.n_scores = ng;
+        P.entry_row = d_entry_row; P.entry_pat = d_entry_pat; P.A = d_A; P.n_kb = n_kb; P.n_scores = ng; P.rps = rps;
         for (int k = 0; k < ng; k++) {
             P.sc_lo[k] = ldexp(1.0, -fexp[k0 + k]); P.sc_hi[k] = ldexp(1.0, 32 - fexp[k0 + k]);
             P.consts[k] = scale[k0 + k].consts; P.denom[k] = (double)(int64_t)nloci[k0 + k] * 2.0; P.offset[k] = offsets[k0 + k];

@@ -21,9 +21,9 @@
 // reference (tests measure ~1e-15).  Per-locus records and nloci come from the same k_decide as
 // every other path: bit-equal.
 //
-// An eighth row per score counts, per sample, the missing calls at entries whose imputed
-// contribution is NaN (--imp-sample=fail / int_fail, eaf = NaN): count > 0 -> score NaN, as the
-// reference's NaN propagation gives.
+// When some imputed contribution is NaN (--imp-sample=fail / int_fail, eaf = NaN) an eighth row per
+// score counts, per sample, the missing calls at those entries: count > 0 -> score NaN, as the
+// reference's NaN propagation gives.  128 accumulator rows hold 18 scores of 7 rows or 16 of 8.
 //
 // Kernel k_multi_contract: persistent, one CTA per SM, a tile = 256 samples x all entries.
 //   warps 4..7   producers: per k-block (64 entries) 64 TMA bulk copies of 512 B (one per genotype row
@@ -35,7 +35,7 @@
 //                operand B, K-major, 128-byte swizzle (the canonical UMMA layout), 2-stage ring
 //   warp 8       one thread issues 4 x tcgen05.mma (M=128, N=256, K=32) per k-block; tcgen05.commit
 //                releases the A / B stages and, after the last k-block, hands the accumulator over
-//   warps 0..3   epilogue: tcgen05.ld -> smem transpose -> int64 recombination -> normalise
+//   warps 0..3   epilogue: tcgen05.ld -> smem (all 128 rows) -> int64 recombination -> normalise
 //                (:643-649) -> coalesced stores; two accumulators (2 x 256 TMEM columns) so the
 //                epilogue of tile t overlaps the main loop of tile t+1
 #pragma once
@@ -43,16 +43,16 @@
 
 namespace npc {
 
-constexpr int MC_M = 128;                    // UMMA M: 16 scores x 8 rows (7 digits + NaN counter)
+constexpr int MC_M = 128;                    // UMMA M: rows_per_score rows for each score
 constexpr int MC_N = 256;                    // UMMA N: samples per tile
 constexpr int MC_ENT = 64;                   // entries per k-block -> 128 plane rows = one 128-byte swizzle row of K
-constexpr int MC_SCORES = 16;                // scores per launch
+constexpr int MC_SCORES = 18;                // scores per launch: 18 x 7 digit rows, or 16 x (7 digits + NaN counter)
 constexpr int MC_DIGITS = 7;
 constexpr int MC_RS = 3, MC_BS = 2, MC_AS = 3, MC_TS = 2;   // ring depths: raw, B, A, accumulators
 constexpr int MC_PITCH = 528;                // raw row pitch in a stage: 512 + 16 so that rows g, g+1, .. hit distinct banks
 constexpr int MC_RAW_STAGE = MC_ENT * MC_PITCH + MC_ENT * 4;   // + the effect-allele byte patterns of the 64 entries
 constexpr int MC_A_STAGE = MC_M * 128, MC_B_STAGE = MC_N * 128;
-constexpr int MC_CW = 8;                     // converter warps
+constexpr int MC_CW = 16;                    // converter warps: one 8-entry x 4-sample-quad step each per k-block
 constexpr int MC_PW = 4;                     // raw producer warps: a bulk copy is issued by one thread at a time per warp
 constexpr int MC_W_MMA = 4 + MC_PW, MC_W_A = MC_W_MMA + 1, MC_FIRST_CW = MC_W_A + 1;   // warps 0..3 epilogue, 4..7 producers, 8 MMA, 9 A loader, 10.. converters
 constexpr int MC_THREADS = (MC_FIRST_CW + MC_CW) * 32;
@@ -73,6 +73,7 @@ struct MultiParams {
     const uint32_t *entry_pat;               // [n_kb*64] (eaidx+1)<<1 in all four bytes
     const uint8_t *A;                        // [n_kb][16 KB] digit tiles, already in the swizzled smem layout
     int32_t n_kb, n_scores;
+    int32_t rps, pad;                        // rows per score: 7 digits, or 8 = 7 digits + NaN counter
     double sc_lo[MC_SCORES], sc_hi[MC_SCORES];   // 2^-F and 2^(32-F) of each score's fixed-point scale
     double consts[MC_SCORES];                // sum of the constant (whole-locus) contributions, NaN if any is NaN
     double denom[MC_SCORES];                 // 2 * nloci
@@ -135,12 +136,11 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void convert4(uint32_t w0, uint32_t w1, uint32_t pat, int eaidx, uint32_t &d4, uint32_t &m4) {
     if (((w0 | w1) & 0x80808080u) == 0u) {
         const uint32_t a0 = __byte_perm(w0, w1, 0x6420), a1 = __byte_perm(w0, w1, 0x7531);   // first / second allele of the 4 samples
-        const uint32_t ne0 = (((a0 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu), ne1 = (((a1 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu);
-        const uint32_t nz0 = ((a0 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu), nz1 = ((a1 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu);
-        const uint32_t called = ((nz0 & nz1) >> 7) & 0x01010101u;                            // 1 = both alleles called
-        const uint32_t d = 0x02020202u - ((ne0 >> 7) & 0x01010101u) - ((ne1 >> 7) & 0x01010101u);
-        d4 = d & (called * 3u);
-        m4 = called ^ 0x01010101u;
+        const uint32_t ne0 = ((a0 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu, ne1 = ((a1 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu;   // bit 7: allele != effect allele
+        const uint32_t nz0 = (a0 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu, nz1 = (a1 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu;                   // bit 7: allele called
+        const uint32_t called = nz0 & nz1 & 0x80808080u;                                       // bit 7: both alleles called
+        d4 = ((~ne0 & called) >> 7) + ((~ne1 & called) >> 7);
+        m4 = (called >> 7) ^ 0x01010101u;
     } else {
         d4 = 0; m4 = 0;
 #pragma unroll
@@ -263,9 +263,8 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                 uint32_t pat[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) pat[j] = lds_u32(stage + MC_ENT * MC_PITCH + (g + 8 * j) * 4);
-#pragma unroll
-                for (int st = 0; st < 2; st++) {
-                    const int q = (cw * 2 + st) * 4 + qsub;              // sample quad 0..63 of the tile
+                {
+                    const int q = cw * 4 + qsub;                         // sample quad 0..63 of the tile
                     uint32_t D[8], M[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {                        // entry g + 8j of the k-block
@@ -289,9 +288,9 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = rows of scores 4w..4w+3 =====
-        const uint32_t epi = sEpi + warp * (32 * MC_EPI_PITCH * 4);
+        // ===== epilogue: warp w reads TMEM lanes 32w..32w+31 (rows of the digit tile) =====
         uint32_t tcount = 0;
+        const int col = tid & 15, grp = tid >> 4;                            // column of the step, score group 0..7
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
             const uint32_t ts = tcount % MC_TS;
             mbar_wait(t_full + 8 * ts, (tcount / MC_TS) & 1);
@@ -300,19 +299,16 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                 uint32_t v[MC_EPI_COLS];
                 tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + ts * MC_N + c0, v);
 #pragma unroll
-                for (int j = 0; j < MC_EPI_COLS; j++) sts_u32(epi + (lane * MC_EPI_PITCH + j) * 4, v[j]);
-                __syncwarp();
-                // lane -> column c0 + (lane & 15), scores 2*(lane>>4) and 2*(lane>>4)+1 of this warp's four
-                const int col = lane & 15;
+                for (int j = 0; j < MC_EPI_COLS; j++) sts_u32(sEpi + (tid * MC_EPI_PITCH + j) * 4, v[j]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps: rows of one score may span two of them
                 const int64_t s = tile * MC_N + c0 + col;
 #pragma unroll
-                for (int kh = 0; kh < 2; kh++) {
-                    const int kk = (lane >> 4) * 2 + kh;
-                    const int k = warp * 4 + kk;
+                for (int kq = 0; kq < (MC_SCORES + 7) / 8; kq++) {
+                    const int k = grp + 8 * kq;
                     if (k < P.n_scores) {
                         int32_t x[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) x[j] = (int32_t)lds_u32(epi + ((kk * 8 + j) * MC_EPI_PITCH + col) * 4);
+                        for (int j = 0; j < 8; j++) x[j] = j < P.rps ? (int32_t)lds_u32(sEpi + ((k * P.rps + j) * MC_EPI_PITCH + col) * 4) : 0;
                         const long long lo = (long long)x[0] + ((long long)x[1] << 8) + ((long long)x[2] << 16) + ((long long)x[3] << 24);
                         const long long hi = (long long)x[4] + ((long long)x[5] << 8) + ((long long)x[6] << 16);
                         double sum = __dadd_rn(__dmul_rn((double)hi, P.sc_hi[k]), __dmul_rn((double)lo, P.sc_lo[k]));
@@ -321,7 +317,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                         if (s < P.n) P.out[k][s] = __dadd_rn(__ddiv_rn(sum, P.denom[k]), P.offset[k]);   // :643-649
                     }
                 }
-                __syncwarp();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             tc_fence_before();
             __syncwarp();
@@ -344,7 +340,7 @@ __global__ void k_multi_gather(const int32_t *__restrict__ ent, int64_t n_rows, 
     counts[2 * r + 1] = e >= 0 ? ecounts[2 * e + 1] : 0;
 }
 
-struct MultiScale { double maxabs; double consts; int32_t flags; int32_t pad; };   // flags bit 0: not representable -> caller falls back
+struct MultiScale { double maxabs; double consts; int32_t flags; int32_t pad; };   // flags bit 0: not representable -> caller falls back; bit 1: has NaN cm
 
 // One block per score: largest |coefficient| over its OK rows, the ordered sum of its constant rows
 // (fixed order: 256 contiguous chunks, then the chunk sums left to right), and the fallback flag.
@@ -363,6 +359,7 @@ __global__ void __launch_bounds__(256) k_multi_scale(const RowP *__restrict__ ro
             else {
                 mx = fmax(mx, fabs(rp.c1));
                 if (rp.cm == rp.cm) { if (fabs(rp.cm) > 1.79e308) flags |= 1; else mx = fmax(mx, fabs(rp.cm)); }
+                else flags |= 2;                                      // a NaN imputed contribution: the launch needs the NaN counter rows
             }
         }
     }
@@ -383,25 +380,25 @@ __global__ void __launch_bounds__(256) k_multi_scale(const RowP *__restrict__ ro
 
 // coef[(k*2 + plane) * E + e] += round(c * 2^F_k): exact integer adds, so repeated rows of one score commute
 __global__ void k_multi_coef(const RowP *__restrict__ rowp, const int32_t *__restrict__ ent, const int32_t *__restrict__ score_of, int64_t n_rows,
-                             const int32_t *__restrict__ fexp, int64_t E, long long *__restrict__ coef, uint8_t *__restrict__ pois) {
+                             int k0, const int32_t *__restrict__ fexp, int64_t E, long long *__restrict__ coef, uint8_t *__restrict__ pois) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const RowP rp = rowp[r];
     const int32_t e = ent[r];
     if (rp.mode != MODE_DECODE || e < 0) return;
     if (!(fabs(rp.c1) <= 1.79e308) || rp.c0 != 0.0) return;             // counted as a NaN constant by k_multi_scale
-    const int k = score_of[r];
+    const int k = score_of[r] - k0;                                    // score within this launch
     const int F = fexp[k];
     atomicAdd((ull *)&coef[((int64_t)k * 2 + 0) * E + e], (ull)__double2ll_rn(scalbn(rp.c1, F)));
     if (rp.cm == rp.cm) atomicAdd((ull *)&coef[((int64_t)k * 2 + 1) * E + e], (ull)__double2ll_rn(scalbn(rp.cm, F)));
     else pois[(int64_t)k * E + e] = 1;
 }
 
-// digit tiles: image kb, row R = score*8 + digit (digit 7 = NaN counter), K byte kbyte = 16*g + 8*plane + j  <->  entry kb*64 + g + 8j
+// digit tiles: image kb, row R = score*rps + digit (digit 7 = NaN counter), K byte kbyte = 16*g + 8*plane + j  <->  entry kb*64 + g + 8j
 __global__ void __launch_bounds__(128) k_multi_digits(const long long *__restrict__ coef, const uint8_t *__restrict__ pois, int64_t E, int n_scores,
-                                                     uint8_t *__restrict__ A) {
+                                                     int rps, uint8_t *__restrict__ A) {
     const int kb = blockIdx.x, R = blockIdx.y, kbyte = threadIdx.x;
-    const int k = R >> 3, dg = R & 7, g = kbyte >> 4, plane = (kbyte >> 3) & 1, j = kbyte & 7;
+    const int k = R / rps, dg = R % rps, g = kbyte >> 4, plane = (kbyte >> 3) & 1, j = kbyte & 7;
     const int64_t e = (int64_t)kb * MC_ENT + g + 8 * j;
     int8_t val = 0;
     if (k < n_scores && e < E) {
