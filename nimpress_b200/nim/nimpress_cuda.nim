@@ -59,7 +59,11 @@ proc npc_accumulate_block_device*(ctx: NpcCtx; gtDev: pointer; rowStride, nGtRow
                                   nRows: int64; rowsOnDevice: int32; countsDev: ptr int64): cint
 proc npc_resident_reserve*(ctx: NpcCtx; capacityRows: int64; grantedRows: ptr int64): cint
 proc npc_stage_upload*(ctx: NpcCtx; slot: int32; nGtRows, dstRow: int64): cint
+proc npc_resident_adopt*(ctx: NpcCtx; gtDev: pointer; rowStride, nGtRows: int64): cint
 proc npc_score_resident*(ctx: NpcCtx; rows: ptr NpcRow; nRows: int64): cint
+proc npc_score_resident_multi*(ctx: NpcCtx; nScores: int32; rows: ptr ptr NpcRow; nRows: ptr int64;
+                               offsets: ptr float64; scoresOut: ptr ptr float64; nlociOut: ptr int64;
+                               lociOut: ptr ptr NpcLocus): cint
 proc npc_finish*(ctx: NpcCtx; offset: float64; scoresOut: ptr float64; nlociOut: ptr int64;
                  lociOut: ptr NpcLocus; lociCap: int64; nLociOut: ptr int64): cint
 proc npc_partial*(ctx: NpcCtx; sumsOut: ptr float64; nlociOut: ptr int64; lociOut: ptr NpcLocus;
@@ -67,6 +71,7 @@ proc npc_partial*(ctx: NpcCtx; sumsOut: ptr float64; nlociOut: ptr int64; lociOu
 proc npc_partial_device_ptr*(ctx: NpcCtx; sumsDev: ptr ptr float64; nlociDev: ptr ptr int64): cint
 proc npc_normalise*(sums: ptr float64; n, nloci: int64; offset: float64)
 proc npc_launch_count*(ctx: NpcCtx): int64
+proc npc_multi_contractions*(ctx: NpcCtx): int64
 proc npc_kernel_shape*(ctx: NpcCtx; shape: ptr array[8, int32]): cint
 proc npc_synth_fill_device*(ctx: NpcCtx; gtDev: pointer; rowStride, v0, nRows: int64; seed: uint64;
                             afThr16Dev, missThr24Dev: ptr uint32; altCodeDev: ptr int32): cint
