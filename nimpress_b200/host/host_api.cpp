@@ -224,6 +224,23 @@ static int parse_enum(const std::string &v, std::initializer_list<const char *> 
     throw InputError("invalid enum value: " + v);
 }
 
+// WARN lines, then one `name<TAB>$score` line per sample (:752-753), formatted into one buffer
+static void print_result(const nph_result *r) {
+    std::string out = r->r.warnings;
+    const std::vector<double> &s = r->r.scores;
+    size_t names = 0;
+    for (const std::string &nm : r->r.samples) names += nm.size();
+    out.reserve(out.size() + names + s.size() * 28);
+    char buf[48];
+    for (size_t i = 0; i < s.size(); i++) {
+        out += r->r.samples[i];
+        out += '\t';
+        out.append(buf, (size_t)format_float_nim_to(s[i], buf));
+        out += '\n';
+    }
+    std::cout.write(out.data(), (std::streamsize)out.size());
+}
+
 int nph_main(int argc, char **argv) {
     nph_params p = { NPC_LOCUS_PS, NPC_MISSING_HOMREF, NPC_SAMPLE_INT_PS, 0, 0, 0, 0, 0, 100, 0.05, 0.001 };
     std::string cov, pos[2];
@@ -270,10 +287,8 @@ int nph_main(int argc, char **argv) {
         if (rc == NPH_EOPEN_SCORE) { std::cout << "FATAL " << nph_last_error() << "\n"; return 255; }
         if (rc) { std::cerr << "nimpress: " << nph_last_error() << "\n"; return 1; }
         for (size_t k = 0; k < rs.size(); k++) {           // per file: a "#score" line, then the reference's output for it
-            std::cout << "#score\t" << paths[k] << "\n" << nph_result_warnings(rs[k]);
-            const double *s = nph_result_scores(rs[k]);
-            for (int64_t i = 0; i < nph_result_n_samples(rs[k]); i++)
-                std::cout << nph_result_sample(rs[k], i) << "\t" << format_float_nim(s[i]) << "\n";
+            std::cout << "#score\t" << paths[k] << "\n";
+            print_result(rs[k]);
             nph_result_free(rs[k]);
         }
         return 0;
@@ -283,10 +298,7 @@ int nph_main(int argc, char **argv) {
     if (rc == NPH_EOPEN_VCF) { std::cout << "FATAL Could not open input VCF file " << pos[1] << "\n"; return 255; }          // :729-730
     if (rc == NPH_EOPEN_SCORE) { std::cout << "FATAL Could not open polygenic score file " << pos[0] << "\n"; return 255; } // :733-734
     if (rc) { std::cerr << "nimpress: " << nph_last_error() << "\n"; return 1; }
-    std::cout << nph_result_warnings(r);
-    const double *s = nph_result_scores(r);
-    for (int64_t i = 0; i < nph_result_n_samples(r); i++)                      // :752-753
-        std::cout << nph_result_sample(r, i) << "\t" << format_float_nim(s[i]) << "\n";
+    print_result(r);
     nph_result_free(r);
     return 0;
 }
