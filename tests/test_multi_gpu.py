@@ -252,3 +252,28 @@ def test_config4_contraction_200k(nb):
     worst = check_lists(got, gt, n, lists, offs, False, 1e-12, threads=8)
     print(f"config 4 contraction: worst relative deviation {worst:.3e}")
     eng.close()
+
+
+def test_multi_wider_layout_restarts_and_scores_one_by_one(api, tmp_path):
+    """int16 GT storage and triploid calls: the pass restarts with the wider layout (as for one file) and
+    the definitions are scored by the general kernels; results still equal the oracle's per file."""
+    rng = np.random.default_rng(9)
+    d = make_dataset(str(tmp_path), rng, n=150, V=60, gt_dtype=np.int16, ploidy=3, haploid_rate=0.1)
+    paths = [d["score"]] + derive_scores(str(tmp_path), rng, d["entries"], 3)
+    got = api.run_multi(paths, d["bcf"], d["bed"])
+    for k, p in enumerate(paths):
+        check(got[k], orc.compute_scores_files(p, d["vcf"], d["bed"]), False)
+
+
+def test_multi_single_file_and_errors(api, tmp_path):
+    """One file through the multi entry point == the single entry point; a missing score file or genotype
+    file is reported like the single call reports it."""
+    rng = np.random.default_rng(10)
+    d = make_dataset(str(tmp_path), rng, n=90, V=45)
+    one = api.run(d["score"], d["bcf"], exact_order=True)
+    multi = api.run_multi([d["score"]], d["bcf"], exact_order=True)
+    assert len(multi) == 1 and np.array_equal(bits(one.scores), bits(multi[0].scores)) and multi[0].warnings == one.warnings
+    with pytest.raises(FileNotFoundError):
+        api.run_multi([d["score"], str(tmp_path / "missing.score")], d["bcf"])
+    with pytest.raises(FileNotFoundError):
+        api.run_multi([d["score"]], str(tmp_path / "missing.bcf"))
