@@ -277,3 +277,26 @@ def test_multi_single_file_and_errors(api, tmp_path):
         api.run_multi([d["score"], str(tmp_path / "missing.score")], d["bcf"])
     with pytest.raises(FileNotFoundError):
         api.run_multi([d["score"]], str(tmp_path / "missing.bcf"))
+
+
+@pytest.mark.parametrize("n,V,S", [(1, 3, 3), (5, 1, 4), (255, 64, 3), (257, 65, 19), (513, 130, 40), (515, 1300, 37), (4099, 129, 17)])
+def test_contraction_edge_shapes(nb, n, V, S):
+    """Tile and k-block edges of the contraction: fewer samples than a tile, one more than a tile, exactly /
+    one more than 64 entries, more definitions than a launch holds (several launches)."""
+    rng = np.random.default_rng(100 + n)
+    gt = random_cohort(rng, n, V, miss_rate=0.05, n_alt=2)
+    lists = [random_rows(rng, V, n_rows=int(rng.integers(1, 2 * V + 2)), n_alt=2) for _ in range(S)]
+    offs = [0.5 * k for k in range(S)]
+    eng = nb.Engine(n, max_rows_per_block=256, n_slots=2)
+    fill_slab(eng, gt, 256)
+    got = eng.score_resident_multi(lists, offs)
+    def repeats(rows):
+        g = rows[rows["kind"] == 0]
+        return max(np.unique(g["gt_row"].astype(np.int64) * 64 + g["eaidx"], return_counts=True)[1], default=0)
+    assert eng.multi_contractions == (1 if max(repeats(r) for r in lists) <= 4 else 0)      # > 4 repeats: one by one
+    check_lists(got, gt, n, lists, offs, False, 1e-12)
+    # the same slab again with other definitions: the scratch arena and the slab are reused
+    lists2 = [random_rows(rng, V, n_rows=V, n_alt=2) for _ in range(3)]
+    got2 = eng.score_resident_multi(lists2, [0.0, 0.0, 1.0])
+    check_lists(got2, gt, n, lists2, [0.0, 0.0, 1.0], False, 1e-12)
+    eng.close()
