@@ -238,6 +238,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
         records_matched++;
         if (!need_gt) continue;                                     // FILTER-failed: never decoded (:553-558)
         if (!rec.has_gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
+        vcf.load_gt(rec);
         if (rec.ploidy > ploidy || rec.gt_width > gt_width)
             throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
         if (slab_base + staged >= slab_cap) {                       // slab full: score its rows, start over

@@ -151,6 +151,7 @@ int nph_read_gt(const char *genotype_path, uint8_t *out, int64_t row_bytes, int6
         while (vcf->next(rec)) {
             if (k >= max_records) return NPH_ECAPACITY;
             if (rec.has_gt) {
+                vcf->load_gt(rec);
                 const int64_t bytes = vcf->n_samples() * rec.ploidy * rec.gt_width;
                 if (bytes > row_bytes) return NPH_ECAPACITY;
                 memcpy(out + k * row_bytes, rec.gt, (size_t)bytes);

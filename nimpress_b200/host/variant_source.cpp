@@ -348,10 +348,46 @@ public:
             q = t + 1;
         }
         if (gt_idx < 0) return true;
-        // per-sample GT strings -> (allele+1)<<1|phased, htslib vcf_parse_format
+        // the genotype columns are parsed only if the caller asks (load_gt): most records of a
+        // genome-wide file match no score row
+        rec.has_gt = true;
+        gt_p_ = p; gt_idx_ = gt_idx; gt_loaded_ = false;
+        return true;
+    }
+    void load_gt(VariantRecord &rec) override {
+        if (!rec.has_gt || gt_loaded_) return;
+        gt_loaded_ = true;
+        const char *p = gt_p_, *end = line_.data() + line_.size();
         const int64_t n = n_samples();
+        // fast path: every sample is "a/b" or "a|b" with one-character alleles and GT the first
+        // sub-field -- written straight as int8 (allele+1)<<1|phased (htslib vcf_parse_format)
+        if (gt_idx_ == 0 && p <= end) {
+            gt_.resize((size_t)n * 2);
+            int8_t *out = (int8_t *)gt_.data();
+            const char *s = p;
+            int64_t i = 0;
+            for (; i < n; i++) {
+                if (end - s < 3) break;
+                const char c0 = s[0], sep = s[1], c1 = s[2];
+                const bool ok0 = c0 == '.' || (c0 >= '0' && c0 <= '9'), ok1 = c1 == '.' || (c1 >= '0' && c1 <= '9');
+                if (!ok0 || !ok1 || (sep != '/' && sep != '|')) break;
+                const char *t = s + 3;
+                if (t < end && *t != '\t') {
+                    if (*t != ':') break;                          // longer allele number or another ploidy
+                    t = (const char *)memchr(t, '\t', end - t);
+                    if (!t) t = end;
+                }
+                out[2 * i] = c0 == '.' ? 0 : (int8_t)((c0 - '0' + 1) << 1);
+                out[2 * i + 1] = (int8_t)((c1 == '.' ? 0 : ((c1 - '0' + 1) << 1)) | (sep == '|'));
+                s = t + 1;
+                if (t >= end && i + 1 < n) { i++; break; }
+            }
+            if (i == n) { rec.ploidy = 2; rec.gt_width = 1; rec.gt = gt_.data(); return; }
+        }
+        // general path: per-sample GT strings -> (allele+1)<<1|phased, any ploidy, any allele number
         vals_.clear(); counts_.assign(n, 0);
         int maxp = 1;
+        const int gt_idx = gt_idx_;
         for (int64_t i = 0; i < n; i++) {
             const char *s = p <= end ? p : end, *se = end;
             if (p <= end) {
@@ -381,12 +417,14 @@ public:
             maxp = std::max(maxp, l);
         }
         pack_gt(vals_, counts_, n, maxp, gt_, rec.gt_width);
-        rec.ploidy = maxp; rec.gt = gt_.data(); rec.has_gt = true;
-        return true;
+        rec.ploidy = maxp; rec.gt = gt_.data();
     }
 private:
     std::unique_ptr<InflateStream> in_;
     std::string line_, contig_;
+    const char *gt_p_ = nullptr;
+    int gt_idx_ = -1;
+    bool gt_loaded_ = true;
     std::vector<int32_t> vals_;
     std::vector<int> counts_;
     std::vector<uint8_t> gt_;

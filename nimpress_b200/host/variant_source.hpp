@@ -56,8 +56,8 @@ struct VariantRecord {
     std::vector<std::string> alts;
     std::string filter;                               // ".", "PASS" or ';'-joined names
     bool has_gt = false;
-    int gt_width = 1, ploidy = 0;                     // bytes per value, values per sample
-    const uint8_t *gt = nullptr;                      // n_samples * ploidy * gt_width bytes, valid until next()
+    int gt_width = 1, ploidy = 0;                     // bytes per value, values per sample            } after
+    const uint8_t *gt = nullptr;                      // n_samples * ploidy * gt_width bytes, until next() } load_gt()
     int64_t end() const { return pos + rlen - 1; }    // 1-based inclusive
 };
 
@@ -65,6 +65,9 @@ class VariantSource {
 public:
     virtual ~VariantSource() = default;
     virtual bool next(VariantRecord &rec) = 0;        // false at end of file; throws InputError on corrupt input
+    // Fills rec.gt / ploidy / gt_width of the record next() just returned (rec.has_gt tells whether
+    // it has a GT field).  Text VCF parses its genotype columns only here; BCF has them already.
+    virtual void load_gt(VariantRecord &) {}
     const std::vector<std::string> &samples() const { return samples_; }
     int64_t n_samples() const { return (int64_t)samples_.size(); }
 protected:
