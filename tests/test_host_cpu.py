@@ -212,3 +212,37 @@ def test_bgzf_thread_pool_equals_sequential(api, tmp_path, monkeypatch):
     out = np.zeros((400, 6016), np.uint8)
     nrec, ns, w, pl = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
     assert L.nph_read_gt(os.fsencode(bad), out.ctypes.data, 6016, 400, C.byref(nrec), C.byref(ns), C.byref(w), C.byref(pl)) == -3
+
+
+def test_vcf_text_gt_paths(api, tmp_path):
+    """Hand-written VCF text lines through both GT parsers of the text reader: the direct int8 path
+    (diploid, one-character alleles, GT first) and the general one (other ploidies, allele numbers >= 10,
+    GT not first, short lines), each expected byte for byte: (allele+1)<<1|phased, 0|phase = missing,
+    vector_end (0x81 / 0x8001) padding."""
+    hdr = "##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\tc\td\n"
+    lines = [
+        "1\t10\t.\tA\tC\t.\tPASS\t.\tGT\t0/0\t0|1\t./.\t1/.",                 # direct
+        "1\t20\t.\tA\tC,G,T\t.\tPASS\t.\tGT:DP\t3/0:7\t.|2:1\t9|9:0\t0/1:.",  # direct, sub-fields after GT
+        "1\t30\t.\tA\tC\t.\tPASS\t.\tGT\t0/1\t1\t0/1/1\t.",                   # general: haploid and triploid calls
+        "1\t40\t.\tA\tC\t.\tPASS\t.\tDP:GT\t5:0/1\t6:1|1\t7:./.\t8:0|0",      # general: GT second
+        "1\t50\t.\tA\tC\t.\tPASS\t.\tGT\t0/1\t1/1",                           # general: two sample columns missing
+        "1\t60\t.\tA\t" + ",".join("C" * (i + 2) for i in range(70)) + "\t.\tPASS\t.\tGT\t0/70\t12|3\t./10\t0/0",   # general: int16
+        "1\t70\t.\tA\tC\t.\tPASS\t.\tDP\t1\t2\t3\t4",                         # no GT at all
+    ]
+    p = tmp_path / "t.vcf"
+    p.write_text(hdr + "\n".join(lines) + "\n")
+    L = api.load_host_library()
+    out = np.zeros((8, 64), np.uint8)
+    nrec, ns, w, pl = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    # nph_read_gt reports the layout of the last GT-bearing record; rows are checked per record below
+    assert L.nph_read_gt(os.fsencode(str(p)), out.ctypes.data, 64, 8, C.byref(nrec), C.byref(ns), C.byref(w), C.byref(pl)) == 0
+    assert (nrec.value, ns.value) == (7, 4)
+    i8 = lambda row, k: list(out[row, :k].view(np.int8))
+    assert i8(0, 8) == [2, 2, 2, 5, 0, 0, 4, 0]
+    assert i8(1, 8) == [8, 2, 0, 7, 20, 21, 2, 4]
+    VE = -127
+    assert i8(2, 12) == [2, 4, VE, 4, VE, VE, 2, 4, 4, 0, VE, VE]
+    assert i8(3, 8) == [2, 4, 4, 5, 0, 0, 2, 3]
+    assert i8(4, 8) == [2, 4, 4, 4, 0, VE, 0, VE]
+    assert list(out[5, :16].view(np.int16)) == [2, 142, 26, 9, 0, 22, 2, 2]
+    assert not out[6].any()
