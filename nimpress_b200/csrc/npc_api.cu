@@ -58,6 +58,7 @@ struct npc_ctx {
     ull *d_fcounts = nullptr;               // [max_rows] arrivals | nmiss | neff words of the fused kernel
     uint8_t *d_multi_scratch = nullptr;     // arena of npc_score_resident_multi's contraction
     size_t multi_scratch_bytes = 0;
+    bool multi_attr_set = false;
     int64_t multi_contractions = 0;         // npc_score_resident_multi calls served by the tensor-core contraction
 };
 
@@ -715,10 +716,9 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     NPC_CUDA(c, cudaMemcpyAsync(d_fexp, fexp.data(), S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
 
     // ---- contraction -------------------------------------------------------------------------------
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->multi_attr_set) {                                           // per device, hence per context
         NPC_CUDA(c, cudaFuncSetAttribute(k_multi_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, npc::MC_SMEM));
-        attr_set = true;
+        c->multi_attr_set = true;
     }
     const int64_t n_tiles = (c->n + npc::MC_N - 1) / npc::MC_N;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, c->num_sms > 0 ? c->num_sms : 148);
