@@ -179,7 +179,9 @@ int npc_score_resident(npc_ctx *ctx, const npc_row *rows, int64_t n_rows);
  * npc_finish(offsets[k], scores_out[k], &nloci_out[k], loci_out[k], n_rows[k]) gives:
  * scores_out[k][n_samples] normalised, loci_out[k][n_rows[k]] in row order (loci_out or
  * loci_out[k] may be NULL).  Synchronous; the context's own running sums and locus log are
- * overwritten.
+ * overwritten.  offsets == NULL: scores_out[k] receives the raw partial sums instead (what
+ * npc_partial gives) -- for variant-sharded cohorts, where the caller adds the shards' partials
+ * per definition in shard order and applies npc_normalise once.
  *   With three or more definitions on an int8 diploid slab (and exact order off) the sums are
  * formed as one dense contraction on the tensor cores (npc_multi.cuh): the genotypes are read
  * once for the tallies and once per 16 definitions instead of once per definition.  Per-locus

@@ -586,8 +586,10 @@ static int multi_one_by_one(npc_ctx *ctx, int32_t n_scores, const npc_row *const
         if (rc) return rc;
         if ((rc = npc_score_resident(ctx, rows[k], n_rows[k]))) return rc;
         int64_t nlog = 0;
-        if ((rc = npc_finish(ctx, offsets[k], scores_out[k], nloci_out ? &nloci_out[k] : nullptr,
-                             loci_out ? loci_out[k] : nullptr, loci_out && loci_out[k] ? n_rows[k] : 0, &nlog))) return rc;
+        npc_locus *lg = loci_out ? loci_out[k] : nullptr;
+        rc = offsets ? npc_finish(ctx, offsets[k], scores_out[k], nloci_out ? &nloci_out[k] : nullptr, lg, lg ? n_rows[k] : 0, &nlog)
+                     : npc_partial(ctx, scores_out[k], nloci_out ? &nloci_out[k] : nullptr, lg, lg ? n_rows[k] : 0, &nlog);
+        if (rc) return rc;
     }
     return NPC_OK;
 }
@@ -741,7 +743,9 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
         P.entry_row = d_entry_row; P.entry_pat = d_entry_pat; P.A = d_A; P.n_kb = n_kb; P.n_scores = ng; P.rps = rps;
         for (int k = 0; k < ng; k++) {
             P.sc_lo[k] = ldexp(1.0, -fexp[k0 + k]); P.sc_hi[k] = ldexp(1.0, 32 - fexp[k0 + k]);
-            P.consts[k] = scale[k0 + k].consts; P.denom[k] = (double)(int64_t)nloci[k0 + k] * 2.0; P.offset[k] = offsets[k0 + k];
+            P.consts[k] = scale[k0 + k].consts;
+            P.denom[k] = offsets ? (double)(int64_t)nloci[k0 + k] * 2.0 : 1.0;       // no offsets: raw partial sums (x / 1 + 0 = x)
+            P.offset[k] = offsets ? offsets[k0 + k] : 0.0;
             P.out[k] = d_out + (size_t)k * c->n;
         }
         mark("digit tiles");
@@ -762,7 +766,7 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
 extern "C" int npc_score_resident_multi(npc_ctx *ctx, int32_t n_scores, const npc_row *const *rows, const int64_t *n_rows,
                                         const double *offsets, double *const *scores_out, int64_t *nloci_out,
                                         npc_locus *const *loci_out) {
-    if (!ctx || n_scores < 0 || (n_scores && (!rows || !n_rows || !offsets || !scores_out))) return NPC_EINVAL;
+    if (!ctx || n_scores < 0 || (n_scores && (!rows || !n_rows || !scores_out))) return NPC_EINVAL;
     for (int32_t k = 0; k < n_scores; k++) if (n_rows[k] < 0 || (n_rows[k] && !rows[k]) || !scores_out[k]) return NPC_EINVAL;
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));
     // the contraction pays one tally pass + one pass per 16 definitions; below three definitions the fused kernel is as cheap

@@ -182,13 +182,13 @@ class Engine:
         rows_list = [np.ascontiguousarray(r, dtype=ROW_DTYPE) for r in rows_list]
         rp = (C.c_void_p * S)(*[r.ctypes.data for r in rows_list])
         nr = np.array([len(r) for r in rows_list], dtype=np.int64)
-        off = np.array(offsets, dtype=np.float64)
+        off = np.array(offsets, dtype=np.float64) if offsets is not None else None      # None: raw partial sums
         scores = scores if scores is not None else [np.zeros(self.n, dtype=np.float64) for _ in range(S)]
         loci = loci if loci is not None else [np.zeros(len(r), dtype=LOCUS_DTYPE) for r in rows_list]
         sp = (C.c_void_p * S)(*[a.ctypes.data for a in scores])
         lp = (C.c_void_p * S)(*[a.ctypes.data for a in loci])
         nloci = np.zeros(S, dtype=np.int64)
-        self._ck(self.L.npc_score_resident_multi(self.h, S, rp, nr.ctypes.data, off.ctypes.data, sp, nloci.ctypes.data, lp))
+        self._ck(self.L.npc_score_resident_multi(self.h, S, rp, nr.ctypes.data, off.ctypes.data if off is not None else None, sp, nloci.ctypes.data, lp))
         return [(scores[k], int(nloci[k]), loci[k]) for k in range(S)]
 
     @property

@@ -300,3 +300,43 @@ def test_contraction_edge_shapes(nb, n, V, S):
     got2 = eng.score_resident_multi(lists2, [0.0, 0.0, 1.0])
     check_lists(got2, gt, n, lists2, [0.0, 0.0, 1.0], False, 1e-12)
     eng.close()
+
+
+@pytest.mark.parametrize("mode", ["contract", "one-by-one"])
+def test_multi_variant_shards_combine(nb, mode, monkeypatch):
+    """Variant-sharded multi-score: two contexts each score their half of every definition's
+    rows as raw partial sums (offsets = None); shard.combine_partials adds them in shard order per
+    definition, npc_normalise once == the oracle on the whole definitions."""
+    import torch
+    from nimpress_b200 import shard
+    if mode == "one-by-one":
+        monkeypatch.setenv("NPC_MULTI", "0")
+    rng = np.random.default_rng(55)
+    n, V, S = 9001, 120, 5
+    gt = random_cohort(rng, n, V, miss_rate=0.03, n_alt=2)
+    lists = [random_rows(rng, V, n_rows=int(rng.integers(20, 200)), n_alt=2) for _ in range(S)]
+    offs = [0.1 * k for k in range(S)]
+    parts = []
+    for r in range(2):
+        eng = nb.Engine(n, max_rows_per_block=128, n_slots=2)
+        fill_slab(eng, gt)
+        sub = [rows[slice(*shard.shard_range(len(rows), 2, r))] for rows in lists]
+        got = eng.score_resident_multi(sub, None)
+        assert eng.multi_contractions == (1 if mode == "contract" else 0)
+        parts.append((np.stack([g[0] for g in got]), np.array([g[1] for g in got]), [g[2] for g in got]))
+        eng.close()
+    total = parts[0][0] + parts[1][0]                       # shard.combine_partials at world size 1 per "rank", added in rank order
+    nloci = parts[0][1] + parts[1][1]
+    t, nl = shard.combine_partials(torch.from_numpy(total), torch.from_numpy(nloci))
+    assert np.array_equal(t.numpy(), total, equal_nan=True) and np.array_equal(nl.numpy(), nloci)
+    L = nb.load_library()
+    for k in range(S):
+        want = orc.score_matrix(gt, n, 2, lists[k], offset=offs[k])
+        sc = total[k].copy()
+        L.npc_normalise(sc.ctypes.data, n, int(nloci[k]), offs[k])
+        assert nloci[k] == want["nloci"]
+        assert_loci_equal(np.concatenate([parts[0][2][k], parts[1][2][k]]), want["loci"])
+        a, b = sc, want["scores"]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        ok = np.isfinite(b)
+        assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(np.abs(b[ok]), 1e-3))
