@@ -644,6 +644,22 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     for (int64_t e = 0; e < E; e++) { entry_row[e] = erows[e].gt_row; entry_pat[e] = 0x01010101u * (uint32_t)((erows[e].eaidx + 1) << 1); }
 
     mark("entries (host)");
+    const int64_t n_tiles = (c->n + npc::MC_N - 1) / npc::MC_N;
+    const int64_t sms = c->num_sms > 0 ? c->num_sms : 148;
+    // split the k-blocks of a tile over `parts` work units when that evens out the last round
+    // (782 tiles on 148 SMs: 6 rounds for 5.3 rounds of work; in thirds 16 rounds of 1/3 = 5.33)
+    int parts = 1;
+    {
+        double best = (double)((n_tiles + sms - 1) / sms);
+        const char *e = getenv("NPC_MULTI_PARTS");
+        for (int p = 2; p <= 4 && n_kb / p >= 16; p++) {
+            const double cost = (double)((n_tiles * p + sms - 1) / sms) / p * 1.01;      // a little for the extra epilogues
+            if (cost < best) { best = cost; parts = p; }
+        }
+        if (e && *e) parts = std::max(1, std::min(atoi(e), std::max(1, n_kb)));
+    }
+    const int kb_per_part = (n_kb + parts - 1) / parts;
+    parts = (n_kb + kb_per_part - 1) / kb_per_part;                     // no empty part
     // scratch: one arena kept by the context, grown when a call needs more
     const int Sg = std::min<int>(S, npc::MC_SCORES);
     size_t need = 0;
@@ -653,7 +669,8 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
                  o_counts = reserve(2 * R * sizeof(ull)), o_rowp = reserve(R * sizeof(RowP)), o_log = reserve(R * sizeof(npc_locus)),
                  o_nloci = reserve(S * sizeof(ull)), o_row0 = reserve((S + 1) * 8), o_scale = reserve(S * sizeof(MultiScale)),
                  o_fexp = reserve(S * 4), o_coef = reserve((size_t)Sg * 2 * Ep * 8), o_pois = reserve((size_t)Sg * Ep),
-                 o_A = reserve((size_t)n_kb * npc::MC_A_STAGE), o_out = reserve((size_t)Sg * c->n * 8);
+                 o_A = reserve((size_t)n_kb * npc::MC_A_STAGE), o_out = reserve((size_t)Sg * c->n * 8),
+                 o_part = reserve(parts > 1 ? (size_t)parts * Sg * c->n * 8 : 16);
     if (need > c->multi_scratch_bytes) {
         NPC_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_multi_scratch); c->d_multi_scratch = nullptr; c->multi_scratch_bytes = 0;
@@ -668,7 +685,7 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     uint32_t *d_entry_pat = (uint32_t *)(base + o_entry_pat);
     RowP *d_rowp = (RowP *)(base + o_rowp); npc_locus *d_log = (npc_locus *)(base + o_log); int64_t *d_row0 = (int64_t *)(base + o_row0);
     MultiScale *d_scale = (MultiScale *)(base + o_scale); long long *d_coef = (long long *)(base + o_coef);
-    uint8_t *d_pois = base + o_pois, *d_A = base + o_A; double *d_out = (double *)(base + o_out);
+    uint8_t *d_pois = base + o_pois, *d_A = base + o_A; double *d_out = (double *)(base + o_out), *d_part = (double *)(base + o_part);
     cudaStream_t st = c->stream;
     mark("scratch arena");
     NPC_CUDA(c, cudaMemcpyAsync(d_erows, erows.data(), E * sizeof(npc_row), cudaMemcpyHostToDevice, st));
@@ -722,8 +739,7 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
         NPC_CUDA(c, cudaFuncSetAttribute(k_multi_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, npc::MC_SMEM));
         c->multi_attr_set = true;
     }
-    const int64_t n_tiles = (c->n + npc::MC_N - 1) / npc::MC_N;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, c->num_sms > 0 ? c->num_sms : 148);
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles * parts, sms);
     const int per_launch = npc::MC_M / rps;                             // 18 definitions of 7 rows, or 16 of 8
     for (int k0 = 0; k0 < S; k0 += per_launch) {
         const int ng = std::min(per_launch, S - k0);
@@ -741,6 +757,7 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
         memset(&P, 0, sizeof(P));
         P.gt = c->d_slab; P.row_stride = c->slab_stride; P.n = c->n;
         P.entry_row = d_entry_row; P.entry_pat = d_entry_pat; P.A = d_A; P.n_kb = n_kb; P.n_scores = ng; P.rps = rps;
+        P.parts = parts; P.kb_per_part = kb_per_part; P.partial = d_part;
         for (int k = 0; k < ng; k++) {
             P.sc_lo[k] = ldexp(1.0, -fexp[k0 + k]); P.sc_hi[k] = ldexp(1.0, 32 - fexp[k0 + k]);
             P.consts[k] = scale[k0 + k].consts;
@@ -752,6 +769,11 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
         k_multi_contract<<<grid, npc::MC_THREADS, npc::MC_SMEM, st>>>(P);
         c->launches++;
         NPC_CUDA(c, cudaGetLastError());
+        if (parts > 1) {
+            k_multi_finish<<<dim3((unsigned)((c->n + 255) / 256), (unsigned)ng), 256, 0, st>>>(P);
+            c->launches++;
+            NPC_CUDA(c, cudaGetLastError());
+        }
         mark("contraction kernel");
         for (int k = 0; k < ng; k++)
             NPC_CUDA(c, cudaMemcpyAsync(scores_out[k0 + k], d_out + (size_t)k * c->n, c->n * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -73,7 +73,13 @@ struct MultiParams {
     const uint32_t *entry_pat;               // [n_kb*64] (eaidx+1)<<1 in all four bytes
     const uint8_t *A;                        // [n_kb][16 KB] digit tiles, already in the swizzled smem layout
     int32_t n_kb, n_scores;
-    int32_t rps, pad;                        // rows per score: 7 digits, or 8 = 7 digits + NaN counter
+    int32_t rps, parts;                      // rows per score: 7 digits, or 8 = 7 digits + NaN counter; parts: see below
+    int32_t kb_per_part, pad;
+    // parts > 1: the k-blocks of a tile are split over `parts` work units so that the number of units
+    // is close to a multiple of the grid (782 tiles on 148 SMs is 6 rounds for 5.3 rounds of work); a
+    // unit then stores its raw partial sum to partial[part][score][sample] and k_multi_finish adds the
+    // parts in order, adds the constants and normalises
+    double *partial;
     double sc_lo[MC_SCORES], sc_hi[MC_SCORES];   // 2^-F and 2^(32-F) of each score's fixed-point scale
     double consts[MC_SCORES];                // sum of the constant (whole-locus) contributions, NaN if any is NaN
     double denom[MC_SCORES];                 // 2 * nloci
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
     const uint32_t raw_full = bars, raw_empty = raw_full + 8 * MC_RS, b_full = raw_empty + 8 * MC_RS, b_empty = b_full + 8 * MC_BS;
     const uint32_t a_full = b_empty + 8 * MC_BS, a_empty = a_full + 8 * MC_AS, t_full = a_empty + 8 * MC_AS, t_empty = t_full + 8 * MC_TS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_tiles = (P.n + MC_N - 1) / MC_N;
+    const int64_t n_units = ((P.n + MC_N - 1) / MC_N) * P.parts;     // unit = (sample tile, part of the k-blocks)
 
     if (tid == 0) {
         for (int i = 0; i < MC_RS; i++) { mbar_init(raw_full + 8 * i, MC_PW); mbar_init(raw_empty + 8 * i, MC_CW); }
@@ -197,11 +203,13 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
         constexpr int PER = MC_ENT / MC_PW;
         const int pw = warp - 4, el = pw * PER + (lane % PER);
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int64_t tile = unit / P.parts;
+            const int kb_lo = (int)(unit % P.parts) * P.kb_per_part, kb_hi = min(P.n_kb, kb_lo + P.kb_per_part);
             const int64_t byte0 = tile * (MC_N * 2);
             const uint32_t seg = (uint32_t)min((int64_t)(MC_N * 2), P.row_stride - byte0);      // multiple of 16: row_stride is
-            int32_t r0 = P.entry_row[el];
-            for (int kb = 0; kb < P.n_kb; kb++, it++) {
+            int32_t r0 = P.entry_row[kb_lo * MC_ENT + el];
+            for (int kb = kb_lo; kb < kb_hi; kb++, it++) {
                 const uint32_t rs = it % MC_RS;
                 const uint32_t stage = sRaw + rs * MC_RAW_STAGE;
                 mbar_wait(raw_empty + 8 * rs, ((it / MC_RS) & 1) ^ 1);
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                 __syncwarp();
                 if (lane < PER) tma_load_1d(stage + el * MC_PITCH, P.gt + (int64_t)r0 * P.row_stride + byte0, seg, raw_full + 8 * rs, pol_stream);
                 if (pw == 0 && lane == 0) tma_load_1d(stage + MC_ENT * MC_PITCH, P.entry_pat + (int64_t)kb * MC_ENT, MC_ENT * 4, raw_full + 8 * rs, pol_keep);
-                if (kb + 1 < P.n_kb) r0 = P.entry_row[(kb + 1) * MC_ENT + el];
+                if (kb + 1 < kb_hi) r0 = P.entry_row[(kb + 1) * MC_ENT + el];
                 __syncwarp();
             }
         }
@@ -218,24 +226,27 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
         if (lane == 0) {
             const uint64_t pol_keep = l2_evict_last_policy();
             uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int kb = 0; kb < P.n_kb; kb++, it++) {
+            for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const int kb_lo = (int)(unit % P.parts) * P.kb_per_part, kb_hi = min(P.n_kb, kb_lo + P.kb_per_part);
+                for (int kb = kb_lo; kb < kb_hi; kb++, it++) {
                     const uint32_t as = it % MC_AS;
                     mbar_wait(a_empty + 8 * as, ((it / MC_AS) & 1) ^ 1);
                     mbar_arrive_expect_tx(a_full + 8 * as, MC_A_STAGE);
                     tma_load_1d(sA + as * MC_A_STAGE, P.A + (int64_t)kb * MC_A_STAGE, MC_A_STAGE, a_full + 8 * as, pol_keep);
                 }
+            }
         }
     } else if (warp == MC_W_MMA) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             uint32_t it = 0, tcount = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
+            for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, tcount++) {
+                const int kb_lo = (int)(unit % P.parts) * P.kb_per_part, kb_hi = min(P.n_kb, kb_lo + P.kb_per_part);
                 const uint32_t ts = tcount % MC_TS;
                 mbar_wait(t_empty + 8 * ts, ((tcount / MC_TS) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t acc = tmem + ts * MC_N;
-                for (int kb = 0; kb < P.n_kb; kb++, it++) {
+                for (int kb = kb_lo; kb < kb_hi; kb++, it++) {
                     const uint32_t bs = it % MC_BS, as = it % MC_AS;
                     mbar_wait(a_full + 8 * as, (it / MC_AS) & 1);
                     mbar_wait(b_full + 8 * bs, (it / MC_BS) & 1);
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                     const uint64_t da = umma_desc_sw128(sA + as * MC_A_STAGE), db = umma_desc_sw128(sB + bs * MC_B_STAGE);
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++)                       // K = 32 bytes per instruction: +2 in the 16-byte address field
-                        umma_i8(acc, da + 2 * ks, db + 2 * ks, (kb | ks) != 0);
+                        umma_i8(acc, da + 2 * ks, db + 2 * ks, ((kb - kb_lo) | ks) != 0);
                     umma_commit(b_empty + 8 * bs);
                     umma_commit(a_empty + 8 * as);
                 }
@@ -254,8 +265,9 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
         // ===== converters =====
         const int cw = warp - MC_FIRST_CW, g = lane & 7, qsub = lane >> 3;
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < P.n_kb; kb++, it++) {
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int kb_lo = (int)(unit % P.parts) * P.kb_per_part, kb_hi = min(P.n_kb, kb_lo + P.kb_per_part);
+            for (int kb = kb_lo; kb < kb_hi; kb++, it++) {
                 const uint32_t rs = it % MC_RS, bs = it % MC_BS;
                 const uint32_t stage = sRaw + rs * MC_RAW_STAGE, bt = sB + bs * MC_B_STAGE;
                 mbar_wait(raw_full + 8 * rs, (it / MC_RS) & 1);
@@ -291,7 +303,9 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
         // ===== epilogue: warp w reads TMEM lanes 32w..32w+31 (rows of the digit tile) =====
         uint32_t tcount = 0;
         const int col = tid & 15, grp = tid >> 4;                            // column of the step, score group 0..7
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, tcount++) {
+            const int64_t tile = unit / P.parts;
+            const int part = (int)(unit % P.parts);
             const uint32_t ts = tcount % MC_TS;
             mbar_wait(t_full + 8 * ts, (tcount / MC_TS) & 1);
             tc_fence_after();
@@ -312,9 +326,11 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                         const long long lo = (long long)x[0] + ((long long)x[1] << 8) + ((long long)x[2] << 16) + ((long long)x[3] << 24);
                         const long long hi = (long long)x[4] + ((long long)x[5] << 8) + ((long long)x[6] << 16);
                         double sum = __dadd_rn(__dmul_rn((double)hi, P.sc_hi[k]), __dmul_rn((double)lo, P.sc_lo[k]));
-                        sum = __dadd_rn(sum, P.consts[k]);
                         if (x[7] != 0) sum = __longlong_as_double(0x7FF8000000000000ll);
-                        if (s < P.n) P.out[k][s] = __dadd_rn(__ddiv_rn(sum, P.denom[k]), P.offset[k]);   // :643-649
+                        if (s < P.n) {
+                            if (P.parts == 1) P.out[k][s] = __dadd_rn(__ddiv_rn(__dadd_rn(sum, P.consts[k]), P.denom[k]), P.offset[k]);   // :643-649
+                            else P.partial[((int64_t)part * P.n_scores + k) * P.n + s] = sum;
+                        }
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -327,6 +343,16 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
     tc_fence_before();
     __syncthreads();
     if (warp == MC_W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// parts > 1: out[k][s] = normalise(partial[0][k][s] + partial[1][k][s] + ... + consts[k])
+__global__ void k_multi_finish(const __grid_constant__ MultiParams P) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (s >= P.n) return;
+    double sum = P.partial[(int64_t)k * P.n + s];
+    for (int p = 1; p < P.parts; p++) sum = __dadd_rn(sum, P.partial[((int64_t)p * P.n_scores + k) * P.n + s]);
+    P.out[k][s] = __dadd_rn(__ddiv_rn(__dadd_rn(sum, P.consts[k]), P.denom[k]), P.offset[k]);
 }
 
 // ---- coefficient preparation -------------------------------------------------------------------

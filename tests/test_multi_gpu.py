@@ -340,3 +340,24 @@ def test_multi_variant_shards_combine(nb, mode, monkeypatch):
         assert np.array_equal(np.isnan(a), np.isnan(b))
         ok = np.isfinite(b)
         assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(np.abs(b[ok]), 1e-3))
+
+
+@pytest.mark.parametrize("parts", ["2", "3", "7"])
+def test_contraction_k_split(nb, parts, monkeypatch):
+    """The k-blocks of a tile split over several work units (NPC_MULTI_PARTS forces what the library
+    otherwise chooses from the tile count): partial sums added in part order by k_multi_finish, NaN
+    counter rows included (imp_sample=fail)."""
+    monkeypatch.setenv("NPC_MULTI_PARTS", parts)
+    rng = np.random.default_rng(77)
+    n, V, S = 2100, 300, 5
+    gt = random_cohort(rng, n, V, miss_rate=0.03, n_alt=2)
+    lists = [random_rows(rng, V, n_rows=int(rng.integers(200, 600)), n_alt=2) for _ in range(S)]
+    offs = [0.25 * k for k in range(S)]
+    for pol in (dict(), dict(imp_sample="fail", maxmis=0.1)):
+        eng = nb.Engine(n, max_rows_per_block=512, n_slots=2)
+        eng.set_policy(**pol)
+        fill_slab(eng, gt, 512)
+        got = eng.score_resident_multi(lists, offs)
+        assert eng.multi_contractions == 1
+        check_lists(got, gt, n, lists, offs, False, 1e-12, **pol)
+        eng.close()
