@@ -31,8 +31,9 @@
 //                patterns into a 3-stage raw ring
 //   warp 9       loads the 16 KB digit tile A of the k-block (prebuilt in global memory as the smem
 //                image, L2-resident) into its own 3-stage ring
-//   warps 10..17 converters: raw GT bytes -> d / m planes with byte-wise SWAR compares, written as
-//                operand B, K-major, 128-byte swizzle (the canonical UMMA layout), 2-stage ring
+//   warps 10..25 converters: raw GT bytes -> d / m planes with byte-wise SWAR compares, written as
+//                operand B, MN-major (the samples of a plane row contiguous: no transpose), 128-byte
+//                swizzle, 2-stage ring
 //   warp 8       one thread issues 4 x tcgen05.mma (M=128, N=256, K=32) per k-block; tcgen05.commit
 //                releases the A / B stages and, after the last k-block, hands the accumulator over
 //   warps 0..3   epilogue: tcgen05.ld -> smem (all 128 rows) -> int64 recombination -> normalise
@@ -98,8 +99,14 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// D = S32, A = B = signed 8-bit, both K-major, N = 256, M = 128
-constexpr uint32_t MC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MC_N >> 3) << 17) | ((uint32_t)(MC_M >> 4) << 24);
+// MN-major operand (the N = 256 samples of a K row contiguous), 128-byte swizzle: two column blocks of 128 samples,
+// 16 KB apart (leading byte offset); in a block K row r at r*128 with its 16-byte chunk c at ((c ^ (r&7)) << 4);
+// 8 K rows = one 1024-byte atom (stride byte offset).  Layout verified by tools/probe/umma_i8_probe.cu.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(16384 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// D = S32, A = B = signed 8-bit, A K-major, B MN-major (bit 16), N = 256, M = 128
+constexpr uint32_t MC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(MC_N >> 3) << 17) | ((uint32_t)(MC_M >> 4) << 24);
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
@@ -127,9 +134,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -159,15 +163,6 @@ __device__ __forceinline__ void convert4(uint32_t w0, uint32_t w1, uint32_t pat,
             m4 |= (uint32_t)(miss ? 1 : 0) << (8 * i);
         }
     }
-}
-
-// 4x4 byte transpose: in r[j] byte i -> out o[i] byte j
-__device__ __forceinline__ void transpose4(const uint32_t r0, const uint32_t r1, const uint32_t r2, const uint32_t r3,
-                                           uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
-    const uint32_t t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140);
-    const uint32_t t2 = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
-    o0 = __byte_perm(t0, t1, 0x5410); o1 = __byte_perm(t0, t1, 0x7632);
-    o2 = __byte_perm(t2, t3, 0x5410); o3 = __byte_perm(t2, t3, 0x7632);
 }
 
 __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_constant__ MultiParams P) {
@@ -251,10 +246,10 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                     mbar_wait(a_full + 8 * as, (it / MC_AS) & 1);
                     mbar_wait(b_full + 8 * bs, (it / MC_BS) & 1);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sA + as * MC_A_STAGE), db = umma_desc_sw128(sB + bs * MC_B_STAGE);
+                    const uint64_t da = umma_desc_sw128(sA + as * MC_A_STAGE), db = umma_desc_sw128_mn(sB + bs * MC_B_STAGE);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++)                       // K = 32 bytes per instruction: +2 in the 16-byte address field
-                        umma_i8(acc, da + 2 * ks, db + 2 * ks, ((kb - kb_lo) | ks) != 0);
+                    for (int ks = 0; ks < 4; ks++)                       // K = 32 per instruction: A +32 bytes in its rows, B 32 K rows (4 KB) further
+                        umma_i8(acc, da + 2 * ks, db + 256 * ks, ((kb - kb_lo) | ks) != 0);
                     umma_commit(b_empty + 8 * bs);
                     umma_commit(a_empty + 8 * as);
                 }
@@ -283,15 +278,15 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                         const uint2 w = lds_v2(stage + (g + 8 * j) * MC_PITCH + q * 8);
                         convert4(w.x, w.y, pat[j], (int)((pat[j] & 0xFFu) >> 1) - 1, D[j], M[j]);
                     }
-                    uint32_t o[4][4];                                    // [sample][word]: d of entries j=0..3, j=4..7, m of j=0..3, j=4..7
-                    transpose4(D[0], D[1], D[2], D[3], o[0][0], o[1][0], o[2][0], o[3][0]);
-                    transpose4(D[4], D[5], D[6], D[7], o[0][1], o[1][1], o[2][1], o[3][1]);
-                    transpose4(M[0], M[1], M[2], M[3], o[0][2], o[1][2], o[2][2], o[3][2]);
-                    transpose4(M[4], M[5], M[6], M[7], o[0][3], o[1][3], o[2][3], o[3][3]);
+                    // operand B, MN-major: K row 16j + 8*plane + g (entry g + 8j; plane 0 = dosage, 1 = missing) holds the
+                    // tile's 256 samples contiguously, so a thread's four samples of a plane are one word: no transpose.
+                    // Lanes g = 0..7 write eight consecutive K rows -> eight different swizzled chunks: conflict-free.
+                    const uint32_t col = bt + (uint32_t)(q >> 5) * 16384u + ((uint32_t)q & 3u) * 4u;
+                    const uint32_t chunk = ((uint32_t)(q & 31) >> 2) ^ (uint32_t)g;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint32_t s = (uint32_t)(4 * q + i);        // row of B = sample of the tile; chunk g of its 128 K-bytes
-                        sts_v4(bt + s * 128 + ((uint32_t)(g ^ (s & 7)) << 4), o[i][0], o[i][1], o[i][2], o[i][3]);
+                    for (int j = 0; j < 8; j++) {
+                        sts_u32(col + (uint32_t)(16 * j + g) * 128u + (chunk << 4), D[j]);
+                        sts_u32(col + (uint32_t)(16 * j + 8 + g) * 128u + (chunk << 4), M[j]);
                     }
                 }
                 fence_async_smem();                                      // these generic-proxy writes are read by the tensor core
@@ -420,11 +415,11 @@ __global__ void k_multi_coef(const RowP *__restrict__ rowp, const int32_t *__res
     else pois[(int64_t)k * E + e] = 1;
 }
 
-// digit tiles: image kb, row R = score*rps + digit (digit 7 = NaN counter), K byte kbyte = 16*g + 8*plane + j  <->  entry kb*64 + g + 8j
+// digit tiles: image kb, row R = score*rps + digit (digit 7 = NaN counter), K byte kbyte = 16*j + 8*plane + g  <->  entry kb*64 + g + 8j
 __global__ void __launch_bounds__(128) k_multi_digits(const long long *__restrict__ coef, const uint8_t *__restrict__ pois, int64_t E, int n_scores,
                                                      int rps, uint8_t *__restrict__ A) {
     const int kb = blockIdx.x, R = blockIdx.y, kbyte = threadIdx.x;
-    const int k = R / rps, dg = R % rps, g = kbyte >> 4, plane = (kbyte >> 3) & 1, j = kbyte & 7;
+    const int k = R / rps, dg = R % rps, j = kbyte >> 4, plane = (kbyte >> 3) & 1, g = kbyte & 7;
     const int64_t e = (int64_t)kb * MC_ENT + g + 8 * j;
     int8_t val = 0;
     if (k < n_scores && e < E) {
@@ -436,7 +431,7 @@ __global__ void __launch_bounds__(128) k_multi_digits(const long long *__restric
             val = (int8_t)d;
         }
     }
-    A[(int64_t)kb * MC_A_STAGE + R * 128 + ((g ^ (R & 7)) << 4) + (kbyte & 15)] = (uint8_t)val;
+    A[(int64_t)kb * MC_A_STAGE + R * 128 + (((kbyte >> 4) ^ (R & 7)) << 4) + (kbyte & 15)] = (uint8_t)val;
 }
 
 }  // namespace npc

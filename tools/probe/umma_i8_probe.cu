@@ -1,6 +1,7 @@
 // Probe (development aid, not product): one CTA, D[128 x 256] (int32, TMEM) = A[128 x 128] (int8) * B[256 x 128]^T
 // (int8), both K-major in the 128-byte-swizzle canonical layout, four tcgen05.mma.kind::i8 (K = 32 each).
-// Checks the smem descriptor, the instruction descriptor and the tcgen05.ld lane/column mapping.
+// Checks the smem descriptors (B both K-major and MN-major = samples contiguous per K row), the instruction
+// descriptor and the tcgen05.ld lane/column mapping.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -o umma_i8_probe umma_i8_probe.cu && ./umma_i8_probe
 #include <cstdint>
 #include <cstdio>
@@ -20,7 +21,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     return d;
 }
 
-__global__ void __launch_bounds__(128, 1) k_probe(const int8_t *A, const int8_t *B, int32_t *D) {
+__global__ void __launch_bounds__(128, 1) k_probe(const int8_t *A, const int8_t *B, int32_t *D, int mode, uint32_t lbo, uint32_t sbo) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                 // 128 rows x 128 B
     uint8_t *sB = smem + 16384;         // 256 rows x 128 B
@@ -29,7 +30,11 @@ __global__ void __launch_bounds__(128, 1) k_probe(const int8_t *A, const int8_t 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // fill: row r, byte k -> r*128 + ((k>>4) ^ (r&7))*16 + (k&15)
     for (int i = tid; i < 128 * 128; i += 128) { int r = i >> 7, k = i & 127; sA[r * 128 + (((k >> 4) ^ (r & 7)) << 4) + (k & 15)] = (uint8_t)A[i]; }
-    for (int i = tid; i < 256 * 128; i += 128) { int r = i >> 7, k = i & 127; sB[r * 128 + (((k >> 4) ^ (r & 7)) << 4) + (k & 15)] = (uint8_t)B[i]; }
+    for (int i = tid; i < 256 * 128; i += 128) {
+        int r = i >> 7, k = i & 127;                  // B[n = r][k]
+        if (mode == 0) sB[r * 128 + (((k >> 4) ^ (r & 7)) << 4) + (k & 15)] = (uint8_t)B[i];
+        else { int nb = r >> 7, nn = r & 127; sB[nb * 16384 + k * 128 + ((((nn >> 4) ^ (k & 7))) << 4) + (nn & 15)] = (uint8_t)B[i]; }   // MN-major: samples contiguous per K row
+    }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -44,9 +49,13 @@ __global__ void __launch_bounds__(128, 1) k_probe(const int8_t *A, const int8_t 
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tb = tmem_base;
     if (tid == 0) {
-        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mode != 0) << 16) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
         for (int ks = 0; ks < 4; ks++) {
             uint64_t da = make_desc_sw128(smem_u32(sA) + ks * 32), db = make_desc_sw128(smem_u32(sB) + ks * 32);
+            if (mode != 0) {
+                const uint32_t sa = smem_u32(sB) + ks * 32 * 128;       // 32 K rows further
+                db = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            }
             uint32_t acc = ks > 0;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
@@ -87,17 +96,24 @@ int main() {
     cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice);
     cudaMemset(dD, 0xFF, 128 * 256 * 4);
     cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 + 1024);
-    k_probe<<<1, 128, 49152>>>(dA, dB, dD);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 2; }
-    std::vector<int32_t> D(128 * 256);
-    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
-    long bad = 0;
-    for (int m = 0; m < 128; m++) for (int n = 0; n < 256; n++) {
-        int32_t ref = 0;
-        for (int k = 0; k < 128; k++) ref += (int32_t)A[m * 128 + k] * (int32_t)B[n * 128 + k];
-        if (ref != D[m * 256 + n]) { if (bad < 8) printf("mismatch m=%d n=%d ref=%d got=%d\n", m, n, ref, D[m * 256 + n]); bad++; }
+    struct { int mode; uint32_t lbo, sbo; const char *what; } cfg[] = {
+        {0, 0, 1024, "B K-major SW128"}, {1, 16384, 1024, "B MN-major SW128, LBO=16384 SBO=1024"} };
+    int rc = 0;
+    for (auto &c : cfg) {
+        cudaMemset(dD, 0xFF, 128 * 256 * 4);
+        k_probe<<<1, 128, 49152>>>(dA, dB, dD, c.mode, c.lbo, c.sbo);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 2; }
+        std::vector<int32_t> D(128 * 256);
+        cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+        long bad = 0;
+        for (int m = 0; m < 128; m++) for (int n = 0; n < 256; n++) {
+            int32_t ref = 0;
+            for (int k = 0; k < 128; k++) ref += (int32_t)A[m * 128 + k] * (int32_t)B[n * 128 + k];
+            if (ref != D[m * 256 + n]) { if (bad < 3) printf("  mismatch m=%d n=%d ref=%d got=%d\n", m, n, ref, D[m * 256 + n]); bad++; }
+        }
+        printf("umma_i8_probe [%s]: %ld mismatches of %d\n", c.what, bad, 128 * 256);
+        if (c.mode == 0) rc |= bad != 0;
     }
-    printf("umma_i8_probe: %ld mismatches of %d\n", bad, 128 * 256);
-    return bad != 0;
+    return rc;
 }
