@@ -141,27 +141,26 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 
 // d and m of four samples of one genotype row.  w0, w1: the eight GT bytes (sample-major allele pairs);
 // pat: (eaidx+1)<<1 in every byte.  Returns dosage bytes (0 where the sample is missing) and missing bytes (0/1).
-// All bytes non-negative (the common case): per byte, bits 1..6 are allele+1 (0 = missing); a byte x is zero iff
-// (x + 0x7F) has bit 7 clear, carry-free since x <= 0x7E.  Otherwise (sentinels, invalid codes): decode_sample.
-__device__ __forceinline__ void convert4(uint32_t w0, uint32_t w1, uint32_t pat, int eaidx, uint32_t &d4, uint32_t &m4) {
-    if (((w0 | w1) & 0x80808080u) == 0u) {
-        const uint32_t a0 = __byte_perm(w0, w1, 0x6420), a1 = __byte_perm(w0, w1, 0x7531);   // first / second allele of the 4 samples
-        const uint32_t ne0 = ((a0 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu, ne1 = ((a1 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu;   // bit 7: allele != effect allele
-        const uint32_t nz0 = (a0 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu, nz1 = (a1 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu;                   // bit 7: allele called
-        const uint32_t called = nz0 & nz1 & 0x80808080u;                                       // bit 7: both alleles called
-        d4 = ((~ne0 & called) >> 7) + ((~ne1 & called) >> 7);
-        m4 = (called >> 7) ^ 0x01010101u;
-    } else {
-        d4 = 0; m4 = 0;
+// convert4_fast -- all bytes non-negative (the common case): per byte, bits 1..6 are allele+1 (0 = missing); a byte x is zero iff
+// (x + 0x7F) has bit 7 clear, carry-free since x <= 0x7E.  convert4_exact -- otherwise (sentinels, invalid codes): decode_sample.
+__device__ __forceinline__ void convert4_fast(uint32_t w0, uint32_t w1, uint32_t pat, uint32_t &d4, uint32_t &m4) {
+    const uint32_t a0 = __byte_perm(w0, w1, 0x6420), a1 = __byte_perm(w0, w1, 0x7531);   // first / second allele of the 4 samples
+    const uint32_t ne0 = ((a0 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu, ne1 = ((a1 ^ pat) & 0x7E7E7E7Eu) + 0x7F7F7F7Fu;   // bit 7: allele != effect allele
+    const uint32_t nz0 = (a0 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu, nz1 = (a1 & 0x7E7E7E7Eu) + 0x7F7F7F7Fu;                   // bit 7: allele called
+    const uint32_t called = nz0 & nz1 & 0x80808080u;                                       // bit 7: both alleles called
+    d4 = ((~ne0 & called) >> 7) + ((~ne1 & called) >> 7);
+    m4 = (called >> 7) ^ 0x01010101u;
+}
+__device__ __forceinline__ void convert4_exact(uint32_t w0, uint32_t w1, int eaidx, uint32_t &d4, uint32_t &m4) {
+    d4 = 0; m4 = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t h = ((i < 2 ? w0 : w1) >> ((i & 1) * 16)) & 0xFFFFu;
-            int8_t a[2] = { (int8_t)(h & 0xFF), (int8_t)(h >> 8) };
-            int d; bool miss;
-            decode_sample<int8_t>(a, 2, eaidx, d, miss);
-            d4 |= (uint32_t)(miss ? 0 : d) << (8 * i);
-            m4 |= (uint32_t)(miss ? 1 : 0) << (8 * i);
-        }
+    for (int i = 0; i < 4; i++) {
+        const uint32_t h = ((i < 2 ? w0 : w1) >> ((i & 1) * 16)) & 0xFFFFu;
+        int8_t a[2] = { (int8_t)(h & 0xFF), (int8_t)(h >> 8) };
+        int d; bool miss;
+        decode_sample<int8_t>(a, 2, eaidx, d, miss);
+        d4 |= (uint32_t)(miss ? 0 : d) << (8 * i);
+        m4 |= (uint32_t)(miss ? 1 : 0) << (8 * i);
     }
 }
 
@@ -273,10 +272,17 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                 {
                     const int q = cw * 4 + qsub;                         // sample quad 0..63 of the tile
                     uint32_t D[8], M[8];
+                    uint2 w[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {                        // entry g + 8j of the k-block
-                        const uint2 w = lds_v2(stage + (g + 8 * j) * MC_PITCH + q * 8);
-                        convert4(w.x, w.y, pat[j], (int)((pat[j] & 0xFFu) >> 1) - 1, D[j], M[j]);
+                    for (int j = 0; j < 8; j++) w[j] = lds_v2(stage + (g + 8 * j) * MC_PITCH + q * 8);   // entry g + 8j of the k-block
+                    const uint32_t any = ((w[0].x | w[0].y) | (w[1].x | w[1].y)) | ((w[2].x | w[2].y) | (w[3].x | w[3].y)) |
+                                         ((w[4].x | w[4].y) | (w[5].x | w[5].y)) | ((w[6].x | w[6].y) | (w[7].x | w[7].y));
+                    if ((any & 0x80808080u) == 0u) {                     // no sentinel, no invalid code in the 32 samples: one test, straight-line
+#pragma unroll
+                        for (int j = 0; j < 8; j++) convert4_fast(w[j].x, w[j].y, pat[j], D[j], M[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) convert4_exact(w[j].x, w[j].y, (int)((pat[j] & 0xFFu) >> 1) - 1, D[j], M[j]);
                     }
                     // operand B, MN-major: K row 16j + 8*plane + g (entry g + 8j; plane 0 = dosage, 1 = missing) holds the
                     // tile's 256 samples contiguously, so a thread's four samples of a plane are one word: no transpose.
