@@ -246,3 +246,54 @@ def test_vcf_text_gt_paths(api, tmp_path):
     assert i8(4, 8) == [2, 4, 4, 4, 0, VE, 0, VE]
     assert list(out[5, :16].view(np.int16)) == [2, 142, 26, 9, 0, 22, 2, 2]
     assert not out[6].any()
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_vcf_text_gt_random_grammar(api, tmp_path, seed):
+    """Random GT strings (ploidy 1-3, '/' and '|', '.', allele numbers up to 150, optional sub-fields after
+    GT, GT sometimes not first) against an encoder written here from the BCF rules: which of the text
+    reader's two parsers a line takes must not be observable."""
+    rng = np.random.default_rng(seed)
+    n = 37
+    hdr = "##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n)) + "\n"
+    lines, want = [], []
+    for rec in range(40):
+        style = rng.integers(4)                     # 0: plain diploid small alleles (direct path), 1: + sub-fields, 2: mixed ploidy / big alleles, 3: GT second
+        max_allele = 150 if (style == 2 and rng.random() < 0.3) else (12 if style == 2 else 9)
+        cols, vals = [], []
+        for s in range(n):
+            pl = 2 if style in (0, 1) else int(rng.integers(1, 4))
+            toks, enc = [], []
+            for k in range(pl):
+                miss = rng.random() < 0.1
+                a = int(rng.integers(0, max_allele + 1))
+                sep = "|" if (k and rng.random() < 0.4) else "/"
+                toks.append((sep if k else "") + ("." if miss else str(a)))
+                enc.append((0 if miss else (a + 1) << 1) | (1 if (k and sep == "|") else 0))
+            gt = "".join(toks)
+            if style == 1:
+                gt += ":" + str(int(rng.integers(0, 99)))
+            if style == 3:
+                gt = str(int(rng.integers(0, 99))) + ":" + gt
+            cols.append(gt); vals.append(enc)
+        fmt = {0: "GT", 1: "GT:DP", 2: "GT", 3: "DP:GT"}[int(style)]
+        lines.append(f"1\t{100 + rec}\t.\tA\t" + ",".join("C" * (i + 2) for i in range(max_allele)) + f"\t.\tPASS\t.\t{fmt}\t" + "\t".join(cols))
+        want.append(vals)
+    p = tmp_path / "r.vcf"
+    p.write_text(hdr + "\n".join(lines) + "\n")
+    L = api.load_host_library()
+    row_bytes = n * 3 * 2
+    # one record at a time would need an API; instead read all rows and decode each with its own layout
+    out = np.zeros((len(lines), row_bytes), np.uint8)
+    nrec, ns, w, pl = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    assert L.nph_read_gt(os.fsencode(str(p)), out.ctypes.data, row_bytes, len(lines), C.byref(nrec), C.byref(ns), C.byref(w), C.byref(pl)) == 0
+    assert (nrec.value, ns.value) == (len(lines), n)
+    for r, vals in enumerate(want):
+        ploidy = max(len(v) for v in vals)
+        width = 1 if max(max(v) for v in vals) <= 127 else 2
+        dt, vend = (np.int8, -127) if width == 1 else (np.int16, -32767)
+        exp = np.full((n, ploidy), vend, dtype=dt)
+        for s, v in enumerate(vals):
+            exp[s, :len(v)] = v
+        got = out[r, :n * ploidy * width].view(dt).reshape(n, ploidy)
+        assert np.array_equal(got, exp), (r, lines[r][:80])
