@@ -142,14 +142,30 @@ def cpu_oracle_rate(n, seconds, threads):
         out = orc.score_matrix(gt, n, 2, rows, threads=threads)
         dt = time.perf_counter() - t0
         assert out["nloci"] == V
-        return dt
+        return dt, out["loci"], rows
 
     v_cal = max(threads * 4, 16)
-    dt = run(v_cal)
+    dt, _, _ = run(v_cal)
     V = int(min(max(v_cal, seconds / max(dt, 1e-6) * v_cal), 40_000, (24 << 30) // stride))
     V = max(V - V % threads, threads)
-    dt = run(V)
+    dt, loci, rows = run(V)
+    cpu_oracle_rate.last = (loci, rows)
     return n * V / dt, V, dt
+
+
+def cpu_af_test_ms_per_locus(n, max_loci=24):
+    """The reference also runs binomTest(neff, 2*(n - nmiss), eaf) per matched locus for its AF-mismatch
+    warning (src/nimpress.nim:573; an O(n) enumeration, :155-188).  Timed here on the tallies of the
+    loci just scored, single thread like the reference, so that the CPU baseline can be quoted with
+    and without it."""
+    import orc
+    loci, rows = cpu_oracle_rate.last
+    L = orc.lib()
+    k = min(max_loci, len(loci))
+    t0 = time.perf_counter()
+    for i in range(k):
+        L.orc_binom_test(int(loci["neff"][i]), int(2 * (n - loci["nmiss"][i])), float(rows["eaf"][i]))
+    return (time.perf_counter() - t0) * 1e3 / max(k, 1)
 
 
 def reference_arm(args):
@@ -361,9 +377,12 @@ def b200_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, Vc, dt = cpu_oracle_rate(n, args.cpu_seconds, 1)
+        af_ms = cpu_af_test_ms_per_locus(n)
         cpu = {"value": r, "unit": "genotypes/s", "cores": 1, "kind": "port",
                "sample": f"{Vc} variants x {n} samples of the same cohort, {dt:.1f} s, single thread like the "
-                         "reference; AF-mismatch binomTest (warning only) not run"}
+                         "reference; scoring only (AF-mismatch binomTest, a warning, not run)",
+               "value_with_af_test": n / (dt / Vc + af_ms * 1e-3), "af_test_ms_per_locus": af_ms,
+               "with_af_test_note": "the reference's default --afmisp also runs one O(n) binomTest per locus; timed on 24 loci of the sample"}
 
     if rank == 0:
         line = {
