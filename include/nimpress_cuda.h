@@ -184,7 +184,8 @@ int npc_score_resident(npc_ctx *ctx, const npc_row *rows, int64_t n_rows);
  * per definition in shard order and applies npc_normalise once.
  *   With three or more definitions on an int8 diploid slab (and exact order off) the sums are
  * formed as one dense contraction on the tensor cores (npc_multi.cuh): the genotypes are read
- * once for the tallies and once per 16 definitions instead of once per definition.  Per-locus
+ * once for the tallies and once per 18 definitions (16 when some imputed contribution is NaN)
+ * instead of once per definition.  Per-locus
  * records and nloci are bit-equal to the one-by-one path; scores agree with it within 1e-9
  * relative (exact integer arithmetic on coefficients rounded to 2^-53 of the definition's
  * largest; measured ~1e-15).  Inputs it does not represent (effect-allele index > 62, a
