@@ -328,7 +328,10 @@ static int launch_count(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const
     if (n_rows == 0 || c->n == 0) return NPC_OK;
     if (c->width == 1 && c->ploidy == 2) {
         const int64_t nchunks = (c->n + 7) / 8;
-        const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>((nchunks + 1023) / 1024, 1), 65535);
+        // blocks are cheap to run but not free to schedule: up to 64 chunks per thread (5.8 TB/s on an 8 GB
+        // slab against 4.6 TB/s at 4 per thread), fewer only to keep ~4096 blocks in the grid
+        const int64_t s_min = (nchunks + 16383) / 16384, s_max = (nchunks + 1023) / 1024, want = (4096 + n_rows - 1) / n_rows;
+        const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>(std::min(std::max(want, s_min), s_max), 1), 65535);
         k_count_i8x2<<<dim3((unsigned)n_rows, slabs), 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, counts);
     } else {
         const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>((c->n + 2047) / 2048, 1), 65535);

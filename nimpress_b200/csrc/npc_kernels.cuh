@@ -155,27 +155,40 @@ k_count_i8x2(const uint8_t *__restrict__ gt, int64_t row_stride, const npc_row *
     const int64_t nchunks = (n + 7) >> 3;
     uint32_t acc = 0;                            // low half: effect alleles, high half: missing samples
     uint32_t nm = 0, ne = 0;
-    for (int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; c < nchunks; c += (int64_t)gridDim.y * blockDim.x) {
-        uint4 w = ldg_stream(base + c);
-        const int valid = (int)min((int64_t)8, n - c * 8);
-        uint32_t ww[4] = { w.x, w.y, w.z, w.w };
-        if (valid == 8 && chunk_is_fast(w)) {
+    // four independent 16-byte loads in flight per thread before any of them is used
+    constexpr int U = 4;
+    for (int64_t c0 = (int64_t)blockIdx.y * blockDim.x * U + threadIdx.x; c0 < nchunks; c0 += (int64_t)gridDim.y * blockDim.x * U) {
+        uint4 wv[U];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                uint32_t o = pack_idx8(ww[k]);
-                acc += *reinterpret_cast<const uint32_t *>(lut + (o & 0xFFFFu));
-                acc += *reinterpret_cast<const uint32_t *>(lut + (o >> 16));
-            }
-        } else {
+        for (int u = 0; u < U; u++) {
+            const int64_t c = c0 + (int64_t)u * blockDim.x;
+            wv[u] = c < nchunks ? ldg_stream(base + c) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (k < valid) {
-                    uint32_t h = (ww[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-                    acc += *reinterpret_cast<const uint32_t *>(lut + slow_off8(h, row.eaidx));
+        for (int u = 0; u < U; u++) {
+            const int64_t c = c0 + (int64_t)u * blockDim.x;
+            if (c >= nchunks) break;
+            const uint4 w = wv[u];
+            const int valid = (int)min((int64_t)8, n - c * 8);
+            uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+            if (valid == 8 && chunk_is_fast(w)) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t o = pack_idx8(ww[k]);
+                    acc += *reinterpret_cast<const uint32_t *>(lut + (o & 0xFFFFu));
+                    acc += *reinterpret_cast<const uint32_t *>(lut + (o >> 16));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k < valid) {
+                        uint32_t h = (ww[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                        acc += *reinterpret_cast<const uint32_t *>(lut + slow_off8(h, row.eaidx));
+                    }
                 }
             }
+            if (acc & 0x80008000u) { ne += acc & 0xFFFFu; nm += acc >> 16; acc = 0; }   // keep halves from overflowing
         }
-        if (acc & 0x80008000u) { ne += acc & 0xFFFFu; nm += acc >> 16; acc = 0; }   // keep halves from overflowing
     }
     ne += acc & 0xFFFFu; nm += acc >> 16;
     nm = __reduce_add_sync(0xffffffffu, nm);
