@@ -334,7 +334,8 @@ static int launch_count(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const
         const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>(std::min(std::max(want, s_min), s_max), 1), 65535);
         k_count_i8x2<<<dim3((unsigned)n_rows, slabs), 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, counts);
     } else {
-        const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>((c->n + 2047) / 2048, 1), 65535);
+        const int64_t s_min = (c->n + 16383) / 16384, s_max = (c->n + 2047) / 2048, want = (4096 + n_rows - 1) / n_rows;   // as above
+        const unsigned slabs = (unsigned)std::min<int64_t>(std::max<int64_t>(std::min(std::max(want, s_min), s_max), 1), 65535);
         dim3 grid((unsigned)n_rows, slabs);
         if (c->width == 1) k_count_generic<int8_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, c->ploidy, counts);
         else if (c->width == 2) k_count_generic<int16_t><<<grid, 256, 0, c->stream>>>(gt, row_stride, d_rows, c->n, c->ploidy, counts);
