@@ -359,7 +359,7 @@ static int launch_decide_accum(npc_ctx *c, const uint8_t *gt, int64_t row_stride
     if (c->n == 0) return NPC_OK;
     if (c->width == 1 && c->ploidy == 2) {
         const int64_t nchunks = (c->n + 7) / 8;
-        k_accum_i8x2<16, 8><<<(unsigned)((nchunks + 255) / 256), 256, 0, c->stream>>>(gt, row_stride, c->d_rowp, n_rows,
+        k_accum_i8x2<64, 8><<<(unsigned)((nchunks + 255) / 256), 256, 0, c->stream>>>(gt, row_stride, c->d_rowp, n_rows,
                                                                                      c->n, c->d_sums);
     } else {
         const unsigned grid = (unsigned)((c->n + 255) / 256);
