@@ -62,6 +62,8 @@ int64_t nph_result_n_samples(const nph_result *r);
 int64_t nph_result_n_loci(const nph_result *r);          /* score rows                      */
 int64_t nph_result_nloci_used(const nph_result *r);      /* loci in the sum (the divisor/2) */
 int64_t nph_result_rounds(const nph_result *r);          /* 1 = exact reference summation order */
+int64_t nph_result_records_read(const nph_result *r);    /* records the reader handed to the matcher         */
+int64_t nph_result_index_seeks(const nph_result *r);     /* > 0: the file's .tbi / .csi index was used        */
 const double *nph_result_scores(const nph_result *r);
 const npc_locus *nph_result_loci(const nph_result *r);   /* score-file order */
 const char *nph_result_sample(const nph_result *r, int64_t i);
@@ -72,6 +74,14 @@ const char *nph_last_error(void);
 /* CPU only: per score row kind (NPC_KIND_*) and eaidx after coverage / lookup / FILTER. */
 int nph_plan(const char *score_path, const char *genotype_path, const char *bed_path, const nph_params *p,
              int32_t *kind_out, int32_t *eaidx_out, int64_t cap, int64_t *n_rows_out, int64_t *n_samples_out);
+/* The same through the reader the scoring calls use: when <genotypes>.tbi / .csi exists, the file is
+ * BGZF and the score's loci cover little of it, only the stretches around the loci are read (the
+ * reference reaches every locus by an index query, src/nimpress.nim:358); otherwise the file is
+ * streamed.  kind / eaidx are identical either way.  NIMPRESS_NO_INDEX=1 disables the index,
+ * NIMPRESS_FORCE_INDEX=1 uses it whatever the coverage. */
+int nph_plan_indexed(const char *score_path, const char *genotype_path, const char *bed_path, const nph_params *p,
+                     int32_t *kind_out, int32_t *eaidx_out, int64_t cap, int64_t *n_rows_out, int64_t *n_samples_out,
+                     int64_t *records_read_out, int64_t *index_seeks_out);
 
 /* CPU only: raw GT payload of every record of a VCF/BCF, for reader tests.  Record r occupies
  * out[r*row_bytes ..]; returns the record count, width and ploidy of the LAST record read. */

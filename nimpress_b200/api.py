@@ -79,6 +79,8 @@ def load_host_library():
         "nph_result_sample": (cp, [vp, i64]), "nph_result_warnings": (cp, [vp]), "nph_result_free": (None, [vp]),
         "nph_last_error": (cp, []),
         "nph_plan": (C.c_int, [cp, cp, cp, C.POINTER(_Params), vp, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+        "nph_plan_indexed": (C.c_int, [cp, cp, cp, C.POINTER(_Params), vp, vp, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "nph_result_records_read": (i64, [vp]), "nph_result_index_seeks": (i64, [vp]),
         "nph_read_gt": (C.c_int, [cp, vp, i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
         "nph_dbinom": (f64, [i64, i64, f64]), "nph_pbinom": (f64, [i64, i64, f64]), "nph_betai": (f64, [f64, f64, f64]),
         "nph_binom_test": (f64, [i64, i64, f64]), "nph_format_float": (C.c_int, [f64, cp, i32]),
@@ -132,8 +134,9 @@ def loadBedIntervals(ivals, path):
 
 
 class Result:
-    def __init__(self, scores, loci, nloci, samples, warnings, rounds):
+    def __init__(self, scores, loci, nloci, samples, warnings, rounds, records_read=0, index_seeks=0):
         self.scores, self.loci, self.nloci, self.samples, self.warnings, self.rounds = scores, loci, nloci, samples, warnings, rounds
+        self.records_read, self.index_seeks = records_read, index_seeks     # index_seeks > 0: the .tbi / .csi index was used
 
 
 def run(score_path, genotype_path, bed_path=None, imp_locus=ImputeMethodLocus.ps, imp_missing=ImputeMethodMissing.homref,
@@ -183,7 +186,7 @@ def _take_result(L, h):
             else np.zeros(0, LOCUS_DTYPE)
         samples = [L.nph_result_sample(h, i).decode() for i in range(n)]
         return Result(scores, loci, L.nph_result_nloci_used(h), samples, L.nph_result_warnings(h).decode(),
-                      L.nph_result_rounds(h))
+                      L.nph_result_rounds(h), L.nph_result_records_read(h), L.nph_result_index_seeks(h))
     finally:
         L.nph_result_free(h)
 

@@ -85,6 +85,13 @@ const std::vector<int64_t> &Matcher::match(const VariantRecord &rec) {
     return hits_;
 }
 
+void Matcher::add_spans(std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>> &spans) const {
+    for (const auto &kv : index_) {
+        auto &v = spans[kv.first];
+        for (const auto &q : kv.second.by_pos) v.emplace_back(E_[q.second].pos, E_[q.second].stop());
+    }
+}
+
 void Matcher::finish() {
     for (auto &k : kind) if (k == PENDING) k = NPC_KIND_ABSENT;
 }
@@ -104,6 +111,7 @@ struct PhaseTimer {
 
 struct LayoutOverflow { int width, ploidy; };      // a matched record does not fit the context's GT layout
 struct SlabOverflow {};                            // several score files, and their matched rows exceed device memory
+struct NoIndex {};                                 // the index-driven pass is not possible / not worthwhile: stream the file
 
 // WARN lines of one score file, in the reference's order (:326, :527-530, :538-541, :554-557, :567-570, :575-579)
 std::string make_warnings(const ScoreFile &score, const Matcher &M, const std::vector<npc_locus> &loci, int64_t n, const ScoreParams &p) {
@@ -140,8 +148,8 @@ std::string make_warnings(const ScoreFile &score, const Matcher &M, const std::v
 // is uploaded once, and the resident slab is then scored for each file).  Throws LayoutOverflow
 // when a matched record needs a wider layout (the caller restarts the pass with it) and
 // SlabOverflow when several files are given and their rows do not fit device memory.
-void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, const GenomeIntervals &cov, const ScoreParams &p,
-              int gt_width, int ploidy, std::vector<ScoreResult> &outs) {
+void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, const std::string &genotype_path, bool seekable,
+              const GenomeIntervals &cov, const ScoreParams &p, int gt_width, int ploidy, std::vector<ScoreResult> &outs) {
     const int S = (int)scores.size();
     const int64_t n = vcf.n_samples();
     struct PerScore {
@@ -169,6 +177,11 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             }
         }
         if (S > 1) n_lookup = (int64_t)keys.size();
+    }
+    if (seekable) {                                   // an index next to the file and few loci: read only where loci are
+        std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>> spans;
+        for (int k = 0; k < S; k++) ps[k].M->add_spans(spans);
+        if (!vcf.use_regions(spans, genotype_path)) throw NoIndex();
     }
     timer.mark("coverage + entry index");
 
@@ -258,7 +271,10 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
         staged++;
         if (staged == block_rows) flush_stage();
     }
-    for (int k = 0; k < S; k++) { ps[k].M->finish(); outs[k].records_read = records_read; outs[k].records_matched = records_matched; }
+    for (int k = 0; k < S; k++) {
+        ps[k].M->finish();
+        outs[k].records_read = records_read; outs[k].records_matched = records_matched; outs[k].index_seeks = vcf.seeks();
+    }
     timer.mark("stream + match + upload");
 
     // ---- score the slab, collect results ------------------------------------------------------
@@ -302,12 +318,15 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
 bool compute_polygenic_scores_multi(const std::vector<const ScoreFile *> &scores, const std::string &genotype_path,
                                     const GenomeIntervals &cov, const ScoreParams &p, std::vector<ScoreResult> &outs) {
     int width = 1, ploidy = 2;                      // BCF's usual GT layout: int8, diploid
-    for (int attempt = 0; attempt < 4; attempt++) {
-        std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path);
+    bool seekable = true;                           // first try the index-driven pass (needs <file>.tbi / .csi)
+    for (int attempt = 0; attempt < 6; attempt++) {
+        std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path, seekable);
         if (!vcf) return false;
         try {
-            run_pass(scores, *vcf, cov, p, width, ploidy, outs);
+            run_pass(scores, *vcf, genotype_path, seekable, cov, p, width, ploidy, outs);
             return true;
+        } catch (const NoIndex &) {
+            seekable = false;
         } catch (const LayoutOverflow &o) {         // rare: wider integers or higher ploidy -- rerun with that layout
             width = o.width; ploidy = o.ploidy;
         } catch (const SlabOverflow &) {            // too many rows for one resident slab: one file at a time

@@ -34,7 +34,7 @@ struct ScoreResult {
     std::vector<npc_locus> loci;           // per score row, score-file order
     int64_t nloci = 0;
     std::string warnings;                  // the "WARN ..." lines the reference logs, in its order
-    int64_t records_read = 0, records_matched = 0, rounds = 0;
+    int64_t records_read = 0, records_matched = 0, rounds = 0, index_seeks = 0;   // index_seeks > 0: the .tbi / .csi index was used
 };
 
 // Host-side part of getImputedDosages that needs no genotypes: coverage (:526), the streaming
@@ -50,6 +50,8 @@ public:
     void finish();                                  // everything still pending is ABSENT (:536)
     bool has_contig(const std::string &c) const { return index_.count(c) != 0; }
     int64_t n_lookup() const { return n_lookup_; }
+    // 1-based inclusive [pos, stop] of every entry that needs a record lookup, per contig (for the index-driven reader)
+    void add_spans(std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>> &spans) const;
 
     static constexpr int32_t PENDING = -1;
     std::vector<int32_t> kind, eaidx;               // per score entry; kind is NPC_KIND_* or PENDING

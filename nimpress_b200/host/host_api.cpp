@@ -110,6 +110,8 @@ int64_t nph_result_n_samples(const nph_result *r) { return (int64_t)r->r.scores.
 int64_t nph_result_n_loci(const nph_result *r) { return (int64_t)r->r.loci.size(); }
 int64_t nph_result_nloci_used(const nph_result *r) { return r->r.nloci; }
 int64_t nph_result_rounds(const nph_result *r) { return r->r.rounds; }
+int64_t nph_result_records_read(const nph_result *r) { return r->r.records_read; }
+int64_t nph_result_index_seeks(const nph_result *r) { return r->r.index_seeks; }
 const double *nph_result_scores(const nph_result *r) { return r->r.scores.data(); }
 const npc_locus *nph_result_loci(const nph_result *r) { return r->r.loci.data(); }
 const char *nph_result_sample(const nph_result *r, int64_t i) { return r->r.samples[(size_t)i].c_str(); }
@@ -133,6 +135,40 @@ int nph_plan(const char *score_path, const char *genotype_path, const char *bed_
         for (size_t i = 0; i < sf.entries.size(); i++) { kind_out[i] = M.kind[i]; eaidx_out[i] = M.eaidx[i]; }
         *n_rows_out = (int64_t)sf.entries.size();
         *n_samples_out = vcf->n_samples();
+        return NPH_OK;
+    } catch (const InputError &e) {
+        g_err = e.what();
+        return NPH_EINPUT;
+    }
+}
+
+int nph_plan_indexed(const char *score_path, const char *genotype_path, const char *bed_path, const nph_params *p,
+                     int32_t *kind_out, int32_t *eaidx_out, int64_t cap, int64_t *n_rows_out, int64_t *n_samples_out,
+                     int64_t *records_read_out, int64_t *index_seeks_out) {
+    try {
+        ScoreParams q = to_params(p);
+        ScoreFile sf; GenomeIntervals cov;
+        int rc = load_inputs(score_path, bed_path, q, sf, cov, nullptr);
+        if (rc) return rc;
+        if ((int64_t)sf.entries.size() > cap) return NPH_ECAPACITY;
+        Matcher M(sf, cov, q);
+        std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path, true);      // the driver's order: index first
+        if (!vcf) return NPH_EOPEN_VCF;
+        std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>> spans;
+        M.add_spans(spans);
+        if (!vcf->use_regions(spans, genotype_path)) {
+            vcf = open_variant_source(genotype_path, false);
+            if (!vcf) return NPH_EOPEN_VCF;
+        }
+        VariantRecord rec;
+        int64_t nrec = 0;
+        while (vcf->next(rec)) { nrec++; M.match(rec); }
+        M.finish();
+        for (size_t i = 0; i < sf.entries.size(); i++) { kind_out[i] = M.kind[i]; eaidx_out[i] = M.eaidx[i]; }
+        *n_rows_out = (int64_t)sf.entries.size();
+        *n_samples_out = vcf->n_samples();
+        if (records_read_out) *records_read_out = nrec;
+        if (index_seeks_out) *index_seeks_out = vcf->seeks();
         return NPH_OK;
     } catch (const InputError &e) {
         g_err = e.what();

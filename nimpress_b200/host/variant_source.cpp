@@ -1,4 +1,5 @@
 #include "variant_source.hpp"
+#include "region_index.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -151,17 +152,22 @@ InflateStream::~InflateStream() {
     if (fp_) fclose(fp_);
 }
 
-bool InflateStream::open(const std::string &path) {
+bool InflateStream::open(const std::string &path, bool seekable) {
     fp_ = fopen(path.c_str(), "rb");
     if (!fp_) return false;
+    fseek(fp_, 0, SEEK_END);
+    file_size_ = (int64_t)ftell(fp_);
+    fseek(fp_, 0, SEEK_SET);
     unsigned char magic[18] = { 0 };
     size_t got = fread(magic, 1, 18, fp_);
     fseek(fp_, 0, SEEK_SET);
     compressed_ = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     const bool bgzf = got == 18 && compressed_ && (magic[3] & 4) && magic[12] == 'B' && magic[13] == 'C';
+    bgzf_ = bgzf;
+    block_mode_ = seekable && bgzf;
     int want = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
     if (const char *e = getenv("NIMPRESS_THREADS")) if (*e) want = std::max(1, atoi(e));
-    if (bgzf && want > 1) {
+    if (bgzf && want > 1 && !block_mode_) {
         threads_ = want;
         pool_ = std::make_unique<BgzfPool>(fp_, want);
         return true;
@@ -192,6 +198,28 @@ bool InflateStream::fill() {
         if (out_len_ == 0) eof_ = true;
         return out_len_ > 0;
     }
+    if (block_mode_) {                                // exactly one BGZF block per fill: the position stays a virtual offset
+        for (;;) {
+            block_coff_ = in_file_off_ - zs_.avail_in;
+            zs_.next_out = out_.data();
+            zs_.avail_out = (uInt)out_.size();
+            int rc = Z_OK;
+            while (rc != Z_STREAM_END) {
+                if (zs_.avail_in == 0) {
+                    zs_.next_in = in_.data();
+                    zs_.avail_in = (uInt)fread(in_.data(), 1, in_.size(), fp_);
+                    in_file_off_ += zs_.avail_in;
+                    if (zs_.avail_in == 0) { eof_ = true; return false; }
+                }
+                rc = inflate(&zs_, Z_NO_FLUSH);
+                if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR)
+                    throw InputError(std::string("zlib: corrupt compressed stream: ") + (zs_.msg ? zs_.msg : "?"));
+            }
+            if (inflateReset(&zs_) != Z_OK) throw InputError("zlib: inflateReset failed");
+            out_len_ = out_.size() - zs_.avail_out;
+            if (out_len_ > 0) return true;            // empty blocks (the EOF marker) are skipped
+        }
+    }
     zs_.next_out = out_.data();
     zs_.avail_out = (uInt)out_.size();
     while (zs_.avail_out == out_.size()) {            // until something was produced
@@ -209,6 +237,19 @@ bool InflateStream::fill() {
     }
     out_len_ = out_.size() - zs_.avail_out;
     return out_len_ > 0;
+}
+
+void InflateStream::seek_virtual(uint64_t voff) {
+    if (!block_mode_) throw InputError("seek on a stream that was not opened seekable");
+    const uint64_t coff = voff >> 16;
+    if (fseek(fp_, (long)coff, SEEK_SET) != 0) throw InputError("index points outside the file");
+    in_file_off_ = coff;
+    zs_.avail_in = 0;
+    if (inflateReset(&zs_) != Z_OK) throw InputError("zlib: inflateReset failed");
+    eof_ = false;
+    out_pos_ = out_len_ = 0;
+    if (!fill()) return;                              // at or past the end: the next read reports end of stream
+    out_pos_ = std::min<size_t>((size_t)(voff & 0xFFFF), out_len_);
 }
 
 size_t InflateStream::read(void *dst, size_t n) {
@@ -311,7 +352,16 @@ public:
         }
         return false;
     }
-    bool next(VariantRecord &rec) override {
+    InflateStream *stream() override { return in_.get(); }
+    bool index_names_contigs() const override { return index_ && !index_->names().empty(); }
+    int contig_rank(const VariantRecord &rec) const override { return contig_rank(*rec.contig); }
+    int contig_rank(const std::string &name) const override {
+        if (!index_) return -1;
+        if (rank_.empty()) for (size_t i = 0; i < index_->names().size(); i++) rank_.emplace(index_->names()[i], (int)i);
+        auto it = rank_.find(name);
+        return it == rank_.end() ? -1 : it->second;
+    }
+    bool next_raw(VariantRecord &rec) override {
         for (;;) {
             if (!in_->getline(line_)) return false;
             if (!line_.empty()) break;
@@ -425,6 +475,7 @@ private:
     const char *gt_p_ = nullptr;
     int gt_idx_ = -1;
     bool gt_loaded_ = true;
+    mutable std::unordered_map<std::string, int> rank_;
     std::vector<int32_t> vals_;
     std::vector<int> counts_;
     std::vector<uint8_t> gt_;
@@ -447,7 +498,13 @@ public:
         parse_header(text);
         return true;
     }
-    bool next(VariantRecord &rec) override {
+    InflateStream *stream() override { return in_.get(); }
+    int contig_rank(const VariantRecord &rec) const override { return rec.contig_id; }       // CSI reference ids = header contig ids
+    int contig_rank(const std::string &name) const override {
+        for (size_t i = 0; i < contigs_.size(); i++) if (contigs_[i] == name) return (int)i;
+        return -1;
+    }
+    bool next_raw(VariantRecord &rec) override {
         uint32_t lens[2];
         size_t got = in_->read(lens, 8);
         if (got == 0) return false;
@@ -605,9 +662,77 @@ private:
     std::vector<uint8_t> shared_, indiv_;
 };
 
-std::unique_ptr<VariantSource> open_variant_source(const std::string &path) {
+// ------------------------------------------------------------------------------------------
+// index-driven region mode
+// ------------------------------------------------------------------------------------------
+
+VariantSource::VariantSource() = default;
+VariantSource::~VariantSource() = default;
+
+bool VariantSource::use_regions(const std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>> &spans,
+                                const std::string &path) {
+    if (const char *e = getenv("NIMPRESS_NO_INDEX")) if (*e && *e != '0') return false;
+    InflateStream *in = stream();
+    if (!in || !in->is_bgzf()) return false;
+    index_ = RegionIndex::load(path);
+    if (!index_) return false;
+    if (!index_names_contigs()) { index_.reset(); return false; }
+    std::vector<Region> regs;
+    for (const auto &kv : spans) {
+        const int ref = contig_rank(kv.first);
+        if (ref < 0 || ref >= index_->n_ref()) continue;            // contig not in the file: its loci stay unmatched, as when streaming
+        for (const auto &sp : kv.second) regs.push_back(Region{ ref, sp.first - 1, sp.second });
+    }
+    std::sort(regs.begin(), regs.end(), [](const Region &a, const Region &b) { return a.ref != b.ref ? a.ref < b.ref : a.beg0 < b.beg0; });
+    std::vector<Region> merged;                                       // spans closer than one 16 kb index window are one region
+    for (const Region &r : regs) {
+        if (!merged.empty() && merged.back().ref == r.ref && r.beg0 <= merged.back().end0 + (1 << 14)) merged.back().end0 = std::max(merged.back().end0, r.end0);
+        else merged.push_back(r);
+    }
+    // a region costs about one or two 64 KiB blocks of sequential inflate; the whole file streams at several GB/s
+    // through the inflate pool.  Use the index only when it saves most of the file.
+    const char *force = getenv("NIMPRESS_FORCE_INDEX");
+    if (!(force && *force && *force != '0') && (int64_t)merged.size() * (192 << 10) > in->file_size() / 4) { index_.reset(); return false; }
+    regions_ = std::move(merged);
+    region_ = 0; filtering_ = true; positioned_ = false;
+    return true;
+}
+
+bool VariantSource::next(VariantRecord &rec) {
+    if (!filtering_) return next_raw(rec);
+    InflateStream *in = stream();
+    for (;;) {
+        if (region_ >= regions_.size()) return false;
+        if (!positioned_) {                                           // entering regions_[region_]: jump if its first record lies ahead
+            const Region &R = regions_[region_];
+            const uint64_t v = index_->query_start(R.ref, R.beg0, R.end0);
+            if (v == RegionIndex::NONE) { region_++; continue; }
+            if (v > in->tell_virtual()) { in->seek_virtual(v); seeks_++; }
+            positioned_ = true;
+        }
+        if (!next_raw(rec)) return false;
+        for (;;) {                                                    // place the record against the current region
+            const Region &R = regions_[region_];
+            const int rank = contig_rank(rec);
+            const bool past = rank > R.ref || (rank == R.ref && rec.pos - 1 >= R.end0);
+            if (!past) {
+                if (rank == R.ref && rec.end() > R.beg0) return true; // overlaps (rec.end() is 1-based inclusive = 0-based exclusive)
+                break;                                                // before the region (or a contig the index does not know): keep reading
+            }
+            if (++region_ >= regions_.size()) return false;
+            const Region &N = regions_[region_];
+            const uint64_t v = index_->query_start(N.ref, N.beg0, N.end0);
+            if (v == RegionIndex::NONE) { positioned_ = false; break; }
+            if (v > in->tell_virtual()) { in->seek_virtual(v); seeks_++; positioned_ = true; break; }   // this record lies before the next region's first
+            positioned_ = true;                                       // no jump: the same record may belong to the next region
+        }
+        if (!positioned_) continue;
+    }
+}
+
+std::unique_ptr<VariantSource> open_variant_source(const std::string &path, bool seekable) {
     auto s = std::make_unique<InflateStream>();
-    if (!s->open(path)) return nullptr;
+    if (!s->open(path, seekable)) return nullptr;
     uint8_t magic[5] = { 0 };
     try {
         if (!s->peek(magic, 5)) return nullptr;

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <memory>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "util.hpp"
@@ -28,7 +30,13 @@ class InflateStream {
 public:
     InflateStream();
     ~InflateStream();
-    bool open(const std::string &path);
+    // seekable: BGZF read one block at a time by one sequential zlib stream, so that the position is
+    // known as a virtual offset and seek_virtual can jump (the reader's index-driven region mode)
+    bool open(const std::string &path, bool seekable = false);
+    bool is_bgzf() const { return bgzf_; }
+    void seek_virtual(uint64_t voff);                 // block file offset << 16 | offset inside the inflated block
+    uint64_t tell_virtual() const { return (block_coff_ << 16) | (uint64_t)out_pos_; }
+    int64_t file_size() const { return file_size_; }
     size_t read(void *dst, size_t n);                 // up to n bytes; 0 at end of stream
     bool read_exact(void *dst, size_t n);
     bool getline(std::string &line);                  // strips \n and a preceding \r
@@ -37,7 +45,9 @@ public:
 private:
     bool fill();
     FILE *fp_ = nullptr;
-    bool compressed_ = false, zinit_ = false, eof_ = false;
+    bool compressed_ = false, zinit_ = false, eof_ = false, bgzf_ = false, block_mode_ = false;
+    uint64_t block_coff_ = 0, in_file_off_ = 0;       // block mode: file offset of the current block / of the next byte to fread
+    int64_t file_size_ = 0;
     z_stream zs_{};
     std::vector<uint8_t> in_, out_;
     size_t out_pos_ = 0, out_len_ = 0;
@@ -61,20 +71,43 @@ struct VariantRecord {
     int64_t end() const { return pos + rlen - 1; }    // 1-based inclusive
 };
 
+class RegionIndex;
+
 class VariantSource {
 public:
-    virtual ~VariantSource() = default;
-    virtual bool next(VariantRecord &rec) = 0;        // false at end of file; throws InputError on corrupt input
+    VariantSource();
+    virtual ~VariantSource();
+    // false at end of file; throws InputError on corrupt input.  With regions set (use_regions) only
+    // records that can overlap one of them are returned, the rest of the file is skipped by seeking.
+    bool next(VariantRecord &rec);
+    // Restrict the pass to records overlapping these 1-based inclusive spans per contig, using the
+    // file's .tbi / .csi index.  false (and nothing changes) when there is no usable index, the file is
+    // not BGZF, or the spans cover so much of the file that streaming it with the inflate pool is faster.
+    bool use_regions(const std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>> &spans, const std::string &path);
+    int64_t seeks() const { return seeks_; }
     // Fills rec.gt / ploidy / gt_width of the record next() just returned (rec.has_gt tells whether
     // it has a GT field).  Text VCF parses its genotype columns only here; BCF has them already.
     virtual void load_gt(VariantRecord &) {}
     const std::vector<std::string> &samples() const { return samples_; }
     int64_t n_samples() const { return (int64_t)samples_.size(); }
 protected:
+    virtual bool next_raw(VariantRecord &rec) = 0;
+    virtual InflateStream *stream() = 0;
+    virtual int contig_rank(const VariantRecord &rec) const = 0;      // position of the record's contig in the index's order, -1 unknown
+    virtual int contig_rank(const std::string &name) const = 0;
+    virtual bool index_names_contigs() const { return true; }         // text VCF: the index must carry the contig names
     std::vector<std::string> samples_;
+    std::unique_ptr<RegionIndex> index_;
+private:
+    struct Region { int ref; int64_t beg0, end0; };                   // 0-based half open
+    std::vector<Region> regions_;
+    size_t region_ = 0;
+    bool filtering_ = false, positioned_ = false;
+    int64_t seeks_ = 0;
 };
 
 // nullptr: the file cannot be opened or is neither VCF nor BCF (the reference: open() == false).
-std::unique_ptr<VariantSource> open_variant_source(const std::string &path);
+// seekable: read BGZF block by block with one zlib stream so that VariantSource::use_regions can jump (no inflate pool).
+std::unique_ptr<VariantSource> open_variant_source(const std::string &path, bool seekable = false);
 
 }  // namespace nph

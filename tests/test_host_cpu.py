@@ -297,3 +297,47 @@ def test_vcf_text_gt_random_grammar(api, tmp_path, seed):
             exp[s, :len(v)] = v
         got = out[r, :n * ploidy * width].view(dt).reshape(n, ploidy)
         assert np.array_equal(got, exp), (r, lines[r][:80])
+
+
+def plan_indexed(api, score, vcf, bed=None, ignorefilt=False):
+    L = api.load_host_library()
+    p = api._Params(0, 0, 3, int(ignorefilt), int(bed is not None), 0, 0, 0, 100, 0.05, 0.001)
+    kind = np.zeros(1 << 16, np.int32); ea = np.zeros(1 << 16, np.int32)
+    n_rows, n_s, nrec, seeks = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    rc = L.nph_plan_indexed(os.fsencode(score), os.fsencode(vcf), os.fsencode(bed) if bed else None, C.byref(p), kind.ctypes.data,
+                            ea.ctypes.data, len(kind), C.byref(n_rows), C.byref(n_s), C.byref(nrec), C.byref(seeks))
+    assert rc == 0, rc
+    return kind[:n_rows.value].copy(), ea[:n_rows.value].copy(), nrec.value, seeks.value
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_index_driven_reader_equals_streaming(api, tmp_path, seed, monkeypatch):
+    """With <file>.tbi (VCF) / <file>.csi (BCF) the reader jumps between the score's loci like the
+    reference's per-locus index queries; what each score row matches -- duplicate sites, a 2-base REF
+    overlapping the next position, INFO/END spans reaching across index windows, contigs missing from
+    the file -- is identical to streaming the whole file, on far fewer records."""
+    import util_bcf
+    rng = np.random.default_rng(seed)
+    monkeypatch.setattr(util_bcf, "INDEX_BLOCK", 3000 + 500 * seed)           # ~40 BGZF blocks: jumps cross block boundaries
+    d = make_dataset(str(tmp_path), rng, n=12, V=1500, index=True, spread=400, sorted_scores=seed % 2 == 0)
+    # a sparse score: a few of the dataset's entries (incl. every trap entry at the end), so that the index pays off
+    offset_and_entries = open(d["score"]).read().split("\n")
+    head, ents = offset_and_entries[:5], offset_and_entries[5:]
+    keep = [e for i, e in enumerate(ents) if e and (rng.random() < 0.03 or i >= len(ents) - 12)]
+    sparse = tmp_path / "sparse.score"
+    sparse.write_text("\n".join(head + keep) + "\n")
+    monkeypatch.setenv("NIMPRESS_FORCE_INDEX", "1")
+    for f in (d["vcf"], d["bcf"]):
+        for bed in (None, d["bed"]):
+            rc, kind, ea, n = plan(api, str(sparse), f, bed)
+            k2, e2, nrec, seeks = plan_indexed(api, str(sparse), f, bed)
+            assert rc == 0 and np.array_equal(kind, k2) and np.array_equal(ea, e2), f
+            assert seeks > 0 and nrec < len(d["records"]) // 2, (f, seeks, nrec)
+    # a dense score reads everything: same answers again
+    k1 = plan(api, d["score"], d["bcf"])
+    k2 = plan_indexed(api, d["score"], d["bcf"])
+    assert np.array_equal(k1[1], k2[0]) and np.array_equal(k1[2], k2[1])
+    # without the override the library weighs regions against file size; with NIMPRESS_NO_INDEX it never uses the index
+    monkeypatch.delenv("NIMPRESS_FORCE_INDEX")
+    monkeypatch.setenv("NIMPRESS_NO_INDEX", "1")
+    assert plan_indexed(api, str(sparse), d["bcf"])[3] == 0

@@ -124,3 +124,40 @@ def test_rounds_when_slab_is_too_small(api, tmp_path, monkeypatch):
     monkeypatch.delenv("NIMPRESS_SLAB_ROWS")
     got = api.run(d["score"], d["bcf"], d["bed"], exact_order=True)
     assert got.rounds == 1 and np.array_equal(bits(got.scores[np.isfinite(got.scores)]), bits(want["scores"][np.isfinite(want["scores"])]))
+
+
+def test_indexed_files_are_read_by_region(api, tmp_path, monkeypatch):
+    """A sparse score over files with a .tbi / .csi next to them: the pass jumps from locus to locus (index_seeks > 0,
+    a fraction of the records read) and scores, per-locus records and WARN text equal the oracle's on the whole file;
+    several score files at once share the one indexed pass."""
+    import util_bcf
+    rng = np.random.default_rng(41)
+    monkeypatch.setattr(util_bcf, "INDEX_BLOCK", 6000)
+    d = make_dataset(str(tmp_path), rng, n=400, V=900, index=True, spread=300)
+    lines = open(d["score"]).read().split("\n")
+    head, ents = lines[:5], [e for e in lines[5:] if e]
+    sparse = []
+    for k in range(3):
+        keep = [e for i, e in enumerate(ents) if rng.random() < 0.04 or i >= len(ents) - 10]
+        p = tmp_path / f"sparse{k}.score"
+        p.write_text("\n".join(head + keep) + "\n")
+        sparse.append(str(p))
+    monkeypatch.setenv("NIMPRESS_FORCE_INDEX", "1")
+    for f in (d["vcf"], d["bcf"]):
+        want = orc.compute_scores_files(sparse[0], d["vcf"], d["bed"])
+        got = api.run(sparse[0], f, d["bed"], exact_order=True)
+        assert got.index_seeks > 0 and got.records_read < len(d["records"]) // 2
+        assert got.nloci == want["nloci"] and got.warnings == want["warn"]
+        assert_loci_equal(got.loci, want["loci"])
+        ok = np.isfinite(want["scores"])
+        assert np.array_equal(bits(got.scores[ok]), bits(want["scores"][ok]))
+    multi = api.run_multi(sparse, d["bcf"], exact_order=True)
+    for k, p in enumerate(sparse):
+        want = orc.compute_scores_files(p, d["vcf"])
+        assert multi[k].index_seeks > 0 and multi[k].warnings == want["warn"]
+        assert_loci_equal(multi[k].loci, want["loci"])
+        ok = np.isfinite(want["scores"])
+        assert np.array_equal(bits(multi[k].scores[ok]), bits(want["scores"][ok]))
+    monkeypatch.setenv("NIMPRESS_NO_INDEX", "1")
+    monkeypatch.delenv("NIMPRESS_FORCE_INDEX")
+    assert api.run(sparse[0], d["bcf"]).index_seeks == 0

@@ -6,11 +6,15 @@ import zlib
 import numpy as np
 
 VEND = {1: -127, 2: -32767, 4: -2147483647}
+INDEX_BLOCK = 0xFF00          # uncompressed bytes per BGZF block of the indexed files; tests shrink it to get many blocks
 
 
-def bgzf_compress(data, block=0xFF00):
+def bgzf_compress(data, block=0xFF00, offsets=None):
+    """offsets: optional list that receives the file offset of every block (for the index writers)."""
     out = bytearray()
     for i in range(0, max(len(data), 1), block):
+        if offsets is not None:
+            offsets.append(len(out))
         chunk = data[i:i + block]
         co = zlib.compressobj(6, zlib.DEFLATED, -15)
         comp = co.compress(chunk) + co.flush()
@@ -35,7 +39,7 @@ def gt_text(row, width):
     return s or "."
 
 
-def write_vcf(path, samples, records, contigs=None, filters=("FAIL",), crlf=False, compress=None):
+def write_vcf(path, samples, records, contigs=None, filters=("FAIL",), crlf=False, compress=None, index=None):
     """records: dicts contig,pos,ref,alts(list),filter(str),gt(int array [n,ploidy], BCF encoding), info(str)."""
     nl = "\r\n" if crlf else "\n"
     lines = ["##fileformat=VCFv4.2"]
@@ -57,6 +61,19 @@ def write_vcf(path, samples, records, contigs=None, filters=("FAIL",), crlf=Fals
             cols += [gt_text(g[i], width) + ":7" for i in range(len(samples))]
         lines.append("\t".join(cols))
     data = (nl.join(lines) + nl).encode()
+    if index:                                              # tabix index of the BGZF file: needs the byte span of every record line
+        assert compress == "bgzf"
+        head = len((nl.join(lines[:len(lines) - len(records)]) + nl).encode())
+        spans, pos = [], head
+        for ln in lines[len(lines) - len(records):]:
+            n = len(ln.encode()) + len(nl)
+            spans.append((pos, pos + n)); pos += n
+        offs = []
+        comp = bgzf_compress(data, block=INDEX_BLOCK, offsets=offs)
+        open(path, "wb").write(comp)
+        write_index(path + (".csi" if index == "csi" else ".tbi"), records, spans, offs, contigs or sorted({r["contig"] for r in records}),
+                    csi=index == "csi", tabix_meta=True, block=INDEX_BLOCK)
+        return
     if compress == "bgzf":
         data = bgzf_compress(data)
     elif compress == "gzip":
@@ -95,7 +112,7 @@ def _typed_ints(vals):
     return _desc(len(vals), 3) + struct.pack(f"<{len(vals)}i", *vals)
 
 
-def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf", with_idx=False, extra_fmt=False):
+def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf", with_idx=False, extra_fmt=False, index=None):
     """BCF2.2.  Dictionary of strings: PASS, then FILTERs, INFO END, FORMAT GT, FORMAT DP (header order,
     or explicit IDX= when with_idx, deliberately permuted)."""
     ids = ["PASS"] + list(filters) + ["END", "GT", "DP"]
@@ -115,7 +132,9 @@ def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf
     text = ("\n".join(lines) + "\n").encode() + b"\0"
     out = bytearray(b"BCF\2\2" + struct.pack("<I", len(text)) + text)
     n = len(samples)
+    spans = []
     for r in records:
+        rec_start = len(out)
         g = np.ascontiguousarray(r["gt"])
         alleles = [r["ref"]] + list(r["alts"])
         rlen = len(r["ref"])
@@ -140,7 +159,84 @@ def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf
         t = {1: 1, 2: 2, 4: 3}[g.dtype.itemsize]
         indiv += _typed_int(idx["GT"]) + _desc(g.shape[1], t) + g.tobytes()
         out += struct.pack("<II", len(shared), len(indiv)) + shared + indiv
+        spans.append((rec_start, len(out)))
     data = bytes(out)
+    if index:                                              # CSI index (what `bcftools index` writes for a BCF)
+        assert compress == "bgzf"
+        offs = []
+        comp = bgzf_compress(data, block=INDEX_BLOCK, offsets=offs)
+        open(path, "wb").write(comp)
+        write_index(path + ".csi", records, spans, offs, contigs, csi=True, tabix_meta=False, block=INDEX_BLOCK)
+        return
     if compress == "bgzf":
         data = bgzf_compress(data)
     open(path, "wb").write(data)
+
+
+# ---- tabix / CSI index writers (tests only; the binning scheme of the SAM / tabix / CSI specifications) ----
+
+def _rec_span0(r):
+    """0-based half-open reference span of a record: REF length, or INFO/END."""
+    beg = r["pos"] - 1
+    end = beg + len(r["ref"])
+    if r.get("info", ".").startswith("END="):
+        end = max(int(r["info"][4:]), r["pos"])
+    return beg, end
+
+
+def _reg2bin(beg, end, min_shift, depth):
+    end -= 1
+    s, t = min_shift, ((1 << (depth * 3)) - 1) // 7
+    for l in range(depth, 0, -1):
+        if beg >> s == end >> s:
+            return t + (beg >> s)
+        s += 3
+        t -= 1 << ((l - 1) * 3)
+    return 0
+
+
+def write_index(path, records, spans, block_offsets, contigs, csi, tabix_meta, block=0xFF00, min_shift=14, depth=5):
+    """records must be sorted by (contig order, pos) as in the data file.  spans: uncompressed byte span of each record."""
+    voff = lambda p: (block_offsets[p // block] << 16) | (p % block) if p // block < len(block_offsets) else ((block_offsets[-1] + 1) << 16)
+    per_ref = {c: dict(bins={}, lin={}) for c in contigs}
+    for r, (a, b) in zip(records, spans):
+        beg, end = _rec_span0(r)
+        R = per_ref[r["contig"]]
+        bn = _reg2bin(beg, end, min_shift, depth)
+        ch = R["bins"].setdefault(bn, [])
+        if ch and ch[-1][1] == voff(a):
+            ch[-1] = (ch[-1][0], voff(b))                   # adjacent records of one bin: one chunk
+        else:
+            ch.append((voff(a), voff(b)))
+        for w in range(beg >> min_shift, ((end - 1) >> min_shift) + 1):
+            R["lin"].setdefault(w, voff(a))                 # first record overlapping the window
+    out = bytearray()
+    names = b"".join(c.encode() + b"\0" for c in contigs)
+    meta = struct.pack("<6i", 2, 1, 2, 0, ord("#"), 0) + struct.pack("<i", len(names)) + names
+    if csi:
+        aux = meta if tabix_meta else b""
+        out += b"CSI\1" + struct.pack("<iii", min_shift, depth, len(aux)) + aux + struct.pack("<i", len(contigs))
+    else:
+        out += b"TBI\1" + struct.pack("<i", len(contigs)) + meta
+    for c in contigs:
+        R = per_ref[c]
+        nwin = max(R["lin"]) + 1 if R["lin"] else 0
+        lin, prev = [], 0
+        for w in range(nwin):                               # empty windows carry the previous offset (htslib back-fill)
+            prev = R["lin"].get(w, prev)
+            lin.append(prev)
+        out += struct.pack("<i", len(R["bins"]))
+        for bn in sorted(R["bins"]):
+            out += struct.pack("<I", bn)
+            if csi:                                         # loffset: linear offset of the bin's first window
+                lvl, t = 0, 0
+                while bn >= t + (1 << (3 * lvl)):
+                    t += 1 << (3 * lvl); lvl += 1
+                w0 = (bn - t) << (3 * (depth - lvl))
+                out += struct.pack("<Q", lin[min(w0, nwin - 1)] if nwin else 0)
+            out += struct.pack("<i", len(R["bins"][bn]))
+            for a, b in R["bins"][bn]:
+                out += struct.pack("<QQ", a, b)
+        if not csi:
+            out += struct.pack("<i", nwin) + b"".join(struct.pack("<Q", v) for v in lin)
+    open(path, "wb").write(bgzf_compress(bytes(out)))

@@ -10,13 +10,15 @@ BASES = "ACGT"
 
 
 def make_dataset(tmp, rng, n=300, V=120, miss_rate=0.03, with_traps=True, gt_dtype=np.int8, ploidy=2, haploid_rate=0.0,
-                 contigs=("1", "2", "X"), sorted_scores=True):
-    """Returns dict(score, vcf, bcf, bed, samples, records, entries)."""
+                 contigs=("1", "2", "X"), sorted_scores=True, index=False, spread=40):
+    """Returns dict(score, vcf, bcf, bed, samples, records, entries).  index: records are put in file order
+    (contig, position; same-site records keep their order) and <vcf>.tbi / <bcf>.csi are written.  spread:
+    average distance between sites."""
     samples = [f"S{i + 1}" for i in range(n)]
     records = []
     vend = {1: -127, 2: -32767, 4: -2147483647}[np.dtype(gt_dtype).itemsize]
     for c in contigs:
-        pos = np.sort(rng.choice(np.arange(100, 100 + 40 * V), size=V // len(contigs), replace=False))
+        pos = np.sort(rng.choice(np.arange(100, 100 + spread * V), size=V // len(contigs), replace=False))
         for p in pos:
             ref = BASES[rng.integers(4)] if rng.random() < 0.85 else "".join(BASES[i] for i in rng.integers(0, 4, size=rng.integers(2, 5)))
             n_alt = 1 if rng.random() < 0.8 else int(rng.integers(2, 4))
@@ -97,10 +99,13 @@ def make_dataset(tmp, rng, n=300, V=120, miss_rate=0.03, with_traps=True, gt_dty
             elif u < 0.8:
                 rows.append((e[0], e[1] - 5, stop - 1))                                                     # ends one short
         fh.write("\n".join(f"{c}\t{s}\t{t}\textra" for c, s, t in rows))
+    if index:
+        order = {c: i for i, c in enumerate(contigs)}
+        records = sorted(records, key=lambda r: (order[r["contig"]], r["pos"]))      # stable: duplicates keep their order
     vcf = os.path.join(tmp, "d.vcf.gz")
-    write_vcf(vcf, samples, records, contigs=list(contigs), filters=("FAIL", "LowQ"), compress="bgzf")
+    write_vcf(vcf, samples, records, contigs=list(contigs), filters=("FAIL", "LowQ"), compress="bgzf", index="tbi" if index else None)
     bcf = os.path.join(tmp, "d.bcf")
-    write_bcf(bcf, samples, records, contigs=list(contigs), filters=("FAIL", "LowQ"), compress="bgzf")
+    write_bcf(bcf, samples, records, contigs=list(contigs), filters=("FAIL", "LowQ"), compress="bgzf", index=bool(index))
     return dict(score=score, vcf=vcf, bcf=bcf, bed=bed, samples=samples, records=records, entries=entries)
 
 
