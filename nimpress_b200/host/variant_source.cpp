@@ -689,10 +689,22 @@ bool VariantSource::use_regions(const std::unordered_map<std::string, std::vecto
         if (!merged.empty() && merged.back().ref == r.ref && r.beg0 <= merged.back().end0 + (1 << 14)) merged.back().end0 = std::max(merged.back().end0, r.end0);
         else merged.push_back(r);
     }
-    // a region costs about one or two 64 KiB blocks of sequential inflate; the whole file streams at several GB/s
-    // through the inflate pool.  Use the index only when it saves most of the file.
+    // Jumping reads block by block with one zlib stream (no inflate pool: several times slower per byte than
+    // streaming).  Estimate the compressed bytes the regions need from the index itself -- from the first record
+    // of a region to the first record at its end, plus a block -- and use the index only when that is a small
+    // part of the file.
     const char *force = getenv("NIMPRESS_FORCE_INDEX");
-    if (!(force && *force && *force != '0') && (int64_t)merged.size() * (192 << 10) > in->file_size() / 4) { index_.reset(); return false; }
+    if (!(force && *force && *force != '0')) {
+        int64_t est = 0;
+        for (const Region &r : merged) {
+            const uint64_t v0 = index_->query_start(r.ref, r.beg0, r.end0);
+            if (v0 == RegionIndex::NONE) continue;
+            const uint64_t v1 = index_->query_start(r.ref, r.end0, r.end0 + 1);
+            const int64_t c0 = (int64_t)(v0 >> 16), c1 = v1 == RegionIndex::NONE ? in->file_size() : (int64_t)(v1 >> 16);
+            est += std::max<int64_t>(c1 - c0, 0) + (64 << 10);
+        }
+        if (est * 8 > in->file_size()) { index_.reset(); return false; }
+    }
     regions_ = std::move(merged);
     region_ = 0; filtering_ = true; positioned_ = false;
     return true;
