@@ -276,6 +276,8 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
         outs[k].records_read = records_read; outs[k].records_matched = records_matched; outs[k].index_seeks = vcf.seeks();
     }
     timer.mark("stream + match + upload");
+    if (timer.on) fprintf(stderr, "[nimpress timing] records read %lld, matched %lld, index seeks %lld%s\n", (long long)records_read,
+                          (long long)records_matched, (long long)vcf.seeks(), vcf.seeks() ? " (.tbi / .csi used)" : "");
 
     // ---- score the slab, collect results ------------------------------------------------------
     std::vector<std::vector<npc_locus>> logs(S);
