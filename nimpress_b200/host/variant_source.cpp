@@ -172,7 +172,7 @@ bool InflateStream::open(const std::string &path, bool seekable) {
         pool_ = std::make_unique<BgzfPool>(fp_, want);
         return true;
     }
-    in_.resize(1 << 20);
+    in_.resize(block_mode_ ? 128 << 10 : 1 << 20);    // seekable: a jump costs one read of two blocks, not a megabyte
     out_.resize(4 << 20);
     if (compressed_) {
         memset(&zs_, 0, sizeof zs_);
