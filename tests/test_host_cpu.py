@@ -341,3 +341,39 @@ def test_index_driven_reader_equals_streaming(api, tmp_path, seed, monkeypatch):
     monkeypatch.delenv("NIMPRESS_FORCE_INDEX")
     monkeypatch.setenv("NIMPRESS_NO_INDEX", "1")
     assert plan_indexed(api, str(sparse), d["bcf"])[3] == 0
+
+
+def test_index_reader_long_spans_and_edges(api, tmp_path, monkeypatch):
+    """Records whose INFO/END reaches over many 16 kb index windows (they sit in a coarse bin, far before the
+    locus they overlap), loci before the first / after the last record, on a contig the file lacks, and at the
+    first base: the index-driven pass finds exactly what streaming finds (TBI and CSI)."""
+    import util_bcf
+    from util_bcf import write_bcf, write_vcf
+    monkeypatch.setattr(util_bcf, "INDEX_BLOCK", 2000)
+    monkeypatch.setenv("NIMPRESS_FORCE_INDEX", "1")
+    rng = np.random.default_rng(8)
+    n = 6
+    samples = [f"s{i}" for i in range(n)]
+    g = lambda: ((rng.integers(0, 2, size=(n, 2)) + 1) << 1).astype(np.int8)
+    recs = []
+    for c in ("1", "2"):
+        recs.append(dict(contig=c, pos=5000, ref="G", alts=["T"], filter="PASS", info="END=405000", gt=g()))     # spans 25 windows
+        for p in range(20000, 900000, 1700):
+            recs.append(dict(contig=c, pos=p, ref="A", alts=["C"], filter="PASS", gt=g()))
+        recs.append(dict(contig=c, pos=300000, ref="AT", alts=["A"], filter="PASS", gt=g()))
+    order = {"1": 0, "2": 1}
+    recs.sort(key=lambda r: (order[r["contig"]], r["pos"]))
+    vcf, bcf = str(tmp_path / "l.vcf.gz"), str(tmp_path / "l.bcf")
+    write_vcf(vcf, samples, recs, contigs=["1", "2"], compress="bgzf", index="tbi")
+    write_bcf(bcf, samples, recs, ["1", "2"], index=True)
+    ents = [("1", 1, "G", "T"), ("1", 4999, "G", "T"), ("1", 5000, "G", "T"), ("1", 200000, "G", "T"), ("1", 404999, "G", "G"), ("1", 405001, "G", "T"),
+            ("1", 300001, "AT", "AT"), ("2", 333300, "G", "T"), ("2", 899700, "A", "C"), ("2", 2000000, "A", "C"), ("3", 100, "A", "C"),
+            ("1", 21700, "A", "C"), ("2", 20000, "A", "A")]
+    sc = tmp_path / "l.score"
+    sc.write_text("x\nd\nc\nhs37d5\n0\n" + "\n".join(f"{c}\t{p}\t{r}\t{e}\t0.1\t0.2" for c, p, r, e in ents) + "\n")
+    for f in (vcf, bcf):
+        rc, kind, ea, _ = plan(api, str(sc), f)
+        k2, e2, nrec, seeks = plan_indexed(api, str(sc), f)
+        assert rc == 0 and np.array_equal(kind, k2) and np.array_equal(ea, e2), (f, kind, k2)
+        assert seeks > 0 and nrec < len(recs) // 3
+        assert list(kind[:7]) == [2, 2, 0, 0, 0, 2, 0] and kind[9] == 2 and kind[10] == 2      # 0 = matched, 2 = absent
