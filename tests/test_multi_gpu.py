@@ -361,3 +361,19 @@ def test_contraction_k_split(nb, parts, monkeypatch):
         assert eng.multi_contractions == 1
         check_lists(got, gt, n, lists, offs, False, 1e-12, **pol)
         eng.close()
+
+
+@pytest.mark.parametrize("S", [1, 2])
+def test_contraction_forced_for_one_or_two_definitions(nb, S, monkeypatch):
+    """NPC_MULTI=1 sends even one or two definitions through the contraction (by default they take the fused kernel)."""
+    monkeypatch.setenv("NPC_MULTI", "1")
+    rng = np.random.default_rng(90 + S)
+    n, V = 5000, 100
+    gt = random_cohort(rng, n, V, miss_rate=0.02, n_alt=2)
+    lists = [random_rows(rng, V, n_rows=150, n_alt=2) for _ in range(S)]
+    eng = nb.Engine(n, max_rows_per_block=128, n_slots=2)
+    fill_slab(eng, gt)
+    got = eng.score_resident_multi(lists, [0.5] * S)
+    assert eng.multi_contractions == 1
+    check_lists(got, gt, n, lists, [0.5] * S, False, 1e-12)
+    eng.close()
