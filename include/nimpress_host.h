@@ -88,6 +88,10 @@ int nph_plan_indexed(const char *score_path, const char *genotype_path, const ch
 int nph_read_gt(const char *genotype_path, uint8_t *out, int64_t row_bytes, int64_t max_records,
                 int64_t *n_records, int64_t *n_samples, int32_t *width, int32_t *ploidy);
 
+/* The pool's raw-DEFLATE decoder on one buffer (tests): `in` readable 16 bytes beyond in_len, `out` writable
+ * 16 bytes beyond out_len; 1 = decoded exactly out_len bytes and the stream ended, 0 = not (the reader then uses zlib). */
+int nph_fast_inflate(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
+
 double nph_dbinom(int64_t x, int64_t n, double p);
 double nph_pbinom(int64_t x, int64_t n, double p);
 double nph_betai(double a, double b, double x);

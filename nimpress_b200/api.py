@@ -79,6 +79,7 @@ def load_host_library():
         "nph_result_sample": (cp, [vp, i64]), "nph_result_warnings": (cp, [vp]), "nph_result_free": (None, [vp]),
         "nph_last_error": (cp, []),
         "nph_plan": (C.c_int, [cp, cp, cp, C.POINTER(_Params), vp, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+        "nph_fast_inflate": (C.c_int, [vp, i64, vp, i64]),
         "nph_plan_indexed": (C.c_int, [cp, cp, cp, C.POINTER(_Params), vp, vp, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "nph_result_records_read": (i64, [vp]), "nph_result_index_seeks": (i64, [vp]),
         "nph_read_gt": (C.c_int, [cp, vp, i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),

@@ -6,6 +6,7 @@
 
 #include "../../include/nimpress_host.h"
 #include "driver.hpp"
+#include "fast_inflate.hpp"
 #include "stats.hpp"
 
 using namespace nph;
@@ -201,6 +202,11 @@ int nph_read_gt(const char *genotype_path, uint8_t *out, int64_t row_bytes, int6
         g_err = e.what();
         return NPH_EINPUT;
     }
+}
+
+int nph_fast_inflate(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len) {
+    static thread_local FastInflateTables t;
+    return fast_inflate(in, (size_t)in_len, out, (size_t)out_len, t) ? 1 : 0;
 }
 
 double nph_dbinom(int64_t x, int64_t n, double p) { return dbinom(x, n, p); }

@@ -1,5 +1,6 @@
 #include "variant_source.hpp"
 #include "region_index.hpp"
+#include "fast_inflate.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -76,7 +77,7 @@ private:
                 if (bsize < 12 + xlen + 8) err = "BGZF: bad block size";
                 else {
                     const size_t rest = bsize - 18;                 // remaining extra fields + deflate data + CRC32 + ISIZE
-                    if (s.in.size() < rest) s.in.resize(std::max<size_t>(rest, 1 << 16));
+                    if (s.in.size() < rest + 16) s.in.resize(std::max<size_t>(rest + 16, (1 << 16) + 64));   // + the decoder's read-ahead
                     if (fread(s.in.data(), 1, rest, fp_) != rest) err = "BGZF: truncated block";
                     else {
                         const size_t skip = xlen - 6;               // extra subfields beyond BC
@@ -101,6 +102,9 @@ private:
         z_stream zs;
         memset(&zs, 0, sizeof zs);
         inflateInit2(&zs, -15);
+        std::unique_ptr<FastInflateTables> tabs(new FastInflateTables);
+        const char *zo = getenv("NIMPRESS_ZLIB_ONLY");
+        const bool zlib_only = zo && *zo && *zo != '0';
         for (;;) {
             Slot *s = nullptr;
             {
@@ -117,15 +121,23 @@ private:
                 }
             }
             const size_t off = s->out_len, tail = 8;
-            uint32_t isize;
+            uint32_t isize, want_crc;
+            memcpy(&want_crc, s->in.data() + s->in_len - 8, 4);
             memcpy(&isize, s->in.data() + s->in_len - 4, 4);
-            if (s->out.size() < isize) s->out.resize(std::max<size_t>(isize, 1 << 16));
-            inflateReset(&zs);
-            zs.next_in = s->in.data() + off; zs.avail_in = (uInt)(s->in_len - off - tail);
-            zs.next_out = s->out.data(); zs.avail_out = (uInt)s->out.size();
-            const int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+            if (s->out.size() < (size_t)isize + 16) s->out.resize(std::max<size_t>((size_t)isize + 16, (1 << 16) + 16));
             std::string err;
-            if (rc != Z_STREAM_END || zs.total_out != isize) err = "BGZF: corrupt deflate data";
+            // this engine's own decoder first (fast_inflate.hpp); zlib when it declines or the CRC disagrees
+            bool ok = !zlib_only && isize && s->in_len >= off + tail &&
+                      fast_inflate(s->in.data() + off, s->in_len - off - tail, s->out.data(), isize, *tabs) &&
+                      (uint32_t)crc32(0L, s->out.data(), isize) == want_crc;
+            if (!ok && isize) {
+                inflateReset(&zs);
+                zs.next_in = s->in.data() + off; zs.avail_in = (uInt)(s->in_len - off - tail);
+                zs.next_out = s->out.data(); zs.avail_out = (uInt)s->out.size();
+                const int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.total_out != isize) err = "BGZF: corrupt deflate data";
+                else if ((uint32_t)crc32(0L, s->out.data(), isize) != want_crc) err = "BGZF: CRC32 mismatch";
+            }
             {
                 std::lock_guard<std::mutex> g(m_);
                 s->out_len = isize; s->error = err; s->state = DONE;

@@ -377,3 +377,66 @@ def test_index_reader_long_spans_and_edges(api, tmp_path, monkeypatch):
         assert rc == 0 and np.array_equal(kind, k2) and np.array_equal(ea, e2), (f, kind, k2)
         assert seeks > 0 and nrec < len(recs) // 3
         assert list(kind[:7]) == [2, 2, 0, 0, 0, 2, 0] and kind[9] == 2 and kind[10] == 2      # 0 = matched, 2 = absent
+
+
+def test_fast_inflate_equals_zlib(api):
+    """The reader's own DEFLATE decoder against zlib: stored, fixed and dynamic blocks, every zlib strategy, run-heavy /
+    random / periodic data, lengths around the word-copy edges; then flipped bits -- whatever it accepts wrongly is what
+    the CRC32 check behind it is for (it must never crash or write out of bounds)."""
+    import zlib
+    L = api.load_host_library()
+    rng = np.random.default_rng(1)
+
+    def run(comp, n):
+        inb = np.frombuffer(comp + b"\0" * 16, dtype=np.uint8).copy()
+        out = np.full(n + 16, 0xAA, np.uint8)
+        ok = L.nph_fast_inflate(inb.ctypes.data, len(comp), out.ctypes.data, n)
+        assert np.all(out[n + 8:] == 0xAA)                       # never beyond the documented slack
+        return ok, out[:n].tobytes()
+
+    for n in (0, 1, 2, 7, 8, 9, 15, 16, 17, 100, 1000, 65280):
+        datas = [bytes(rng.integers(0, 256, n, dtype=np.uint8)), bytes(rng.integers(0, 3, n, dtype=np.uint8) * 2),
+                 (b"\x02\x02\x02\x04" * (n // 4 + 1))[:n], bytes(np.repeat(rng.integers(0, 256, max(n // 50, 1), dtype=np.uint8), 50)[:n]),
+                 b"a" * n, bytes((np.arange(n) % 251).astype(np.uint8)), (b"abcdefg" * (n // 7 + 1))[:n]]
+        for d in datas:
+            for level in (0, 1, 6, 9):
+                for strat in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+                    co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strat)
+                    comp = co.compress(d) + co.flush()
+                    ok, got = run(comp, len(d))
+                    assert ok == 1 and got == d, (n, level, strat)
+                    assert run(comp, len(d) + 1)[0] == 0 and (len(d) == 0 or run(comp, len(d) - 1)[0] == 0)   # wrong expected size
+    d = bytes(rng.integers(0, 4, 30000, dtype=np.uint8))
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(d) + co.flush()
+    for trial in range(400):
+        c = bytearray(comp)
+        i = int(rng.integers(0, len(c)))
+        c[i] ^= 1 << int(rng.integers(0, 8))
+        run(bytes(c), len(d))
+    assert run(comp[:len(comp) // 2], len(d))[0] == 0               # truncated
+
+
+def test_bgzf_pool_decoders_agree_and_crc_is_checked(api, tmp_path, monkeypatch):
+    """Pool with this engine's decoder == pool with zlib only == sequential zlib; a flipped payload bit in a block is
+    reported (CRC32), not scored."""
+    rng = np.random.default_rng(5)
+    d = make_dataset(str(tmp_path), rng, n=300, V=400)
+    monkeypatch.setenv("NIMPRESS_THREADS", "4")
+    a = read_gt(api, d["bcf"], 1024)
+    monkeypatch.setenv("NIMPRESS_ZLIB_ONLY", "1")
+    b = read_gt(api, d["bcf"], 1024)
+    monkeypatch.setenv("NIMPRESS_THREADS", "1")
+    c = read_gt(api, d["bcf"], 1024)
+    assert a[1:] == b[1:] == c[1:] and np.array_equal(a[0], b[0]) and np.array_equal(a[0], c[0])
+    monkeypatch.delenv("NIMPRESS_ZLIB_ONLY")
+    monkeypatch.setenv("NIMPRESS_THREADS", "4")
+    raw = bytearray(open(d["bcf"], "rb").read())
+    raw[len(raw) // 2] ^= 0x10
+    bad = tmp_path / "bad.bcf"
+    bad.write_bytes(bytes(raw))
+    L = api.load_host_library()
+    out = np.zeros((4096, 1024), np.uint8)
+    nrec, ns, w, pl = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    rc = L.nph_read_gt(os.fsencode(str(bad)), out.ctypes.data, 1024, 4096, C.byref(nrec), C.byref(ns), C.byref(w), C.byref(pl))
+    assert rc == -3 and b"BGZF" in L.nph_last_error()
