@@ -250,10 +250,6 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
         if (!any) continue;
         records_matched++;
         if (!need_gt) continue;                                     // FILTER-failed: never decoded (:553-558)
-        if (!rec.has_gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
-        vcf.load_gt(rec);
-        if (rec.ploidy > ploidy || rec.gt_width > gt_width)
-            throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
         if (slab_base + staged >= slab_cap) {                       // slab full: score its rows, start over
             if (S > 1) throw SlabOverflow();
             score_round(false);
@@ -265,8 +261,15 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             stage = (uint8_t *)ptr; staged = 0;
         }
         uint8_t *dst = stage + staged * stride;
-        if (rec.gt_width == gt_width && rec.ploidy == ploidy) memcpy(dst, rec.gt, (size_t)n * ploidy * gt_width);
-        else convert_gt(rec, n, gt_width, ploidy, dst);
+        // BCF with the context's layout: the GT payload goes from the inflated blocks straight into the pinned row
+        const bool direct = vcf.load_gt_into(rec, dst, gt_width, ploidy);
+        if (!rec.has_gt || !rec.gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
+        if (!direct) {
+            if (rec.ploidy > ploidy || rec.gt_width > gt_width)
+                throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
+            if (rec.gt_width == gt_width && rec.ploidy == ploidy) memcpy(dst, rec.gt, (size_t)n * ploidy * gt_width);
+            else convert_gt(rec, n, gt_width, ploidy, dst);
+        }
         for (int k = 0; k < S; k++) for (int64_t i : ps[k].M->match_last()) if (ps[k].M->kind[i] == NPC_KIND_GT) ps[k].slab_row[i] = slab_base + staged;
         staged++;
         if (staged == block_rows) flush_stage();

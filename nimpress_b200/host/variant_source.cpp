@@ -278,6 +278,15 @@ size_t InflateStream::read(void *dst, size_t n) {
 
 bool InflateStream::read_exact(void *dst, size_t n) { return read(dst, n) == n; }
 
+bool InflateStream::skip(size_t n) {                  // advance without copying
+    while (n) {
+        if (out_pos_ == out_len_ && !fill()) return false;
+        const size_t k = std::min(n, out_len_ - out_pos_);
+        out_pos_ += k; n -= k;
+    }
+    return true;
+}
+
 bool InflateStream::peek(void *dst, size_t n) {
     if (out_pos_ == out_len_ && !fill()) return false;
     if (out_len_ - out_pos_ < n) return false;        // only used at the very start of the stream
@@ -511,19 +520,24 @@ public:
         return true;
     }
     InflateStream *stream() override { return in_.get(); }
+    void after_seek() override { indiv_left_ = 0; gt_done_ = true; }
     int contig_rank(const VariantRecord &rec) const override { return rec.contig_id; }       // CSI reference ids = header contig ids
     int contig_rank(const std::string &name) const override {
         for (size_t i = 0; i < contigs_.size(); i++) if (contigs_[i] == name) return (int)i;
         return -1;
     }
     bool next_raw(VariantRecord &rec) override {
+        // the per-sample block of the previous record is consumed only on demand (load_gt / load_gt_into):
+        // a record no score row matches costs no copy of its genotypes at all
+        if (indiv_left_ && !in_->skip(indiv_left_)) throw InputError("BCF: truncated record");
+        indiv_left_ = 0;
         uint32_t lens[2];
         size_t got = in_->read(lens, 8);
         if (got == 0) return false;
         if (got != 8) throw InputError("BCF: truncated record header");
-        shared_.resize(lens[0]); indiv_.resize(lens[1]);
-        if (!in_->read_exact(shared_.data(), lens[0]) || !in_->read_exact(indiv_.data(), lens[1]))
-            throw InputError("BCF: truncated record");
+        shared_.resize(lens[0]);
+        if (!in_->read_exact(shared_.data(), lens[0])) throw InputError("BCF: truncated record");
+        indiv_left_ = lens[1];
         if (lens[0] < 24) throw InputError("BCF: shared block too short");
         const uint8_t *p = shared_.data(), *e = p + shared_.size();
         int32_t chrom, pos0, rlen; uint32_t nai, nfs;
@@ -553,25 +567,85 @@ public:
                 rec.filter += dict_name(id);
             }
         }
-        // FORMAT fields: find GT
+        // FORMAT fields are looked at when the genotypes are asked for
+        rec.has_gt = n_fmt > 0 && n_sample > 0; rec.gt = nullptr; rec.ploidy = 0; rec.gt_width = 1;
+        n_fmt_ = n_fmt; n_sample_ = n_sample; gt_done_ = false;
+        return true;
+    }
+    // whole per-sample block into indiv_, GT located inside it
+    void load_gt(VariantRecord &rec) override {
+        if (gt_done_) return;
+        gt_done_ = true;
+        indiv_.resize(indiv_left_);
+        if (!in_->read_exact(indiv_.data(), indiv_left_)) throw InputError("BCF: truncated record");
+        indiv_left_ = 0;
         rec.has_gt = false; rec.gt = nullptr; rec.ploidy = 0; rec.gt_width = 1;
         const uint8_t *q = indiv_.data(), *qe = q + indiv_.size();
-        for (uint32_t f = 0; f < n_fmt && q < qe; f++) {
+        for (uint32_t f = 0; f < n_fmt_ && q < qe; f++) {
             int kt; uint32_t kl;
             read_desc(q, qe, kt, kl);
             int32_t key = read_int(q, qe, kt);
             int type; uint32_t len;
             read_desc(q, qe, type, len);
             const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
-            const size_t bytes = (size_t)n_sample * len * esz;
+            const size_t bytes = (size_t)n_sample_ * len * esz;
             if (q + bytes > qe) throw InputError("BCF: FORMAT field overruns the record");
             if (key == gt_key_ && (type == 1 || type == 2 || type == 3)) {
-                if ((int64_t)n_sample != n_samples()) throw InputError("BCF: record sample count differs from header");
+                if ((int64_t)n_sample_ != n_samples()) throw InputError("BCF: record sample count differs from header");
                 rec.has_gt = true; rec.gt = q; rec.gt_width = (int)esz; rec.ploidy = (int)len;
             }
             q += bytes;
         }
-        return true;
+    }
+    // The GT payload straight from the inflated blocks into dst (the pinned staging row) when its layout is the wanted
+    // one: the only copy the genotypes make on the host.  The field headers in front of it are a few bytes each.
+    bool load_gt_into(VariantRecord &rec, uint8_t *dst, int want_width, int want_ploidy) override {
+        if (gt_done_) return false;
+        uint8_t hdr[16];
+        size_t left = indiv_left_;
+        for (uint32_t f = 0; f < n_fmt_ && left; f++) {
+            // key (typed int) and the type descriptor: read what a short header needs, byte by byte where lengths chain
+            size_t h = 0;
+            auto need = [&](size_t n) { if (left < n || !in_->read_exact(hdr + h, n)) throw InputError("BCF: truncated record"); h += n; left -= n; };
+            need(1);
+            const int kt = hdr[0] & 0xF;
+            if ((hdr[0] >> 4) != 1 || (kt != 1 && kt != 2 && kt != 3)) { finish_general(rec, hdr, h, left); return false; }
+            const size_t ksz = kt == 1 ? 1 : kt == 2 ? 2 : 4;
+            need(ksz);
+            const uint8_t *kp = hdr + 1;
+            const int32_t key = read_int(kp, hdr + h, kt);
+            const size_t d0 = h;
+            need(1);
+            int type = hdr[d0] & 0xF; uint32_t len = hdr[d0] >> 4;
+            if (len == 15) {                                                // long vector: the length follows as a typed int
+                need(1);
+                const int lt = hdr[d0 + 1] & 0xF;
+                if ((hdr[d0 + 1] >> 4) != 1 || (lt != 1 && lt != 2 && lt != 3)) { finish_general(rec, hdr, h, left); return false; }
+                need(lt == 1 ? 1 : lt == 2 ? 2 : 4);
+                const uint8_t *lp = hdr + d0 + 2;
+                len = (uint32_t)read_int(lp, hdr + h, lt);
+            }
+            const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
+            const size_t bytes = (size_t)n_sample_ * len * esz;
+            if (bytes > left) throw InputError("BCF: FORMAT field overruns the record");
+            if (key == gt_key_ && (type == 1 || type == 2 || type == 3)) {
+                if ((int64_t)n_sample_ != n_samples()) throw InputError("BCF: record sample count differs from header");
+                gt_done_ = true;
+                rec.has_gt = true; rec.gt_width = (int)esz; rec.ploidy = (int)len;
+                const bool direct = (int)esz == want_width && (int)len == want_ploidy;
+                uint8_t *to = dst;
+                if (!direct) { indiv_.resize(bytes); to = indiv_.data(); }
+                if (!in_->read_exact(to, bytes)) throw InputError("BCF: truncated record");
+                rec.gt = to;
+                indiv_left_ = left - bytes;                                 // later fields: skipped when the next record is read
+                return direct;
+            }
+            if (!in_->skip(bytes)) throw InputError("BCF: truncated record");
+            left -= bytes;
+        }
+        indiv_left_ = left; gt_done_ = true;
+        rec.has_gt = false; rec.gt = nullptr;
+        return false;
     }
 private:
     static void read_desc(const uint8_t *&p, const uint8_t *e, int &type, uint32_t &len) {
@@ -670,7 +744,32 @@ private:
     std::unique_ptr<InflateStream> in_;
     std::vector<std::string> contigs_, dict_;
     size_t dict_next_ = 0, contig_next_ = 0;
+    // an unusual field header inside load_gt_into: put the bytes read so far back in front and take the general path
+    void finish_general(VariantRecord &rec, const uint8_t *hdr, size_t h, size_t left) {
+        indiv_.resize(h + left);
+        memcpy(indiv_.data(), hdr, h);
+        if (!in_->read_exact(indiv_.data() + h, left)) throw InputError("BCF: truncated record");
+        // fields already skipped are gone; the general parser starts at this field
+        indiv_left_ = 0; gt_done_ = true;
+        rec.has_gt = false; rec.gt = nullptr; rec.ploidy = 0; rec.gt_width = 1;
+        const uint8_t *q = indiv_.data(), *qe = q + indiv_.size();
+        while (q < qe) {
+            int kt; uint32_t kl;
+            read_desc(q, qe, kt, kl);
+            int32_t key = read_int(q, qe, kt);
+            int type; uint32_t len;
+            read_desc(q, qe, type, len);
+            const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
+            const size_t bytes = (size_t)n_sample_ * len * esz;
+            if (q + bytes > qe) throw InputError("BCF: FORMAT field overruns the record");
+            if (key == gt_key_ && (type == 1 || type == 2 || type == 3)) { rec.has_gt = true; rec.gt = q; rec.gt_width = (int)esz; rec.ploidy = (int)len; }
+            q += bytes;
+        }
+    }
     int32_t gt_key_ = -1;
+    size_t indiv_left_ = 0;
+    uint32_t n_fmt_ = 0, n_sample_ = 0;
+    bool gt_done_ = true;
     std::vector<uint8_t> shared_, indiv_;
 };
 
@@ -731,7 +830,7 @@ bool VariantSource::next(VariantRecord &rec) {
             const Region &R = regions_[region_];
             const uint64_t v = index_->query_start(R.ref, R.beg0, R.end0);
             if (v == RegionIndex::NONE) { region_++; continue; }
-            if (v > in->tell_virtual()) { in->seek_virtual(v); seeks_++; }
+            if (v > in->tell_virtual()) { in->seek_virtual(v); after_seek(); seeks_++; }
             positioned_ = true;
         }
         if (!next_raw(rec)) return false;
@@ -747,7 +846,7 @@ bool VariantSource::next(VariantRecord &rec) {
             const Region &N = regions_[region_];
             const uint64_t v = index_->query_start(N.ref, N.beg0, N.end0);
             if (v == RegionIndex::NONE) { positioned_ = false; break; }
-            if (v > in->tell_virtual()) { in->seek_virtual(v); seeks_++; positioned_ = true; break; }   // this record lies before the next region's first
+            if (v > in->tell_virtual()) { in->seek_virtual(v); after_seek(); seeks_++; positioned_ = true; break; }   // this record lies before the next region's first
             positioned_ = true;                                       // no jump: the same record may belong to the next region
         }
         if (!positioned_) continue;

@@ -39,6 +39,7 @@ public:
     int64_t file_size() const { return file_size_; }
     size_t read(void *dst, size_t n);                 // up to n bytes; 0 at end of stream
     bool read_exact(void *dst, size_t n);
+    bool skip(size_t n);                              // false: the stream ended first
     bool getline(std::string &line);                  // strips \n and a preceding \r
     bool peek(void *dst, size_t n);                   // look ahead without consuming (n <= 64)
     int threads() const { return threads_; }
@@ -88,6 +89,13 @@ public:
     // Fills rec.gt / ploidy / gt_width of the record next() just returned (rec.has_gt tells whether
     // it has a GT field).  Text VCF parses its genotype columns only here; BCF has them already.
     virtual void load_gt(VariantRecord &) {}
+    // The same, but when the record's GT layout is (want_width, want_ploidy) the payload is written to dst and rec.gt = dst
+    // (true); otherwise as load_gt (false: rec.gt points into the reader's buffer, the caller converts or restarts).
+    virtual bool load_gt_into(VariantRecord &rec, uint8_t *dst, int want_width, int want_ploidy) {
+        (void)dst; (void)want_width; (void)want_ploidy;
+        load_gt(rec);
+        return false;
+    }
     const std::vector<std::string> &samples() const { return samples_; }
     int64_t n_samples() const { return (int64_t)samples_.size(); }
 protected:
@@ -95,6 +103,7 @@ protected:
     virtual InflateStream *stream() = 0;
     virtual int contig_rank(const VariantRecord &rec) const = 0;      // position of the record's contig in the index's order, -1 unknown
     virtual int contig_rank(const std::string &name) const = 0;
+    virtual void after_seek() {}                                      // forget whatever of the previous record was still unread
     virtual bool index_names_contigs() const { return true; }         // text VCF: the index must carry the contig names
     std::vector<std::string> samples_;
     std::unique_ptr<RegionIndex> index_;
