@@ -176,9 +176,9 @@ bool InflateStream::open(const std::string &path, bool seekable) {
     compressed_ = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     const bool bgzf = got == 18 && compressed_ && (magic[3] & 4) && magic[12] == 'B' && magic[13] == 'C';
     bgzf_ = bgzf;
-    block_mode_ = seekable && bgzf;
     int want = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
     if (const char *e = getenv("NIMPRESS_THREADS")) if (*e) want = std::max(1, atoi(e));
+    block_mode_ = bgzf && (seekable || want == 1);     // one thread: block by block with this engine's decoder
     if (bgzf && want > 1 && !block_mode_) {
         threads_ = want;
         pool_ = std::make_unique<BgzfPool>(fp_, want);
@@ -212,24 +212,38 @@ bool InflateStream::fill() {
     }
     if (block_mode_) {                                // exactly one BGZF block per fill: the position stays a virtual offset
         for (;;) {
-            block_coff_ = in_file_off_ - zs_.avail_in;
-            zs_.next_out = out_.data();
-            zs_.avail_out = (uInt)out_.size();
-            int rc = Z_OK;
-            while (rc != Z_STREAM_END) {
-                if (zs_.avail_in == 0) {
-                    zs_.next_in = in_.data();
-                    zs_.avail_in = (uInt)fread(in_.data(), 1, in_.size(), fp_);
-                    in_file_off_ += zs_.avail_in;
-                    if (zs_.avail_in == 0) { eof_ = true; return false; }
-                }
-                rc = inflate(&zs_, Z_NO_FLUSH);
-                if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR)
-                    throw InputError(std::string("zlib: corrupt compressed stream: ") + (zs_.msg ? zs_.msg : "?"));
+            block_coff_ = in_file_off_;
+            uint8_t hdr[18];
+            const size_t got = fread(hdr, 1, 18, fp_);
+            if (got == 0) { eof_ = true; return false; }
+            if (got != 18 || hdr[0] != 0x1f || hdr[1] != 0x8b || !(hdr[3] & 4) || hdr[12] != 'B' || hdr[13] != 'C')
+                throw InputError("BGZF: malformed block header");
+            const size_t bsize = (size_t)(hdr[16] | (hdr[17] << 8)) + 1, xlen = (size_t)(hdr[10] | (hdr[11] << 8));
+            if (bsize < 12 + xlen + 8 || xlen < 6) throw InputError("BGZF: bad block size");
+            const size_t rest = bsize - 18, off = xlen - 6;         // remaining extra fields, deflate data, CRC32, ISIZE
+            if (in_.size() < rest + 16) in_.resize(rest + 16);
+            if (fread(in_.data(), 1, rest, fp_) != rest) throw InputError("BGZF: truncated block");
+            in_file_off_ += bsize;
+            uint32_t want_crc, isize;
+            memcpy(&want_crc, in_.data() + rest - 8, 4);
+            memcpy(&isize, in_.data() + rest - 4, 4);
+            if (isize == 0) continue;                               // empty blocks (the EOF marker) are skipped
+            if (out_.size() < (size_t)isize + 16) out_.resize((size_t)isize + 16);
+            if (!tabs_) tabs_.reset(new FastInflateTables);
+            const char *zo = getenv("NIMPRESS_ZLIB_ONLY");
+            bool ok = !(zo && *zo && *zo != '0') && rest >= off + 8 &&
+                      fast_inflate(in_.data() + off, rest - off - 8, out_.data(), isize, *tabs_) &&
+                      (uint32_t)crc32(0L, out_.data(), isize) == want_crc;
+            if (!ok) {                                              // zlib, raw deflate
+                if (inflateReset2(&zs_, -15) != Z_OK) throw InputError("zlib: inflateReset failed");
+                zs_.next_in = in_.data() + off; zs_.avail_in = (uInt)(rest - off - 8);
+                zs_.next_out = out_.data(); zs_.avail_out = (uInt)out_.size();
+                const int rc = inflate(&zs_, Z_FINISH);
+                if (rc != Z_STREAM_END || zs_.total_out != isize) throw InputError("BGZF: corrupt deflate data");
+                if ((uint32_t)crc32(0L, out_.data(), isize) != want_crc) throw InputError("BGZF: CRC32 mismatch");
             }
-            if (inflateReset(&zs_) != Z_OK) throw InputError("zlib: inflateReset failed");
-            out_len_ = out_.size() - zs_.avail_out;
-            if (out_len_ > 0) return true;            // empty blocks (the EOF marker) are skipped
+            out_len_ = isize;
+            return true;
         }
     }
     zs_.next_out = out_.data();
@@ -256,8 +270,6 @@ void InflateStream::seek_virtual(uint64_t voff) {
     const uint64_t coff = voff >> 16;
     if (fseek(fp_, (long)coff, SEEK_SET) != 0) throw InputError("index points outside the file");
     in_file_off_ = coff;
-    zs_.avail_in = 0;
-    if (inflateReset(&zs_) != Z_OK) throw InputError("zlib: inflateReset failed");
     eof_ = false;
     out_pos_ = out_len_ = 0;
     if (!fill()) return;                              // at or past the end: the next read reports end of stream

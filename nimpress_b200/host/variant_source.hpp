@@ -19,7 +19,8 @@
 
 namespace nph {
 
-class BgzfPool;                                      // multi-threaded BGZF block inflater (variant_source.cpp)
+class BgzfPool;
+struct FastInflateTables;                                      // multi-threaded BGZF block inflater (variant_source.cpp)
 
 // Byte stream over a plain / gzip / BGZF file.  BGZF (concatenated <= 64 KiB gzip members with a
 // `BC` extra field giving each member's size) is inflated by a pool of worker threads, blocks
@@ -54,6 +55,7 @@ private:
     size_t out_pos_ = 0, out_len_ = 0;
     const uint8_t *cur() const { return pool_ ? pool_data_ : out_.data(); }
     std::unique_ptr<BgzfPool> pool_;
+    std::unique_ptr<FastInflateTables> tabs_;
     const uint8_t *pool_data_ = nullptr;
     int threads_ = 1;
 };
