@@ -168,9 +168,14 @@ bool fast_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len
                 if (e_kind(e) == K_LIT) {
                     if (op >= out_end) return false;
                     *op++ = (uint8_t)e_payload(e);
-                    // a second literal from the same refill when it is there (runs of literals are common)
-                    uint32_t e2 = t.lit[bb & ((1u << LIT_P) - 1u)];
-                    if (e_kind(e2) == K_LIT && op < out_end) { TAKE(e_bits(e2)); *op++ = (uint8_t)e_payload(e2); }
+                    // more literals from the same refill while they are there (short runs of literals are common):
+                    // 56 bits hold at least three further primary-table codes
+                    for (int k = 0; k < 3; k++) {
+                        const uint32_t e2 = t.lit[bb & ((1u << LIT_P) - 1u)];
+                        if (e_kind(e2) != K_LIT || op >= out_end) break;
+                        TAKE(e_bits(e2));
+                        *op++ = (uint8_t)e_payload(e2);
+                    }
                     continue;
                 }
                 if (e_kind(e) == K_EOB) break;
@@ -192,8 +197,14 @@ bool fast_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len
                 uint8_t *const stop = op + len;
                 if (dist >= 8) {                                        // word copies; the last one may run up to 7 bytes past `stop` (caller's slack)
                     do { store64(op, load64(src)); op += 8; src += 8; } while (op < stop);
-                } else if (dist == 1) {
-                    memset(op, *src, len);
+                } else if (dist == 1) {                                 // a run of one byte
+                    const uint64_t v = 0x0101010101010101ull * *src;
+                    do { store64(op, v); op += 8; } while (op < stop);
+                } else if (dist == 2 || dist == 4) {                    // period 2 or 4: one replicated word (GT pairs repeat at distance 2)
+                    uint64_t v;
+                    if (dist == 2) { uint16_t h; memcpy(&h, src, 2); v = 0x0001000100010001ull * h; }
+                    else { uint32_t w; memcpy(&w, src, 4); v = 0x0000000100000001ull * w; }
+                    do { store64(op, v); op += 8; } while (op < stop);
                 } else {
                     // period < 8: copy bytes until the gap back to the source is a multiple of the period >= 8, then words
                     const uint32_t m = ((8 + dist - 1) / dist) * dist;
