@@ -440,3 +440,27 @@ def test_bgzf_pool_decoders_agree_and_crc_is_checked(api, tmp_path, monkeypatch)
     nrec, ns, w, pl = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
     rc = L.nph_read_gt(os.fsencode(str(bad)), out.ctypes.data, 1024, 4096, C.byref(nrec), C.byref(ns), C.byref(w), C.byref(pl))
     assert rc == -3 and b"BGZF" in L.nph_last_error()
+
+
+def test_broken_index_files_are_ignored(api, tmp_path, monkeypatch):
+    """A truncated, empty or garbage .tbi / .csi must not crash the reader or change what is matched: it does not
+    parse, so the file is streamed."""
+    import util_bcf
+    monkeypatch.setattr(util_bcf, "INDEX_BLOCK", 4000)
+    monkeypatch.setenv("NIMPRESS_FORCE_INDEX", "1")
+    rng = np.random.default_rng(12)
+    d = make_dataset(str(tmp_path), rng, n=8, V=300, index=True, spread=300)
+    want = plan(api, d["score"], d["bcf"])
+    for f, ext in ((d["vcf"], ".tbi"), (d["bcf"], ".csi")):
+        import gzip
+        raw = gzip.decompress(open(f + ext, "rb").read())
+        for cut in (0, 3, 4, 11, 40, len(raw) // 2, len(raw) - 1):
+            open(f + ext, "wb").write(util_bcf.bgzf_compress(raw[:cut]))
+            k, e, nrec, seeks = plan_indexed(api, d["score"], f)
+            assert seeks == 0 and nrec == len(d["records"]) and np.array_equal(k, want[1]) and np.array_equal(e, want[2]), (ext, cut)
+        open(f + ext, "wb").write(bytes(rng.integers(0, 256, 500, dtype=np.uint8)))          # not even gzip
+        k, e, nrec, seeks = plan_indexed(api, d["score"], f)
+        assert seeks == 0 and np.array_equal(k, want[1])
+        open(f + ext, "wb").write(util_bcf.bgzf_compress(raw))                               # intact again
+        k, e, _, _ = plan_indexed(api, d["score"], f)
+        assert np.array_equal(k, want[1]) and np.array_equal(e, want[2])
