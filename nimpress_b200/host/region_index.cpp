@@ -1,5 +1,7 @@
 #include "region_index.hpp"
 
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -23,6 +25,8 @@ struct Cur {
 std::unique_ptr<RegionIndex> RegionIndex::load(const std::string &data_path) {
     for (int k = 0; k < 2; k++) {
         const std::string path = data_path + (k == 0 ? ".tbi" : ".csi");
+        struct stat si, sd;                                         // an index older than its data file is not trusted (htslib warns; here: stream)
+        if (stat(path.c_str(), &si) != 0 || stat(data_path.c_str(), &sd) != 0 || si.st_mtime < sd.st_mtime) continue;
         InflateStream s;
         if (!s.open(path)) continue;
         std::vector<uint8_t> d;

@@ -464,3 +464,20 @@ def test_broken_index_files_are_ignored(api, tmp_path, monkeypatch):
         open(f + ext, "wb").write(util_bcf.bgzf_compress(raw))                               # intact again
         k, e, _, _ = plan_indexed(api, d["score"], f)
         assert np.array_equal(k, want[1]) and np.array_equal(e, want[2])
+
+
+def test_stale_index_is_not_used(api, tmp_path, monkeypatch):
+    """An index older than its data file (the file was rewritten since) is ignored: the file is streamed."""
+    import util_bcf
+    monkeypatch.setattr(util_bcf, "INDEX_BLOCK", 4000)
+    monkeypatch.setenv("NIMPRESS_FORCE_INDEX", "1")
+    rng = np.random.default_rng(13)
+    d = make_dataset(str(tmp_path), rng, n=8, V=600, index=True, spread=300)
+    lines = open(d["score"]).read().split("\n")
+    sparse = tmp_path / "s.score"
+    sparse.write_text("\n".join(lines[:5] + [e for i, e in enumerate(lines[5:]) if e and i % 40 == 0]) + "\n")
+    assert plan_indexed(api, str(sparse), d["bcf"])[3] > 0
+    st = os.stat(d["bcf"] + ".csi")
+    os.utime(d["bcf"], (st.st_atime + 100, st.st_mtime + 100))           # data "modified" after the index was made
+    k, e, nrec, seeks = plan_indexed(api, str(sparse), d["bcf"])
+    assert seeks == 0 and nrec == len(d["records"])
