@@ -32,6 +32,16 @@
  * width-specific sentinels missing = MIN, vector_end = MIN+1 (both ignored, and a vector_end
  * ends the sample), rows `row_stride` bytes apart (row_stride % 16 == 0).
  */
+/*
+ * Environment (diagnostics and tests; none is needed in normal use):
+ *   NPC_FUSED=0              two-kernel sequence instead of the fused tile kernel
+ *   NPC_EXACT=1              exact-order mode for every context (as npc_set_exact_order)
+ *   NPC_TILE_K / _SR / _SC / _L / _A / _GR   launch shape of the fused tile kernel (chunks per thread, raw stages,
+ *                            index tiles, lag, decider warps, row groups)
+ *   NPC_MULTI=0 | 1          npc_score_resident_multi: never / always the tensor-core contraction (default: >= 3 definitions)
+ *   NPC_MULTI_PARTS=<n>      split of a tile's entry range over work units in the contraction (default: chosen from the tile count)
+ *   NPC_TIMING=1             phase wall times of npc_score_resident_multi on stderr
+ */
 #ifndef NIMPRESS_CUDA_H
 #define NIMPRESS_CUDA_H
 #include <stdint.h>
