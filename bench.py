@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--brief", action="store_true", help="print value / roofline / shape only (tuning sweeps)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config to time as the headline (default 3: the genome-wide shard)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short timings of configs 2, 4 and 5 (N = 1 only)")
     return ap.parse_args()
 
 
@@ -199,13 +202,98 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+# ---- the other BASELINE configs, timed briefly (N = 1) ---------------------------------------------
+
+def time_resident(nb, torch, dev, n, V, miss_lo, miss_hi, steps=20, warmup=5, policy=None):
+    """Kernel-only rate of one npc_score_block_device call over a resident V x n slab (CUDA events around the
+    call, L2 flushed by a 512 MB write before every timed call: these slabs are near or below the L2 size)."""
+    stride = -(-2 * n // 128) * 128
+    af, beta, ref_is_ea, af_thr, _, alt = cohort_params(0, V)
+    rng = np.random.default_rng([SEED, 99])
+    miss_thr = (rng.uniform(miss_lo, miss_hi, size=V) * (1 << 24)).astype(np.uint32)
+    rows = make_rows(nb.ROW_DTYPE, V, af, beta, ref_is_ea)
+    eng = nb.Engine(n, max_rows_per_block=V, n_slots=0, device=dev.index)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_policy(**(policy or {}))
+    gt = torch.empty((V, stride), dtype=torch.uint8, device=dev)
+    eng.synth_fill_device(gt, stride, 0, V, SEED, torch.from_numpy(af_thr.view(np.int32)).to(dev),
+                          torch.from_numpy(miss_thr.view(np.int32)).to(dev), torch.from_numpy(alt).to(dev))
+    d_rows = torch.from_numpy(rows.view(np.uint8).reshape(V, -1)).to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    ms = []
+    for i in range(warmup + steps):
+        eng.reset()
+        flush.fill_(i & 255)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.score_block_device(gt, stride, V, d_rows, n_rows=V)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    out = eng.finish(want_loci=True)
+    shape = eng.kernel_shape
+    eng.close()
+    t = float(np.median(ms)) * 1e-3
+    return t, out, shape, 2.0 * n * V + 32.0 * V + 16.0 * n
+
+
+def extra_configs(nb, torch, dev, peak):
+    """configs[1], [3] and [4] of BASELINE.json, a few launches each, so that the driver's line carries them."""
+    ex = {}
+    t, out, shape, alg = time_resident(nb, torch, dev, 100_000, 697, 0.005, 0.005)
+    ex["config2"] = {"workload": "697 loci (the wood height score's size) x 100,000 samples, 0.5% missing, one launch",
+                     "value": 100_000 * 697 / t, "unit": "genotypes/s", "launch_us": t * 1e6, "roofline_frac": alg / t / 1e9 / peak,
+                     "grid": shape["grid"], "row_groups": shape.get("row_groups"), "l2": "flushed before every timed launch"}
+    t, out, shape, alg = time_resident(nb, torch, dev, 50_000, 10_000, 0.0, 0.10)
+    ex["config5"] = {"workload": "10,000 loci x 50,000 samples, per-locus missing rate U(0, 0.10), --maxmis 0.05 (default policies), one launch",
+                     "value": 50_000 * 10_000 / t, "unit": "genotypes/s", "launch_us": t * 1e6, "roofline_frac": alg / t / 1e9 / peak,
+                     "loci_over_maxmis": int((out["loci"]["klass"] == 4).sum()), "grid": shape["grid"], "row_groups": shape.get("row_groups"),
+                     "l2": "flushed before every timed launch"}
+    # config 4: 18 score definitions over one resident slab in one call (tensor-core contraction)
+    n, V, S = 200_000, 20_000, 18
+    stride = -(-2 * n // 128) * 128
+    af, beta, ref_is_ea, af_thr, miss_thr, alt = cohort_params(0, V)
+    base = make_rows(nb.ROW_DTYPE, V, af, beta, ref_is_ea)
+    rng = np.random.default_rng(7)
+    lists = []
+    for k in range(S):
+        r = base.copy()
+        r["beta"] = np.round(rng.normal(0, 0.05, V), 4)
+        lists.append(r)
+    eng = nb.Engine(n, max_rows_per_block=V, n_slots=0, device=dev.index)
+    gt = torch.empty((V, stride), dtype=torch.uint8, device=dev)
+    eng.synth_fill_device(gt, stride, 0, V, SEED, torch.from_numpy(af_thr.view(np.int32)).to(dev),
+                          torch.from_numpy(miss_thr.view(np.int32)).to(dev), torch.from_numpy(alt).to(dev))
+    torch.cuda.synchronize()
+    eng.resident_adopt(gt, stride, V)
+    pin_s = torch.empty((S, n), dtype=torch.float64).pin_memory()
+    pin_l = torch.empty((S, V * nb.LOCUS_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    sc_out = [pin_s[k].numpy() for k in range(S)]
+    lo_out = [pin_l[k].numpy().view(nb.LOCUS_DTYPE) for k in range(S)]
+    ts = []
+    for rep in range(6):
+        t0 = time.perf_counter()
+        eng.score_resident_multi(lists, [0.0] * S, sc_out, lo_out)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts[1:]))
+    ex["config4"] = {"workload": f"{S} score definitions x {V} loci x {n} samples over one resident 8 GB slab, one npc_score_resident_multi call "
+                                 "(wall clock: row tables H2D, tally + contraction kernels, 18 x n scores and records D2H)",
+                     "value": float(V) * n * S / t, "unit": "genotype-score cells/s", "call_ms": t * 1e3,
+                     "slab_reads_per_s_gb": 2.0 * V * n / t / 1e9, "contractions_served": int(eng.multi_contractions),
+                     "substitution": "BASELINE names 18 bundled score files; 4 of the bundled files are score definitions, so 18 synthetic "
+                                     "definitions over one site set stand in (DESIGN.md section 7)"}
+    eng.close()
+    return ex
+
+
 # ---- B200 arm -------------------------------------------------------------------------------------
 
 def b200_arm(args):
     import torch
     import torch.distributed as dist
     import nimpress_b200 as nb
-    from nimpress_b200 import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,6 +305,12 @@ def b200_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.config == 2:
+        args.samples, args.variants = 100_000, 697
+    elif args.config == 5:
+        args.samples, args.variants = 50_000, 10_000
+    elif args.config == 4:
+        raise SystemExit("--config 4 is reported under `extra.config4` of the default run (npc_score_resident_multi is a synchronous host call)")
     n, V = args.samples, args.variants
     stride = -(-2 * n // 128) * 128
     fused = os.environ.get("NPC_FUSED", "1") != "0"
@@ -247,11 +341,21 @@ def b200_arm(args):
     d_rows = torch.from_numpy(rows_rel.view(np.uint8).reshape(V, -1)).to(dev)
     torch.cuda.synchronize()
 
-    sums_ptr, nloci_ptr = eng.partial_device_ptr()
-
-    class _Wrap:   # expose the library-owned partial sums to torch.distributed without a copy
+    class _Wrap:   # expose library-owned device memory to torch without a copy
         def __init__(self, ptr, shape, typestr):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+    def new_comm(e):
+        """NCCL communicator of the C ABI (npc_comm_init): rank 0's id reaches the others over torch.distributed."""
+        ident = [nb.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        e.comm_init(ident[0], rank, world)
+
+    if world > 1:
+        new_comm(eng)
+        sums_ptr, nloci_ptr = eng.combined_device_ptr()         # combined sums / nloci after npc_comm_combine
+    else:
+        sums_ptr, nloci_ptr = eng.partial_device_ptr()
     t_sums = torch.as_tensor(_Wrap(sums_ptr, (n,), "<f8"), device=dev)
     t_nloci = torch.as_tensor(_Wrap(nloci_ptr, (1,), "<i8"), device=dev)
 
@@ -268,8 +372,8 @@ def b200_arm(args):
             if timed:
                 e1.record(stream)
                 launch_events.append((e0, e1, nr))
-        if world > 1:                                  # combine: gather partials, add in rank order (NCCL over NVLink)
-            return shard.combine_partials(t_sums, t_nloci)
+        if world > 1:                                  # npc_comm_combine: all-gather over NCCL/NVLink, add in rank order, on the stream
+            eng.comm_combine(offset=None, want_scores=False)
         return t_sums, t_nloci
 
     def barrier():
@@ -303,6 +407,39 @@ def b200_arm(args):
     value = genotypes_step / (ms_step * 1e-3)
     assert int(nl.item()) == V * world, (int(nl.item()), V * world)
 
+    # N > 1: the combine is checked, not assumed.  Every rank scores the first Vp rows of its shard into a
+    # fresh context and the ranks combine them through the same npc_comm_combine; rank 0 then scores every
+    # rank's Vp rows ALONE on its own GPU (the cohort is a pure function of the variant index) and adds the
+    # partial sums in rank order on the host: the two must agree bit for bit, nloci included.
+    parity_checked = None
+    if world > 1:
+        Vp = min(512, V)
+        pe = nb.Engine(n, max_rows_per_block=Vp, n_slots=0, device=local)
+        pe.set_policy(); pe.reset()
+        new_comm(pe)
+        pe.score_block_device(gt[0], stride, Vp, rows_rel[:Vp])
+        comb, comb_nl = pe.comm_combine(offset=None)
+        pe.close()
+        if rank == 0:
+            total, total_nl = None, 0
+            small = torch.empty((Vp, stride), dtype=torch.uint8, device=dev)
+            for k in range(world):
+                afk, betak, refk, afthr_k, missthr_k, altk = cohort_params(k * V, V)
+                rk = make_rows(nb.ROW_DTYPE, V, afk, betak, refk)[:Vp]
+                e = nb.Engine(n, max_rows_per_block=Vp, n_slots=0, device=local)
+                e.set_policy(); e.reset()
+                e.synth_fill_device(small, stride, k * V, Vp, SEED, torch.from_numpy(afthr_k[:Vp].view(np.int32).copy()).to(dev),
+                                    torch.from_numpy(missthr_k[:Vp].view(np.int32).copy()).to(dev), torch.from_numpy(altk[:Vp].copy()).to(dev))
+                e.score_block_device(small, stride, Vp, rk)
+                pk = e.partial()
+                total = pk["sums"] if total is None else total + pk["sums"]
+                total_nl += pk["nloci"]
+                e.close()
+            same = np.array_equal(comb.view(np.uint64), total.view(np.uint64)) and comb_nl == total_nl
+            assert same, "N-GPU combine differs from the rank-order sum of the shards scored alone"
+            parity_checked = True
+            del small
+
     # roofline of the dominant kernel on this rank: algorithmic bytes per launch (SURVEY.md 8d:
     # 2 B per genotype + 32 B per row + 16 B per sample per launch) / mean duration of the full-size
     # launches, measured with CUDA events on the launching stream inside the timed region
@@ -330,29 +467,34 @@ def b200_arm(args):
                            0: "k_count_i8x2 + k_decide + k_accum_i8x2 sequence"}[shape["fused"]],
                 "algorithmic_bytes_per_launch": alg_bytes}
 
-    # end to end through the staged C-ABI call with host buffers
+    # end to end through the staged C-ABI call with HOST buffers: every step the rows are copied from ordinary
+    # (pageable) host memory -- where a reader leaves the decoded BCF GT payloads -- into the pinned slot the
+    # library lends, by a few host threads, then H2D -> kernels, and the scores come back D2H.  The fill is
+    # inside the timed region (round 1 timed pre-filled slots).
     e2e = None
     if not args.no_e2e:
+        from concurrent.futures import ThreadPoolExecutor
         Ve = min(args.e2e_variants, V)
         eb = max(1, min(Ve, (256 << 20) // stride))
         e_eng = nb.Engine(n, max_rows_per_block=eb, n_slots=3, device=local)
         e_eng.set_policy()
-        slots = {}
         host_rows = rows[:Ve].copy()
         host_rows["gt_row"] = np.arange(Ve) % eb
-        first = gt[:eb].cpu().numpy()
-        for _ in range(3):                              # the pinned ring holds the (synthetic) decoded BCF rows
-            s, view = e_eng.stage_acquire()
-            view[:first.shape[0], :stride] = first
-            slots[s] = view
-            e_eng.score_block(s, 0, host_rows[:0])
+        host_gt = gt[:Ve].cpu().numpy()                 # the host's copy of the rows (pageable memory)
+        T = max(1, min(8, (os.cpu_count() or 1) // max(world, 1)))
+        pool = ThreadPoolExecutor(T)
         scores_host = None
+
+        def fill(view, r0, nr):                         # numpy releases the GIL inside the copies
+            cuts = [nr * k // T for k in range(T + 1)]
+            list(pool.map(lambda k: np.copyto(view[cuts[k]:cuts[k + 1], :stride], host_gt[r0 + cuts[k]:r0 + cuts[k + 1]]), range(T)))
 
         def e2e_step():
             e_eng.reset()
             for r0 in range(0, Ve, eb):
                 nr = min(eb, Ve - r0)
-                s, _ = e_eng.stage_acquire()            # blocks until the slot's previous block is done
+                s, view = e_eng.stage_acquire()         # blocks until the slot's previous block is done
+                fill(view, r0, nr)
                 e_eng.score_block(s, nr, host_rows[r0:r0 + nr])
             return e_eng.finish(want_loci=False)["scores"]
         for _ in range(max(args.warmup, 1)):
@@ -369,10 +511,13 @@ def b200_arm(args):
         dt = float(t.item())
         e2e = {"value": float(n) * Ve * world / dt, "unit": "genotypes/s",
                "h2d_bytes_per_step": int(stride) * Ve + 32 * Ve, "d2h_bytes_per_step": 8 * n + 8,
-               "variants_per_step": Ve, "ms_per_step": dt * 1e3,
-               "note": "npc_stage_acquire/npc_score_block from pinned host rows + npc_finish D2H; per rank"}
+               "variants_per_step": Ve, "ms_per_step": dt * 1e3, "fill_threads": T,
+               "note": "per rank and step: rows copied from pageable host memory into the pinned slot of npc_stage_acquire "
+                       f"by {T} host threads, npc_score_block (H2D + kernels), npc_finish (D2H of the scores); all inside the timed region"}
         assert np.isfinite(scores_host).all()
+        pool.shutdown()
         e_eng.close()
+        del host_gt
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -383,6 +528,13 @@ def b200_arm(args):
                          "reference; scoring only (AF-mismatch binomTest, a warning, not run)",
                "value_with_af_test": n / (dt / Vc + af_ms * 1e-3), "af_test_ms_per_locus": af_ms,
                "with_af_test_note": "the reference's default --afmisp also runs one O(n) binomTest per locus; timed on 24 loci of the sample"}
+
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra and not args.brief and args.config == 3:
+        eng.close()
+        del gt, d_rows
+        torch.cuda.empty_cache()
+        extra = extra_configs(nb, torch, dev, peak)
 
     if rank == 0:
         line = {
@@ -396,6 +548,12 @@ def b200_arm(args):
                        "l2": "inputs larger than L2 (shard >> 126 MB), no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity_checked is not None:
+            line["parity_checked"] = parity_checked
+            line["parity_note"] = (f"first {min(512, V)} rows of every rank's shard: npc_comm_combine over {world} GPUs == rank-order sum of the "
+                                   "same rows scored alone on rank 0's GPU, bit for bit, nloci equal")
+        if extra:
+            line["extra"] = extra
         if args.brief:
             print(f"{value:.4e} genotypes/s  frac={roofline['frac']:.3f}  ms={ms_step:.3f} launch_ms={launch_ms:.3f}  {shape}")
         else:

@@ -38,6 +38,8 @@
  *   NPC_EXACT=1              exact-order mode for every context (as npc_set_exact_order)
  *   NPC_TILE_K / _SR / _SC / _L / _A / _GR   launch shape of the fused tile kernel (chunks per thread, raw stages,
  *                            index tiles, lag, decider warps, row groups)
+ *   NPC_TILE_V=4             the round-1 tile kernel (npc_fused4.cuh) instead of the pair-lookup kernel (npc_fused5.cuh)
+ *   NPC_TILE_SLEEP=<ns>      auxiliary warps of the tile kernel poll + nanosleep instead of a suspended try_wait
  *   NPC_MULTI=0 | 1          npc_score_resident_multi: never / always the tensor-core contraction (default: >= 3 definitions)
  *   NPC_MULTI_PARTS=<n>      split of a tile's entry range over work units in the contraction (default: chosen from the tile count)
  *   NPC_TIMING=1             phase wall times of npc_score_resident_multi on stderr
@@ -113,6 +115,12 @@ typedef struct {
  * the *_device entry points are usable). */
 int  npc_create(npc_ctx **out, int device, int64_t n_samples, int32_t ploidy, int32_t gt_width,
                 int64_t max_rows_per_block, int32_t n_slots);
+/* The same with the pinned staging slots sized separately: staging_rows (<= max_rows_per_block) rows per
+ * slot bound npc_score_block / npc_stage_upload, max_rows_per_block still bounds the score rows of one
+ * launch.  A host that uploads into the resident slab wants small slots (pinning costs ~1 ms per MB)
+ * and large launches. */
+int  npc_create2(npc_ctx **out, int device, int64_t n_samples, int32_t ploidy, int32_t gt_width,
+                 int64_t max_rows_per_block, int32_t n_slots, int64_t staging_rows);
 void npc_destroy(npc_ctx *ctx);
 const char *npc_last_error(const npc_ctx *ctx);   /* ctx may be NULL: text of the last npc_create failure */
 
@@ -220,6 +228,36 @@ int npc_partial(npc_ctx *ctx, double *sums_out, int64_t *nloci_out,
 int npc_partial_device_ptr(npc_ctx *ctx, double **sums_dev, int64_t **nloci_dev);
 /* sums[i] = sums[i] / (2*nloci) + offset on host memory: the reference's epilogue. */
 void npc_normalise(double *sums, int64_t n, int64_t nloci, double offset);
+
+/* ---- several GPUs: the combine of a variant-sharded run ------------------- */
+
+/* Replaces nothing the reference has -- it is single-process, single-threaded -- but is what makes
+ * `scores[i] += dosages[i]*beta` over ALL loci (src/nimpress.nim:634-641) and the one normalisation
+ * (:643-649) come out of several GPUs: the score rows are partitioned into contiguous ranges in
+ * score-file order, context k scores range k over all samples, and the combine adds the raw partial
+ * sums in context order -- total[s] = ((p0[s] + p1[s]) + p2[s]) + ... -- a fixed order, so the result
+ * does not depend on the transport or on the number of ranks that computed each partial.  nloci is
+ * summed; a NaN in any partial propagates like the reference's.
+ *
+ * npc_reduce: ONE process, one context per GPU (ctxs[0..n_ctx) in score-file order of their ranges,
+ * all with the same n_samples).  Waits for every context's submitted work; one kernel on ctxs[0]'s
+ * device reads the other partials through NVLink peer mappings (bridged by peer copies when the
+ * devices cannot map each other).  offset != NULL: scores_out[s] = total / (2*nloci) + *offset (the
+ * reference's epilogue); offset == NULL: the raw total.  Synchronous.  Per-locus records stay with
+ * the context that scored the row (npc_partial). */
+int npc_reduce(npc_ctx *const *ctxs, int32_t n_ctx, const double *offset, double *scores_out, int64_t *nloci_out);
+
+/* One process PER GPU: NCCL, bound at run time with dlopen("libnccl.so.2") -- no link-time dependency;
+ * NPC_EUNSUPPORTED when the library is absent.  Rank 0 calls npc_comm_unique_id and hands the 128
+ * bytes to the other ranks by whatever channel the host has; every rank then calls npc_comm_init
+ * (collective), and after scoring its range npc_comm_combine (collective, rank order = score-file
+ * order): all-gather of the partial sums over NVLink, the same fixed-order add on every rank, an
+ * all-reduce of nloci.  scores_out and nloci_out both NULL: asynchronous on the context's stream,
+ * the result stays on the device (npc_combined_device_ptr). */
+int npc_comm_unique_id(uint8_t *id128);
+int npc_comm_init(npc_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world);
+int npc_comm_combine(npc_ctx *ctx, const double *offset, double *scores_out, int64_t *nloci_out);
+int npc_combined_device_ptr(npc_ctx *ctx, double **scores_dev, int64_t **nloci_dev);
 
 /* Kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t npc_launch_count(const npc_ctx *ctx);

@@ -23,6 +23,7 @@
  *   NIMPRESS_NO_INDEX=1      never use <genotypes>.tbi / .csi;  NIMPRESS_FORCE_INDEX=1  use it whatever it saves
  *   NIMPRESS_TIMING=1        phase wall times on stderr
  *   NIMPRESS_SLAB_ROWS=<n>   cap the device-resident genotype rows (tests: forces scoring in rounds)
+ *   NIMPRESS_SPLIT=<k>       with one device: k contexts on it, combined by npc_reduce (tests of the multi-GPU path on one GPU)
  */
 #ifndef NIMPRESS_HOST_H
 #define NIMPRESS_HOST_H
@@ -49,7 +50,9 @@ typedef struct {
     int32_t use_cov;        /* restrictToCoveredRgns */
     int32_t device;
     int32_t exact_order;    /* 1: npc_set_exact_order(ctx, 1) -- the reference's summation order bit for bit */
-    int32_t reserved;
+    int32_t device_mask;    /* != 0: score on every CUDA device whose bit is set (ascending order): the score rows are split
+                               into contiguous ranges, one per device, combined in range order by npc_reduce; `device` is then
+                               ignored.  0: one device, `device`.  (Several score files at once use the first device only.) */
     int64_t mincs;
     double  maxmis;
     double  afmisp;
@@ -70,6 +73,7 @@ int64_t nph_result_n_samples(const nph_result *r);
 int64_t nph_result_n_loci(const nph_result *r);          /* score rows                      */
 int64_t nph_result_nloci_used(const nph_result *r);      /* loci in the sum (the divisor/2) */
 int64_t nph_result_rounds(const nph_result *r);          /* 1 = exact reference summation order */
+int64_t nph_result_devices(const nph_result *r);         /* GPUs that scored this result             */
 int64_t nph_result_records_read(const nph_result *r);    /* records the reader handed to the matcher         */
 int64_t nph_result_index_seeks(const nph_result *r);     /* > 0: the file's .tbi / .csi index was used        */
 const double *nph_result_scores(const nph_result *r);

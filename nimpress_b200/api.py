@@ -50,7 +50,7 @@ class NimpressInputError(ValueError):
 class _Params(C.Structure):
     _fields_ = [("imp_locus", C.c_int32), ("imp_missing", C.c_int32), ("imp_sample", C.c_int32),
                 ("ignorefilt", C.c_int32), ("use_cov", C.c_int32), ("device", C.c_int32),
-                ("exact_order", C.c_int32), ("reserved", C.c_int32),
+                ("exact_order", C.c_int32), ("device_mask", C.c_int32),
                 ("mincs", C.c_int64), ("maxmis", C.c_double), ("afmisp", C.c_double)]
 
 
@@ -75,7 +75,7 @@ def load_host_library():
         "nph_compute_polygenic_scores": (C.c_int, [cp, cp, cp, C.POINTER(_Params), C.POINTER(vp)]),
         "nph_compute_polygenic_scores_multi": (C.c_int, [C.POINTER(cp), C.c_int32, cp, cp, C.POINTER(_Params), C.POINTER(vp)]),
         "nph_result_n_samples": (i64, [vp]), "nph_result_n_loci": (i64, [vp]), "nph_result_nloci_used": (i64, [vp]),
-        "nph_result_rounds": (i64, [vp]), "nph_result_scores": (vp, [vp]), "nph_result_loci": (vp, [vp]),
+        "nph_result_rounds": (i64, [vp]), "nph_result_devices": (i64, [vp]), "nph_result_scores": (vp, [vp]), "nph_result_loci": (vp, [vp]),
         "nph_result_sample": (cp, [vp, i64]), "nph_result_warnings": (cp, [vp]), "nph_result_free": (None, [vp]),
         "nph_last_error": (cp, []),
         "nph_plan": (C.c_int, [cp, cp, cp, C.POINTER(_Params), vp, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
@@ -142,11 +142,13 @@ class Result:
 
 def run(score_path, genotype_path, bed_path=None, imp_locus=ImputeMethodLocus.ps, imp_missing=ImputeMethodMissing.homref,
         imp_sample=ImputeMethodSample.int_ps, maxmis=0.05, afmisp=0.001, mincs=100, ignorefilt=False, device=0,
-        exact_order=False):
-    """nph_compute_polygenic_scores -> Result (scores, per-locus records, WARN text)."""
+        exact_order=False, devices=None):
+    """nph_compute_polygenic_scores -> Result (scores, per-locus records, WARN text).  devices: list of CUDA
+    device indices to split the score rows over (npc_reduce combines their partial sums)."""
     L = load_host_library()
+    mask = sum(1 << int(d) for d in set(devices)) if devices else 0
     p = _Params(int(imp_locus), int(imp_missing), int(imp_sample), int(ignorefilt), int(bed_path is not None), device,
-                int(bool(exact_order)), 0, int(mincs), float(maxmis), float(afmisp))
+                int(bool(exact_order)), mask, int(mincs), float(maxmis), float(afmisp))
     h = C.c_void_p()
     rc = L.nph_compute_polygenic_scores(os.fsencode(score_path), os.fsencode(genotype_path),
                                         os.fsencode(bed_path) if bed_path else None, C.byref(p), C.byref(h))
@@ -186,8 +188,10 @@ def _take_result(L, h):
         loci = np.frombuffer(C.string_at(L.nph_result_loci(h), nl * LOCUS_DTYPE.itemsize), dtype=LOCUS_DTYPE).copy() if nl \
             else np.zeros(0, LOCUS_DTYPE)
         samples = [L.nph_result_sample(h, i).decode() for i in range(n)]
-        return Result(scores, loci, L.nph_result_nloci_used(h), samples, L.nph_result_warnings(h).decode(),
-                      L.nph_result_rounds(h), L.nph_result_records_read(h), L.nph_result_index_seeks(h))
+        r = Result(scores, loci, L.nph_result_nloci_used(h), samples, L.nph_result_warnings(h).decode(),
+                   L.nph_result_rounds(h), L.nph_result_records_read(h), L.nph_result_index_seeks(h))
+        r.devices = L.nph_result_devices(h)
+        return r
     finally:
         L.nph_result_free(h)
 

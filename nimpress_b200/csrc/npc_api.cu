@@ -12,7 +12,9 @@
 #include <vector>
 
 #include "npc_fused4.cuh"
+#include "npc_fused5.cuh"
 #include "npc_multi.cuh"
+#include "npc_reduce.cuh"
 
 using namespace npc;
 
@@ -23,6 +25,7 @@ struct npc_ctx {
     int64_t n = 0;
     int32_t ploidy = 2, width = 1;
     int64_t max_rows = 0;
+    int64_t staging_rows = 0;               // rows per pinned staging slot (<= max_rows)
     int32_t n_slots = 0;
     int64_t row_stride = 0;                 // of the staging ring
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
@@ -43,6 +46,7 @@ struct npc_ctx {
     struct TileCfg {
         bool ok = false;
         int Gs = 1, Gr = 1, K = 1, nc = 1, slab = 0, Sr = 3, Sc = 16, L = 15, A = 2;
+        int ver = 5;                        // 5: pair-lookup kernel (npc_fused5.cuh); 4: the round-1 kernel (npc_fused4.cuh, NPC_TILE_V=4)
         uint32_t smem = 0;
     };
     TileCfg fast;                           // default: sample slabs x row groups, tile-wise summation
@@ -60,7 +64,17 @@ struct npc_ctx {
     size_t multi_scratch_bytes = 0;
     bool multi_attr_set = false;
     int64_t multi_contractions = 0;         // npc_score_resident_multi calls served by the tensor-core contraction
+    // cross-GPU combine (npc_reduce.cuh)
+    cudaEvent_t ev_reduce = nullptr;        // "this context's partial sums are final"
+    ull *d_nloci_total = nullptr;           // combined nloci, next to d_out (the combined scores)
+    double *d_bridge = nullptr;             // npc_reduce without peer access: [n_ctx - 1][n] copies of the other partials
+    size_t bridge_bytes = 0;
+    void *comm = nullptr;                   // ncclComm_t of npc_comm_init
+    int comm_rank = 0, comm_world = 1;
+    double *d_gather = nullptr;             // [world][n] all-gathered partial sums
 };
+
+static npc::NcclApi g_nccl;
 
 #define NPC_CUDA(ctx, call)                                                                       \
     do {                                                                                          \
@@ -93,6 +107,9 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
     cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
     if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
+    if (ctx->ev_reduce) cudaEventDestroy(ctx->ev_reduce);
+    cudaFree(ctx->d_nloci_total); cudaFree(ctx->d_bridge); cudaFree(ctx->d_gather);
+    if (ctx->comm && g_nccl.lib) g_nccl.CommDestroy(ctx->comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -103,7 +120,11 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-static const void *tile_kernel(int K, bool exact) {
+static const void *tile_kernel(int ver, int K, bool exact) {
+    if (ver == 5) {
+        if (K == 1) return exact ? (const void *)k_fused_pair<1, true> : (const void *)k_fused_pair<1, false>;
+        return exact ? (const void *)k_fused_pair<2, true> : (const void *)k_fused_pair<2, false>;
+    }
     if (K == 1) return exact ? (const void *)k_fused_tile4<1, true> : (const void *)k_fused_tile4<1, false>;
     return exact ? (const void *)k_fused_tile4<2, true> : (const void *)k_fused_tile4<2, false>;
 }
@@ -122,18 +143,23 @@ static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg
     if (nc > 16) return false;                        // cohort too wide for one resident pass
     const int slab = (int)(nc * 32 * K * 16);
     int Sr = env_int("NPC_TILE_SR", 0), Sc = env_int("NPC_TILE_SC", 0), L = env_int("NPC_TILE_L", 0), A = env_int("NPC_TILE_A", 2);
+    const int ver = env_int("NPC_TILE_V", 5) == 4 ? 4 : 5;
+    auto smem_of = [&](int sr, int sc) {
+        return ver == 5 ? (int)Fused5Smem::make(sr, sc, slab, (int)nc, K).total : (int)Fused4Smem::make(sr, sc, slab).total;
+    };
     if (Sr <= 0) Sr = std::max(2, std::min(8, (112 * 1024) / (F4_R * slab)));
     if (Sc <= 0) {
         Sc = 32;
-        while (Sc > 2 && (int)Fused4Smem::make(Sr, Sc, slab).total > max_smem) Sc--;
+        while (Sc > 2 && smem_of(Sr, Sc) > max_smem) Sc--;
     }
-    while (Sr > 2 && (int)Fused4Smem::make(Sr, Sc, slab).total > max_smem) Sr--;
+    while (Sr > 2 && smem_of(Sr, Sc) > max_smem) Sr--;
     // deciders work on groups of 8 tiles: the lag must cover a whole group
-    if ((int)Fused4Smem::make(Sr, Sc, slab).total > max_smem || Sc < 10) return false;
+    if (smem_of(Sr, Sc) > max_smem || Sc < 10) return false;
     if (L <= 8 || L > Sc - 1) L = Sc - 1;
     t.Gs = gs; t.Gr = gr; t.K = K; t.nc = (int)nc; t.slab = slab; t.Sr = Sr; t.Sc = Sc; t.L = L;
     t.A = std::max(1, std::min(2, A));
-    t.smem = Fused4Smem::make(Sr, Sc, slab).total;
+    t.smem = (uint32_t)smem_of(Sr, Sc);
+    t.ver = ver;
     t.ok = true;
     return true;
 }
@@ -165,7 +191,7 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     for (int ex = 0; ex < 2; ex++) {
         const npc_ctx::TileCfg &t = ex ? c->exact_cfg : c->fast;
         if (!t.ok) continue;
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.K, ex != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, ex != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
         if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     }
     if (c->fast.ok || c->exact_cfg.ok) NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
@@ -202,9 +228,10 @@ static int create_impl(npc_ctx *c) {
     c->ev_h2d.assign(c->n_slots, nullptr); c->ev_done.assign(c->n_slots, nullptr);
     c->slot_state.assign(c->n_slots, 0);
     for (int s = 0; s < c->n_slots; s++) {
-        const size_t bytes = (size_t)c->row_stride * (size_t)r1;
+        // pinned host slots only: the device copy of a slot is allocated when npc_score_block first needs it
+        // (the resident path uploads straight into the slab)
+        const size_t bytes = (size_t)c->row_stride * (size_t)std::max<int64_t>(c->staging_rows, 1);
         NPC_CUDA(c, cudaMallocHost(&c->h_gt[s], bytes));
-        NPC_CUDA(c, cudaMalloc(&c->d_gt[s], bytes));
         NPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_h2d[s], cudaEventDisableTiming));
         NPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming));
     }
@@ -216,16 +243,21 @@ static int create_impl(npc_ctx *c) {
 
 extern "C" int npc_create(npc_ctx **out, int device, int64_t n_samples, int32_t ploidy, int32_t gt_width,
                           int64_t max_rows_per_block, int32_t n_slots) {
+    return npc_create2(out, device, n_samples, ploidy, gt_width, max_rows_per_block, n_slots, max_rows_per_block);
+}
+
+extern "C" int npc_create2(npc_ctx **out, int device, int64_t n_samples, int32_t ploidy, int32_t gt_width,
+                           int64_t max_rows_per_block, int32_t n_slots, int64_t staging_rows) {
     if (!out) return NPC_EINVAL;
     *out = nullptr;
     if (n_samples < 0 || ploidy < 1 || ploidy > 64 || (gt_width != 1 && gt_width != 2 && gt_width != 4) ||
-        max_rows_per_block < 1 || n_slots < 0 || n_slots == 1) {
+        max_rows_per_block < 1 || n_slots < 0 || n_slots == 1 || staging_rows < 1 || staging_rows > max_rows_per_block) {
         g_create_error = "npc_create: invalid argument";
         return NPC_EINVAL;
     }
     npc_ctx *c = new npc_ctx();
     c->device = device; c->n = n_samples; c->ploidy = ploidy; c->width = gt_width;
-    c->max_rows = max_rows_per_block; c->n_slots = n_slots;
+    c->max_rows = max_rows_per_block; c->n_slots = n_slots; c->staging_rows = staging_rows;
     c->pol.imp_locus = NPC_LOCUS_PS; c->pol.imp_missing = NPC_MISSING_HOMREF; c->pol.imp_sample = NPC_SAMPLE_INT_PS;
     c->pol.mincs = 100; c->pol.maxmis = 0.05; c->pol.n_total = n_samples;      // defaults of main (:670-687)
     int rc = create_impl(c);
@@ -386,8 +418,9 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
     P.sums = c->d_sums; P.counts = c->d_fcounts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
     P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
     P.Gs = t.Gs; P.Gr = gr; P.partials = c->d_partials;
+    P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
     void *args[] = { &P };
-    NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.K, exact), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
+    NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
     c->launches++;
     if (gr > 1) {
         k_add_partials<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_sums, c->d_partials, c->n, gr - 1);
@@ -427,9 +460,11 @@ extern "C" int npc_score_block(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, co
     if (!ctx) return NPC_EINVAL;
     if (slot < 0 || slot >= ctx->n_slots || ctx->slot_state[slot] != 1)
         return fail(ctx, NPC_ESTATE, "slot was not acquired");
+    if (n_gt_rows > ctx->staging_rows) return fail(ctx, NPC_EINVAL, "more genotype rows than a staging slot holds");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_gt[slot]) NPC_CUDA(ctx, cudaMalloc(&ctx->d_gt[slot], (size_t)ctx->row_stride * (size_t)std::max<int64_t>(ctx->staging_rows, 1)));
     int rc = check_block(ctx, ctx->d_gt[slot], ctx->row_stride, n_gt_rows, rows, n_rows);
     if (rc) return rc;
-    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_gt_rows)
         NPC_CUDA(ctx, cudaMemcpyAsync(ctx->d_gt[slot], ctx->h_gt[slot], (size_t)n_gt_rows * ctx->row_stride,
                                       cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -516,7 +551,7 @@ extern "C" int npc_resident_adopt(npc_ctx *ctx, const void *gt_dev, int64_t row_
 extern "C" int npc_stage_upload(npc_ctx *ctx, int32_t slot, int64_t n_gt_rows, int64_t dst_row) {
     if (!ctx) return NPC_EINVAL;
     if (slot < 0 || slot >= ctx->n_slots || ctx->slot_state[slot] != 1) return fail(ctx, NPC_ESTATE, "slot was not acquired");
-    if (n_gt_rows < 0 || n_gt_rows > ctx->max_rows || dst_row < 0 || dst_row + n_gt_rows > ctx->slab_rows)
+    if (n_gt_rows < 0 || n_gt_rows > ctx->staging_rows || dst_row < 0 || dst_row + n_gt_rows > ctx->slab_rows)
         return fail(ctx, NPC_EINVAL, "npc_stage_upload: rows outside the resident slab");
     if (ctx->slab_stride != ctx->row_stride) return fail(ctx, NPC_ESTATE, "npc_stage_upload: the adopted slab has another row stride");
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -834,6 +869,144 @@ extern "C" void npc_normalise(double *sums, int64_t n, int64_t nloci, double off
         volatile double q = sums[i] / denom;
         sums[i] = q + offset;
     }
+}
+
+// ---- several GPUs ---------------------------------------------------------------------------------
+
+static int ensure_combine_buffers(npc_ctx *c) {
+    if (!c->ev_reduce) NPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_reduce, cudaEventDisableTiming));
+    if (!c->d_nloci_total) NPC_CUDA(c, cudaMalloc(&c->d_nloci_total, sizeof(ull)));
+    return NPC_OK;
+}
+
+extern "C" int npc_reduce(npc_ctx *const *ctxs, int32_t n_ctx, const double *offset, double *scores_out, int64_t *nloci_out) {
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return NPC_EINVAL;
+    npc_ctx *root = ctxs[0];
+    if (n_ctx > REDUCE_MAX) return fail(root, NPC_EINVAL, "npc_reduce: too many contexts");
+    for (int k = 0; k < n_ctx; k++) {
+        if (!ctxs[k] || ctxs[k]->n != root->n) return fail(root, NPC_EINVAL, "npc_reduce: contexts must hold the same samples");
+        for (int j = 0; j < k; j++) if (ctxs[j] == ctxs[k]) return fail(root, NPC_EINVAL, "npc_reduce: a context is listed twice");
+    }
+    ReduceParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_parts = n_ctx; P.normalise = offset ? 1 : 0; P.offset = offset ? *offset : 0.0;
+    // every context's partial sums are final when its stream reaches this point
+    for (int k = 1; k < n_ctx; k++) {
+        npc_ctx *c = ctxs[k];
+        NPC_CUDA(c, cudaSetDevice(c->device));
+        int rc = ensure_combine_buffers(c);
+        if (rc) return rc;
+        NPC_CUDA(c, cudaEventRecord(c->ev_reduce, c->stream));
+    }
+    NPC_CUDA(root, cudaSetDevice(root->device));
+    int rc = ensure_combine_buffers(root);
+    if (rc) return rc;
+    int n_bridge = 0;
+    std::vector<int> bridged(n_ctx, 0);
+    for (int k = 1; k < n_ctx; k++) {
+        npc_ctx *c = ctxs[k];
+        NPC_CUDA(root, cudaStreamWaitEvent(root->stream, c->ev_reduce, 0));
+        if (c->device == root->device) continue;
+        int can = 0;
+        NPC_CUDA(root, cudaDeviceCanAccessPeer(&can, root->device, c->device));
+        if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(c->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { cudaGetLastError(); can = 0; }
+        }
+        if (!can) bridged[k] = ++n_bridge;
+    }
+    const size_t nbytes = (size_t)std::max<int64_t>(root->n, 1) * sizeof(double);
+    if (n_bridge && root->bridge_bytes < (size_t)n_bridge * (nbytes + 256)) {
+        NPC_CUDA(root, cudaStreamSynchronize(root->stream));
+        cudaFree(root->d_bridge); root->d_bridge = nullptr; root->bridge_bytes = 0;
+        NPC_CUDA(root, cudaMalloc(&root->d_bridge, (size_t)n_bridge * (nbytes + 256)));
+        root->bridge_bytes = (size_t)n_bridge * (nbytes + 256);
+    }
+    for (int k = 0; k < n_ctx; k++) {
+        npc_ctx *c = ctxs[k];
+        if (!bridged[k]) { P.part[k] = c->d_sums; P.nloci[k] = c->d_nloci; continue; }
+        uint8_t *slot = (uint8_t *)root->d_bridge + (size_t)(bridged[k] - 1) * (nbytes + 256);      // [n doubles][nloci]
+        NPC_CUDA(root, cudaMemcpyPeerAsync(slot, root->device, c->d_sums, c->device, (size_t)root->n * sizeof(double), root->stream));
+        NPC_CUDA(root, cudaMemcpyPeerAsync(slot + nbytes, root->device, c->d_nloci, c->device, sizeof(ull), root->stream));
+        P.part[k] = (const double *)slot; P.nloci[k] = (const ull *)(slot + nbytes);
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>((root->n + 255) / 256, 1), 148 * 8);
+    k_combine<<<grid, 256, 0, root->stream>>>(P, root->n, root->d_out, root->d_nloci_total);
+    root->launches++;
+    NPC_CUDA(root, cudaGetLastError());
+    ull nl = 0;
+    if (scores_out && root->n)
+        NPC_CUDA(root, cudaMemcpyAsync(scores_out, root->d_out, (size_t)root->n * sizeof(double), cudaMemcpyDeviceToHost, root->stream));
+    NPC_CUDA(root, cudaMemcpyAsync(&nl, root->d_nloci_total, sizeof(ull), cudaMemcpyDeviceToHost, root->stream));
+    NPC_CUDA(root, cudaStreamSynchronize(root->stream));
+    if (nloci_out) *nloci_out = (int64_t)nl;
+    return NPC_OK;
+}
+
+extern "C" int npc_comm_unique_id(uint8_t *id128) {
+    if (!id128) return NPC_EINVAL;
+    if (!g_nccl.load()) { g_create_error = g_nccl.err; return NPC_EUNSUPPORTED; }
+    NcclId id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return NPC_ECUDA; }
+    memcpy(id128, id.internal, 128);
+    return NPC_OK;
+}
+
+extern "C" int npc_comm_init(npc_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return NPC_EINVAL;
+    if (world > REDUCE_MAX) return fail(ctx, NPC_EINVAL, "npc_comm_init: too many ranks");
+    if (!g_nccl.load()) return fail(ctx, NPC_EUNSUPPORTED, g_nccl.err.c_str());
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    const int r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+    if (r) { ctx->comm = nullptr; ctx->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return NPC_ECUDA; }
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    cudaFree(ctx->d_gather); ctx->d_gather = nullptr;
+    NPC_CUDA(ctx, cudaMalloc(&ctx->d_gather, (size_t)world * (size_t)std::max<int64_t>(ctx->n, 1) * sizeof(double)));
+    return ensure_combine_buffers(ctx);
+}
+
+extern "C" int npc_comm_combine(npc_ctx *ctx, const double *offset, double *scores_out, int64_t *nloci_out) {
+    if (!ctx) return NPC_EINVAL;
+    if (!ctx->comm) return fail(ctx, NPC_ESTATE, "npc_comm_combine: npc_comm_init was not called");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = ctx->comm_world;
+    int r = 0;
+    if (ctx->n) r = g_nccl.AllGather(ctx->d_sums, ctx->d_gather, (size_t)ctx->n, NCCL_FLOAT64, ctx->comm, ctx->stream);
+    if (!r) r = g_nccl.AllReduce(ctx->d_nloci, ctx->d_nloci_total, 1, NCCL_UINT64, NCCL_SUM, ctx->comm, ctx->stream);
+    if (r) { ctx->err = std::string("NCCL: ") + g_nccl.GetErrorString(r); return NPC_ECUDA; }
+    ReduceParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_parts = W; P.normalise = offset ? 1 : 0; P.offset = offset ? *offset : 0.0;
+    for (int k = 0; k < W; k++) P.part[k] = ctx->d_gather + (size_t)k * ctx->n;
+    // nloci: the all-reduced total lives in d_nloci_total; the kernel reads it as a one-element "shard" list
+    P.n_parts = W;
+    k_combine_total<<<(unsigned)std::min<int64_t>(std::max<int64_t>((ctx->n + 255) / 256, 1), 148 * 8), 256, 0, ctx->stream>>>(
+        P, ctx->n, ctx->d_out, ctx->d_nloci_total);
+    ctx->launches++;
+    NPC_CUDA(ctx, cudaGetLastError());
+    if (!scores_out && !nloci_out) return NPC_OK;                        // asynchronous: results stay on the device (npc_combined_device_ptr)
+    ull nl = 0;
+    if (scores_out && ctx->n)
+        NPC_CUDA(ctx, cudaMemcpyAsync(scores_out, ctx->d_out, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NPC_CUDA(ctx, cudaMemcpyAsync(&nl, ctx->d_nloci_total, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+    NPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nloci_out) *nloci_out = (int64_t)nl;
+    return NPC_OK;
+}
+
+extern "C" int npc_combined_device_ptr(npc_ctx *ctx, double **scores_dev, int64_t **nloci_dev) {
+    if (!ctx) return NPC_EINVAL;
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_combine_buffers(ctx);
+    if (rc) return rc;
+    if (scores_dev) *scores_dev = ctx->d_out;
+    if (nloci_dev) *nloci_dev = (int64_t *)ctx->d_nloci_total;
+    return NPC_OK;
 }
 
 extern "C" int npc_synth_fill_device(npc_ctx *ctx, void *gt_dev, int64_t row_stride, int64_t v0, int64_t n_rows,

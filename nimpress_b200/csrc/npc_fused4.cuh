@@ -160,7 +160,7 @@ k_fused_tile4(const FusedParams P) {
             const uint32_t gt_all = __ballot_sync(0xffffffffu, is_gt);
             const int ng = (int)min((int64_t)G, n_tiles - t0);
             for (int j = 0; j < ng; j++) {
-                mbar_wait(bar_rempty + 8u * s, ph ^ 1u);
+                mbar_wait_sleep(bar_rempty + 8u * s, ph ^ 1u, P.aux_sleep_ns);
                 const uint32_t gt_mask = (gt_all >> (R * j)) & ((1u << R) - 1u);
                 const bool mine = (lane / R) == j;                   // lanes R*j .. R*j+R-1 own this tile's rows
                 if (mine) s_reaidx[s * R + (lane % R)] = is_gt ? cur.eaidx : 0;
@@ -178,7 +178,7 @@ k_fused_tile4(const FusedParams P) {
         // ================= publisher ===========================================================
         int s = 0; uint32_t ph = 0;
         for (int64_t t = 0; t < n_tiles; t++) {
-            mbar_wait(bar_cnt + 8u * s, ph);
+            mbar_wait_sleep(bar_cnt + 8u * s, ph, P.aux_sleep_ns);
             const int nr = (int)min((int64_t)R, P.n_rows - (tile_lo + t) * R);
             if (lane < nr) {
                 ull miss = 0, eff = 0;
@@ -211,7 +211,7 @@ k_fused_tile4(const FusedParams P) {
             // group's last tile first (tiles are counted in order)
             {
                 const int64_t tl = t0 + ng - 1;
-                mbar_wait(bar_cnt + 8u * (uint32_t)(tl % Sc), (uint32_t)((tl / Sc) & 1));
+                mbar_wait_sleep(bar_cnt + 8u * (uint32_t)(tl % Sc), (uint32_t)((tl / Sc) & 1), P.aux_sleep_ns);
             }
             double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // a dropped row adds +0.0: the identity
             int used = 0;

@@ -51,6 +51,7 @@ def load_library():
     pi64 = C.POINTER(C.c_int64)
     sig = {
         "npc_create": (C.c_int, [C.POINTER(vp), C.c_int, i64, i32, i32, i64, i32]),
+        "npc_create2": (C.c_int, [C.POINTER(vp), C.c_int, i64, i32, i32, i64, i32, i64]),
         "npc_destroy": (None, [vp]),
         "npc_last_error": (C.c_char_p, [vp]),
         "npc_set_stream": (C.c_int, [vp, vp]),
@@ -72,6 +73,11 @@ def load_library():
         "npc_partial": (C.c_int, [vp, vp, pi64, vp, i64, pi64]),
         "npc_partial_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "npc_normalise": (None, [vp, i64, i64, f64]),
+        "npc_reduce": (C.c_int, [C.POINTER(vp), i32, C.POINTER(f64), vp, pi64]),
+        "npc_comm_unique_id": (C.c_int, [vp]),
+        "npc_comm_init": (C.c_int, [vp, vp, i32, i32]),
+        "npc_comm_combine": (C.c_int, [vp, C.POINTER(f64), vp, pi64]),
+        "npc_combined_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "npc_launch_count": (i64, [vp]),
         "npc_kernel_shape": (C.c_int, [vp, C.POINTER(i32 * 8)]),
         "npc_set_exact_order": (C.c_int, [vp, i32]),
@@ -97,16 +103,30 @@ def _ptr(x):
     return x.data_ptr()
 
 
+def reduce_contexts(engines, offset=None):
+    """npc_reduce over Engine objects in score-file order of their row ranges: (scores, nloci)."""
+    L = load_library()
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    scores = np.empty(engines[0].n, dtype=np.float64)
+    nloci = C.c_int64()
+    off = C.byref(C.c_double(float(offset))) if offset is not None else None
+    rc = L.npc_reduce(arr, len(engines), off, scores.ctypes.data, C.byref(nloci))
+    if rc:
+        raise NpcError(f"npc_reduce rc={rc}: {L.npc_last_error(engines[0].h).decode()}")
+    return scores, nloci.value
+
+
 class Engine:
     """One scoring context on one GPU: the state of one computePolygenicScores call
     (src/nimpress.nim:592-649) -- per-sample fp64 sums, nloci and the per-locus log."""
 
-    def __init__(self, n_samples, ploidy=2, gt_width=1, max_rows_per_block=4096, n_slots=0, device=0):
+    def __init__(self, n_samples, ploidy=2, gt_width=1, max_rows_per_block=4096, n_slots=0, device=0, staging_rows=None):
         self.L = load_library()
         self.n = int(n_samples)
         self.ploidy, self.gt_width, self.max_rows = int(ploidy), int(gt_width), int(max_rows_per_block)
         h = C.c_void_p()
-        rc = self.L.npc_create(C.byref(h), device, self.n, ploidy, gt_width, max_rows_per_block, n_slots)
+        self.staging_rows = int(staging_rows) if staging_rows else self.max_rows
+        rc = self.L.npc_create2(C.byref(h), device, self.n, ploidy, gt_width, max_rows_per_block, n_slots, self.staging_rows)
         if rc:
             raise NpcError(f"npc_create rc={rc}: {self.L.npc_last_error(None).decode()}")
         self.h = h
@@ -142,8 +162,8 @@ class Engine:
     def stage_acquire(self):
         slot, ptr, stride = C.c_int32(), C.c_void_p(), C.c_int64()
         self._ck(self.L.npc_stage_acquire(self.h, C.byref(slot), C.byref(ptr), C.byref(stride)))
-        buf = (C.c_uint8 * (stride.value * self.max_rows)).from_address(ptr.value)
-        view = np.frombuffer(buf, dtype=np.uint8).reshape(self.max_rows, stride.value)
+        buf = (C.c_uint8 * (stride.value * self.staging_rows)).from_address(ptr.value)
+        view = np.frombuffer(buf, dtype=np.uint8).reshape(self.staging_rows, stride.value)
         return slot.value, view
 
     def score_block(self, slot, n_gt_rows, rows):
@@ -245,6 +265,37 @@ class Engine:
             self._ck(self.L.npc_partial(self.h, sums.ctypes.data, C.byref(nloci), loci.ctypes.data, len(loci),
                                         C.byref(nlog)))
         return dict(sums=sums, nloci=nloci.value, loci=loci)
+
+    # -- several GPUs
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes that rank 0 hands to the other ranks (npc_comm_unique_id)."""
+        buf = (C.c_uint8 * 128)()
+        rc = load_library().npc_comm_unique_id(buf)
+        if rc:
+            raise NpcError(f"npc_comm_unique_id rc={rc}: {load_library().npc_last_error(None).decode()}")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.L.npc_comm_init(self.h, buf, int(rank), int(world)))
+
+    def comm_combine(self, offset=None, want_scores=True):
+        """npc_comm_combine: (scores or None, nloci) -- normalised when offset is given, raw sums otherwise.
+        want_scores=False with offset=None queues the combine on the stream and returns nothing."""
+        off = C.byref(C.c_double(float(offset))) if offset is not None else None
+        if not want_scores:
+            self._ck(self.L.npc_comm_combine(self.h, off, None, None))
+            return None, None
+        scores = np.empty(self.n, dtype=np.float64)
+        nloci = C.c_int64()
+        self._ck(self.L.npc_comm_combine(self.h, off, scores.ctypes.data, C.byref(nloci)))
+        return scores, nloci.value
+
+    def combined_device_ptr(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.npc_combined_device_ptr(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def partial_device_ptr(self):
         a, b = C.c_void_p(), C.c_void_p()

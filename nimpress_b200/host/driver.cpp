@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 
 #include "stats.hpp"
@@ -154,7 +155,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
     const int64_t n = vcf.n_samples();
     struct PerScore {
         std::unique_ptr<Matcher> M;
-        std::vector<int64_t> slab_row, submitted;   // submitted: entry index of every row sent to the GPU, in order
+        std::vector<int64_t> slab_row;              // per entry: row of its device's resident slab
         std::vector<uint8_t> done;
         std::vector<npc_row> rows;
     };
@@ -169,7 +170,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             outs[k].samples = vcf.samples();
             ps[k].M.reset(new Matcher(*scores[k], cov, p));
             const int64_t nE = (int64_t)scores[k]->entries.size();
-            ps[k].slab_row.assign(nE, -1); ps[k].done.assign(nE, 0); ps[k].submitted.reserve(nE);
+            ps[k].slab_row.assign(nE, -1); ps[k].done.assign(nE, 0);
             if (S == 1) { n_lookup = ps[k].M->n_lookup(); break; }
             for (int64_t i = 0; i < nE; i++) if (ps[k].M->kind[i] == Matcher::PENDING) {
                 const ScoreEntry &e = scores[k]->entries[i];
@@ -185,94 +186,146 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
     }
     timer.mark("coverage + entry index");
 
-    // staging slots of ~32 MB: big enough for efficient H2D copies, small enough that pinning three
-    // of them does not dominate a short run (pinning costs ~1 ms per MB)
+    // Devices: one context per GPU.  With several, the score rows are partitioned into contiguous ranges in
+    // score-file order (a contig / region partition for a sorted score file): context d scores range d over all
+    // samples, a matched record is uploaded to the device(s) whose ranges name it, and the partial sums are
+    // combined in range order by npc_reduce.  Several score files at once (S > 1) use the first device only.
+    std::vector<int> dev_ids = p.devices.empty() ? std::vector<int>{ p.device } : p.devices;
+    if (const char *e = getenv("NIMPRESS_SPLIT")) if (*e && dev_ids.size() == 1 && atoi(e) > 1)      // tests: several contexts on one GPU
+        dev_ids.assign((size_t)std::min(atoi(e), 16), dev_ids[0]);
+    if (S > 1) dev_ids.resize(1);
+    const int D = (int)dev_ids.size();
+    const int64_t nE0 = (int64_t)scores[0]->entries.size();
+    auto dev_of = [&](int64_t i) -> int { return D == 1 ? 0 : (int)std::min<int64_t>(D - 1, i * D / std::max<int64_t>(nE0, 1)); };
+    std::vector<int64_t> dev_lookup(D, 0);            // rows of each device's range that need a record
+    if (D == 1) dev_lookup[0] = n_lookup;
+    else for (int64_t i = 0; i < nE0; i++) if (ps[0].M->kind[i] == Matcher::PENDING) dev_lookup[dev_of(i)]++;
+
+    // staging slots of ~8 MB: big enough for efficient H2D copies, small enough that pinning three of them per
+    // device does not dominate a short run (pinning costs ~1 ms per MB); scoring launches are sized separately
     const int64_t row_bytes = std::max<int64_t>(16, n * ploidy * gt_width);
-    const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(4096, (32ll << 20) / row_bytes + 1),
-                                                                     std::max<int64_t>(n_lookup, 1)));
-    Ctx ctx;
+    struct Dev {
+        Ctx ctx;
+        int32_t slot = -1; uint8_t *stage = nullptr; int64_t stride = 0, staged = 0, slab_base = 0, slab_cap = 0, block_rows = 1;
+        std::vector<npc_row> rows; std::vector<int64_t> submitted;   // S == 1: this device's rows, entry index of each
+        std::string err;
+    };
+    std::vector<Dev> devs(D);
     npc_policy pol = { p.imp_locus, p.imp_missing, p.imp_sample, 0, p.mincs, p.maxmis };
-    ctx.ck(npc_create(&ctx.h, p.device, n, ploidy, gt_width, block_rows, 3), "npc_create");
-    ctx.ck(npc_set_policy(ctx.h, &pol), "npc_set_policy");
-    if (p.exact_order) ctx.ck(npc_set_exact_order(ctx.h, 1), "npc_set_exact_order");
-    ctx.ck(npc_reset(ctx.h), "npc_reset");
-    int64_t slab_cap = 0, slab_want = std::max<int64_t>(n_lookup, 1);
-    if (const char *e = getenv("NIMPRESS_SLAB_ROWS")) if (*e) slab_want = std::max<int64_t>(1, std::min<int64_t>(slab_want, atoll(e)));   // tests: force rounds
-    ctx.ck(npc_resident_reserve(ctx.h, slab_want, &slab_cap), "npc_resident_reserve");
+    auto open_dev = [&](int d) {
+        Dev &v = devs[d];
+        try {
+            const int64_t want = std::max<int64_t>(dev_lookup[d], 1);
+            v.block_rows = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(4096, (8ll << 20) / row_bytes + 1), want));
+            const int64_t launch_rows = std::max<int64_t>(v.block_rows, 32768);
+            v.ctx.ck(npc_create2(&v.ctx.h, dev_ids[d], n, ploidy, gt_width, launch_rows, 3, v.block_rows), "npc_create");
+            v.ctx.ck(npc_set_policy(v.ctx.h, &pol), "npc_set_policy");
+            if (p.exact_order) v.ctx.ck(npc_set_exact_order(v.ctx.h, 1), "npc_set_exact_order");
+            v.ctx.ck(npc_reset(v.ctx.h), "npc_reset");
+            int64_t slab_want = want;
+            if (const char *e = getenv("NIMPRESS_SLAB_ROWS")) if (*e) slab_want = std::max<int64_t>(1, std::min<int64_t>(slab_want, atoll(e)));   // tests: force rounds
+            v.ctx.ck(npc_resident_reserve(v.ctx.h, slab_want, &v.slab_cap), "npc_resident_reserve");
+        } catch (const std::exception &e) { v.err = e.what(); }
+    };
+    if (D == 1) open_dev(0);
+    else {                                            // CUDA context creation dominates: one thread per device
+        std::vector<std::thread> th;
+        for (int d = 0; d < D; d++) th.emplace_back(open_dev, d);
+        for (auto &t : th) t.join();
+    }
+    for (int d = 0; d < D; d++) if (!devs[d].err.empty()) throw std::runtime_error(devs[d].err);
     timer.mark("GPU context + buffers");
 
-    int32_t slot = -1; uint8_t *stage = nullptr; int64_t stride = 0, staged = 0, slab_base = 0;
-    auto flush_stage = [&]() {
-        if (slot < 0) return;
-        ctx.ck(npc_stage_upload(ctx.h, slot, staged, slab_base), "npc_stage_upload");
-        slab_base += staged; staged = 0; slot = -1;
+    auto flush_stage = [&](Dev &v) {
+        if (v.slot < 0) return;
+        v.ctx.ck(npc_stage_upload(v.ctx.h, v.slot, v.staged, v.slab_base), "npc_stage_upload");
+        v.slab_base += v.staged; v.staged = 0; v.slot = -1;
     };
-    // the rows of score k that a round takes, in score-file order
-    auto collect_rows = [&](int k, bool final_round) {
+    // the rows of score k that a round takes on device d, in score-file order
+    auto collect_rows = [&](int k, int d, bool final_round, std::vector<npc_row> &rows, std::vector<int64_t> &submitted) {
         PerScore &q = ps[k];
         const std::vector<ScoreEntry> &E = scores[k]->entries;
-        q.rows.clear();
+        rows.clear();
         for (int64_t i = 0; i < (int64_t)E.size(); i++) {
-            if (q.done[i]) continue;
+            if (q.done[i] || (S == 1 && dev_of(i) != d)) continue;
             const int32_t kind = q.M->kind[i];
             if (!final_round && !(kind == NPC_KIND_GT && q.slab_row[i] >= 0)) continue;
             npc_row r;
             r.gt_row = kind == NPC_KIND_GT ? (int32_t)q.slab_row[i] : -1;
             r.eaidx = q.M->eaidx[i]; r.beta = E[i].beta; r.eaf = E[i].eaf;
             r.ref_is_ea = E[i].ref_is_ea() ? 1 : 0; r.kind = kind;
-            q.rows.push_back(r);
-            q.submitted.push_back(i);
+            rows.push_back(r);
+            submitted.push_back(i);
             q.done[i] = 1;
         }
     };
-    // A round scores rows over the resident slab in score-file order.  The normal case is ONE
-    // final round holding every row: exactly the reference's loop order (:634-641).  Only when the
-    // matched genotype rows exceed device memory are there earlier rounds; those take the rows
-    // whose genotypes sit in the slab, and the summation order then differs from the reference's
-    // by a reordering of terms (scores agree to ~1 ulp of the partial sums, not bit for bit).
-    auto score_round = [&](bool final_round) {     // one score file only
-        flush_stage();
-        collect_rows(0, final_round);
-        if (!ps[0].rows.empty()) ctx.ck(npc_score_resident(ctx.h, ps[0].rows.data(), (int64_t)ps[0].rows.size()), "npc_score_resident");
-        outs[0].rounds++;
+    // A round scores rows over a device's resident slab in score-file order.  The normal case is ONE
+    // final round per device holding every row of its range: exactly the reference's loop order
+    // (:634-641).  Only when the matched genotype rows exceed device memory are there earlier rounds;
+    // those take the rows whose genotypes sit in the slab, and the summation order then differs from
+    // the reference's by a reordering of terms (scores agree to ~1 ulp of the partial sums, not bit for bit).
+    std::vector<int64_t> rounds(D, 0);
+    auto score_round = [&](int d, bool final_round) {     // one score file only
+        Dev &v = devs[d];
+        flush_stage(v);
+        collect_rows(0, d, final_round, v.rows, v.submitted);
+        if (!v.rows.empty()) v.ctx.ck(npc_score_resident(v.ctx.h, v.rows.data(), (int64_t)v.rows.size()), "npc_score_resident");
+        rounds[d]++;
     };
 
     // ---- one streaming pass over the genotype file (findVariant :353-364, eaidx :375-379) ---
     VariantRecord rec;
     int64_t records_read = 0, records_matched = 0;
+    std::vector<int64_t> rec_row(D);                   // slab row this record got on each device, -1 = not uploaded there
     while (vcf.next(rec)) {
         records_read++;
         bool any = false, need_gt = false;
+        uint32_t need_dev = 0;
         for (int k = 0; k < S; k++) {
             const std::vector<int64_t> &hits = ps[k].M->match(rec);
-            for (int64_t i : hits) { any = true; need_gt |= ps[k].M->kind[i] == NPC_KIND_GT; }
+            for (int64_t i : hits) {
+                any = true;
+                if (ps[k].M->kind[i] == NPC_KIND_GT) { need_gt = true; need_dev |= 1u << (S == 1 ? dev_of(i) : 0); }
+            }
         }
         if (!any) continue;
         records_matched++;
         if (!need_gt) continue;                                     // FILTER-failed: never decoded (:553-558)
-        if (slab_base + staged >= slab_cap) {                       // slab full: score its rows, start over
-            if (S > 1) throw SlabOverflow();
-            score_round(false);
-            slab_base = 0;
+        const uint8_t *first = nullptr;
+        for (int d = 0; d < D; d++) {
+            rec_row[d] = -1;
+            if (!((need_dev >> d) & 1u)) continue;
+            Dev &v = devs[d];
+            if (v.slab_base + v.staged >= v.slab_cap) {             // slab full: score its rows, start over
+                if (S > 1) throw SlabOverflow();
+                score_round(d, false);
+                v.slab_base = 0;
+            }
+            if (v.slot < 0) {
+                void *ptr;
+                v.ctx.ck(npc_stage_acquire(v.ctx.h, &v.slot, &ptr, &v.stride), "npc_stage_acquire");
+                v.stage = (uint8_t *)ptr; v.staged = 0;
+            }
+            uint8_t *dst = v.stage + v.staged * v.stride;
+            if (first) memcpy(dst, first, (size_t)n * ploidy * gt_width);   // a record named by two ranges: same bytes
+            else {
+                // BCF with the context's layout: the GT payload goes from the inflated blocks straight into the pinned row
+                const bool direct = vcf.load_gt_into(rec, dst, gt_width, ploidy);
+                if (!rec.has_gt || !rec.gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
+                if (!direct) {
+                    if (rec.ploidy > ploidy || rec.gt_width > gt_width)
+                        throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
+                    if (rec.gt_width == gt_width && rec.ploidy == ploidy) memcpy(dst, rec.gt, (size_t)n * ploidy * gt_width);
+                    else convert_gt(rec, n, gt_width, ploidy, dst);
+                }
+                first = dst;
+            }
+            rec_row[d] = v.slab_base + v.staged;
+            v.staged++;
         }
-        if (slot < 0) {
-            void *ptr;
-            ctx.ck(npc_stage_acquire(ctx.h, &slot, &ptr, &stride), "npc_stage_acquire");
-            stage = (uint8_t *)ptr; staged = 0;
-        }
-        uint8_t *dst = stage + staged * stride;
-        // BCF with the context's layout: the GT payload goes from the inflated blocks straight into the pinned row
-        const bool direct = vcf.load_gt_into(rec, dst, gt_width, ploidy);
-        if (!rec.has_gt || !rec.gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
-        if (!direct) {
-            if (rec.ploidy > ploidy || rec.gt_width > gt_width)
-                throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
-            if (rec.gt_width == gt_width && rec.ploidy == ploidy) memcpy(dst, rec.gt, (size_t)n * ploidy * gt_width);
-            else convert_gt(rec, n, gt_width, ploidy, dst);
-        }
-        for (int k = 0; k < S; k++) for (int64_t i : ps[k].M->match_last()) if (ps[k].M->kind[i] == NPC_KIND_GT) ps[k].slab_row[i] = slab_base + staged;
-        staged++;
-        if (staged == block_rows) flush_stage();
+        for (int k = 0; k < S; k++) for (int64_t i : ps[k].M->match_last())
+            if (ps[k].M->kind[i] == NPC_KIND_GT) ps[k].slab_row[i] = rec_row[S == 1 ? dev_of(i) : 0];
+        for (int d = 0; d < D; d++) if (devs[d].slot >= 0 && devs[d].staged == devs[d].block_rows) flush_stage(devs[d]);
     }
     for (int k = 0; k < S; k++) {
         ps[k].M->finish();
@@ -282,37 +335,60 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
     if (timer.on) fprintf(stderr, "[nimpress timing] records read %lld, matched %lld, index seeks %lld%s\n", (long long)records_read,
                           (long long)records_matched, (long long)vcf.seeks(), vcf.seeks() ? " (.tbi / .csi used)" : "");
 
-    // ---- score the slab, collect results ------------------------------------------------------
+    // ---- score the slab(s), collect results ----------------------------------------------------
     std::vector<std::vector<npc_locus>> logs(S);
+    std::vector<std::vector<int64_t>> order(S);          // entry index of every log record
     if (S == 1) {
-        score_round(true);
+        for (int d = 0; d < D; d++) score_round(d, true);
         outs[0].scores.assign(n, 0.0);
-        logs[0].resize(ps[0].submitted.size());
-        int64_t nlog = 0;
-        ctx.ck(npc_finish(ctx.h, scores[0]->offset, outs[0].scores.data(), &outs[0].nloci, logs[0].data(), (int64_t)logs[0].size(), &nlog), "npc_finish");
-        if (nlog != (int64_t)ps[0].submitted.size()) throw std::runtime_error("locus log length mismatch");
+        outs[0].rounds = *std::max_element(rounds.begin(), rounds.end());
+        outs[0].devices = D;
+        if (D == 1) {
+            Dev &v = devs[0];
+            logs[0].resize(v.submitted.size());
+            int64_t nlog = 0;
+            v.ctx.ck(npc_finish(v.ctx.h, scores[0]->offset, outs[0].scores.data(), &outs[0].nloci, logs[0].data(), (int64_t)logs[0].size(), &nlog), "npc_finish");
+            if (nlog != (int64_t)v.submitted.size()) throw std::runtime_error("locus log length mismatch");
+            order[0] = v.submitted;
+        } else {
+            std::vector<npc_ctx *> hs(D);
+            for (int d = 0; d < D; d++) hs[d] = devs[d].ctx.h;
+            const double off = scores[0]->offset;
+            devs[0].ctx.ck(npc_reduce(hs.data(), D, &off, outs[0].scores.data(), &outs[0].nloci), "npc_reduce");
+            std::vector<double> scratch((size_t)std::max<int64_t>(n, 1));
+            for (int d = 0; d < D; d++) {
+                Dev &v = devs[d];
+                std::vector<npc_locus> lg(v.submitted.size());
+                int64_t nlog = 0, nl = 0;
+                v.ctx.ck(npc_partial(v.ctx.h, scratch.data(), &nl, lg.data(), (int64_t)lg.size(), &nlog), "npc_partial");
+                if (nlog != (int64_t)v.submitted.size()) throw std::runtime_error("locus log length mismatch");
+                logs[0].insert(logs[0].end(), lg.begin(), lg.end());
+                order[0].insert(order[0].end(), v.submitted.begin(), v.submitted.end());
+            }
+        }
     } else {
-        flush_stage();
+        Dev &v = devs[0];
+        flush_stage(v);
         std::vector<const npc_row *> rows(S);
         std::vector<int64_t> n_rows(S), nloci(S);
         std::vector<double> offsets(S);
         std::vector<double *> sc(S);
         std::vector<npc_locus *> lg(S);
         for (int k = 0; k < S; k++) {
-            collect_rows(k, true);
+            collect_rows(k, 0, true, ps[k].rows, order[k]);
             rows[k] = ps[k].rows.data(); n_rows[k] = (int64_t)ps[k].rows.size(); offsets[k] = scores[k]->offset;
             outs[k].scores.assign(n, 0.0); sc[k] = outs[k].scores.data();
             logs[k].resize(ps[k].rows.size()); lg[k] = logs[k].data();
-            outs[k].rounds = 1;
+            outs[k].rounds = 1; outs[k].devices = 1;
         }
-        ctx.ck(npc_score_resident_multi(ctx.h, S, rows.data(), n_rows.data(), offsets.data(), sc.data(), nloci.data(), lg.data()),
-               "npc_score_resident_multi");
+        v.ctx.ck(npc_score_resident_multi(v.ctx.h, S, rows.data(), n_rows.data(), offsets.data(), sc.data(), nloci.data(), lg.data()),
+                 "npc_score_resident_multi");
         for (int k = 0; k < S; k++) outs[k].nloci = nloci[k];
     }
     timer.mark("score + finish (GPU)");
     for (int k = 0; k < S; k++) {
         outs[k].loci.assign(scores[k]->entries.size(), npc_locus());
-        for (size_t j = 0; j < ps[k].submitted.size(); j++) outs[k].loci[ps[k].submitted[j]] = logs[k][j];
+        for (size_t j = 0; j < order[k].size(); j++) outs[k].loci[order[k][j]] = logs[k][j];
         outs[k].warnings = make_warnings(*scores[k], *ps[k].M, outs[k].loci, n, p);
     }
     timer.mark("WARN lines (binomial tests)");

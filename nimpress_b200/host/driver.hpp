@@ -25,6 +25,7 @@ struct ScoreParams {
     bool ignorefilt = false;               // --ignorefilt
     bool use_cov = false;                  // --cov given (restrictToCoveredRgns)
     int device = 0;                        // CUDA device (not a reference option)
+    std::vector<int> devices;              // several GPUs: the score rows are split into contiguous ranges, one per device (empty: `device`)
     bool exact_order = false;              // npc_set_exact_order: bit-for-bit reference summation order
 };
 
@@ -34,6 +35,7 @@ struct ScoreResult {
     std::vector<npc_locus> loci;           // per score row, score-file order
     int64_t nloci = 0;
     std::string warnings;                  // the "WARN ..." lines the reference logs, in its order
+    int64_t devices = 1;                   // GPUs that scored (npc_reduce combined their partial sums when > 1)
     int64_t records_read = 0, records_matched = 0, rounds = 0, index_seeks = 0;   // index_seeks > 0: the .tbi / .csi index was used
 };
 

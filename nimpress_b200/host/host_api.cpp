@@ -22,6 +22,7 @@ static ScoreParams to_params(const nph_params *p) {
     q.imp_locus = p->imp_locus; q.imp_missing = p->imp_missing; q.imp_sample = p->imp_sample;
     q.ignorefilt = p->ignorefilt != 0; q.use_cov = p->use_cov != 0; q.device = p->device; q.exact_order = p->exact_order != 0;
     q.mincs = p->mincs; q.maxmis = p->maxmis; q.afmisp = p->afmisp;
+    for (int d = 0; d < 32; d++) if (((uint32_t)p->device_mask >> d) & 1u) q.devices.push_back(d);
     return q;
 }
 
@@ -111,6 +112,7 @@ int64_t nph_result_n_samples(const nph_result *r) { return (int64_t)r->r.scores.
 int64_t nph_result_n_loci(const nph_result *r) { return (int64_t)r->r.loci.size(); }
 int64_t nph_result_nloci_used(const nph_result *r) { return r->r.nloci; }
 int64_t nph_result_rounds(const nph_result *r) { return r->r.rounds; }
+int64_t nph_result_devices(const nph_result *r) { return r->r.devices; }
 int64_t nph_result_records_read(const nph_result *r) { return r->r.records_read; }
 int64_t nph_result_index_seeks(const nph_result *r) { return r->r.index_seeks; }
 const double *nph_result_scores(const nph_result *r) { return r->r.scores.data(); }
@@ -257,6 +259,9 @@ static const char *USAGE =
     "                     mismatch [default: 0.001].\n"
     "  --ignorefilt       Ignore the VCF FILTER field.\n"
     "  --device=<n>       CUDA device to score on [default: 0] (not a reference option).\n"
+    "  --devices=<list>   Several CUDA devices, e.g. 0-7 or 0,2,3: the score file is split into\n"
+    "                     contiguous ranges, one per device, and the partial sums are combined\n"
+    "                     in range order (not a reference option).\n"
     "  --exact-order      Add every locus to the running sums in score-file order, bit for bit\n"
     "                     like the reference (default: sum tiles of four loci first; same\n"
     "                     products, scores equal to ~1e-15 relative) (not a reference option).\n";
@@ -265,6 +270,24 @@ static int parse_enum(const std::string &v, std::initializer_list<const char *> 
     int i = 0;
     for (const char *nm : names) { if (v == nm) return i; i++; }
     throw InputError("invalid enum value: " + v);
+}
+
+// "0-3", "0,2,5", "1" -> bit mask of CUDA devices
+static uint32_t parse_device_list(const std::string &v) {
+    uint32_t mask = 0;
+    for (size_t a = 0; a <= v.size();) {
+        size_t b = v.find(',', a);
+        if (b == std::string::npos) b = v.size();
+        const std::string item = v.substr(a, b - a);
+        const size_t dash = item.find('-');
+        const int64_t lo = parse_int_nim(dash == std::string::npos ? item : item.substr(0, dash), "--devices");
+        const int64_t hi = dash == std::string::npos ? lo : parse_int_nim(item.substr(dash + 1), "--devices");
+        if (lo < 0 || hi > 31 || hi < lo) throw InputError("--devices: device indices are 0..31, ranges lo-hi");
+        for (int64_t d = lo; d <= hi; d++) mask |= 1u << d;
+        a = b + 1;
+    }
+    if (!mask) throw InputError("--devices: empty list");
+    return mask;
 }
 
 // WARN lines, then one `name<TAB>$score` line per sample (:752-753), formatted into one buffer
@@ -307,6 +330,7 @@ int nph_main(int argc, char **argv) {
             else if (is("--maxmis")) p.maxmis = parse_float_nim(val("--maxmis"), "--maxmis");
             else if (is("--mincs")) p.mincs = parse_int_nim(val("--mincs"), "--mincs");
             else if (is("--afmisp")) p.afmisp = parse_float_nim(val("--afmisp"), "--afmisp");
+            else if (is("--devices")) p.device_mask = (int32_t)parse_device_list(val("--devices"));
             else if (is("--device")) p.device = (int)parse_int_nim(val("--device"), "--device");
             else if (a == "--ignorefilt") p.ignorefilt = 1;
             else if (a == "--exact-order") p.exact_order = 1;

@@ -66,6 +66,28 @@ def params(imp_locus="ps", imp_missing="homref", imp_sample="int_ps", maxmis=0.0
                   int(skip_aftest), int(mincs), float(maxmis), float(afmisp))
 
 
+def abs_floor(betas, nloci):
+    """Absolute part of the score tolerance for paths that add the reference's rounded products in another
+    association: 8 * eps * sum|beta| / nloci.  Every term of a sample's sum is at most 2*|beta| in magnitude
+    and the sum is divided by 2*nloci, so this is eight roundings of the largest value a normalised partial
+    sum can take -- the scale of the arithmetic, not a constant."""
+    b = np.asarray(betas, dtype=np.float64)
+    b = b[np.isfinite(b)]
+    return 8.0 * np.finfo(np.float64).eps * float(np.abs(b).sum()) / max(int(nloci), 1)
+
+
+def _score_file_betas(path):
+    out = []
+    for ln in open(path).read().split("\n")[5:]:
+        f = ln.rstrip().split("\t")
+        if len(f) >= 5:
+            try:
+                out.append(float(f[4]))
+            except ValueError:
+                pass
+    return out
+
+
 def format_float(v):
     b = C.create_string_buffer(64)
     lib().orc_format_float(float(v), b, 64)
@@ -86,7 +108,8 @@ def compute_scores_files(score, vcf, bed=None, cap_samples=1 << 20, cap_loci=1 <
     if rc:
         raise RuntimeError(f"oracle rc={rc}")
     return dict(scores=scores[:n.value].copy(), loci=loci[:nl.value].copy(), nloci=used.value,
-                warn=warn.value.decode(), samples=names.value.decode().split("\n")[:n.value])
+                warn=warn.value.decode(), samples=names.value.decode().split("\n")[:n.value],
+                abs_floor=abs_floor(_score_file_betas(score), used.value))
 
 
 def score_matrix(gt, n_samples, ploidy, rows, offset=0.0, threads=1, **kw):
@@ -104,7 +127,7 @@ def score_matrix(gt, n_samples, ploidy, rows, offset=0.0, threads=1, **kw):
                                 loci.ctypes.data, C.byref(used))
     if rc:
         raise RuntimeError(f"oracle rc={rc}")
-    return dict(scores=scores, loci=loci, nloci=used.value)
+    return dict(scores=scores, loci=loci, nloci=used.value, abs_floor=abs_floor(rows["beta"], used.value))
 
 
 def synth_fill(gt, n_samples, v0, seed, af_thr16, miss_thr24, alt_code):

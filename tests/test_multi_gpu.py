@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import orc
-from util_cohort import assert_loci_equal, bits, random_cohort, random_rows
+from util_cohort import assert_loci_equal, bits, random_cohort, random_rows, score_excess
 from util_files import derive_scores, make_dataset, write_score
 from util_bcf import write_bcf, write_vcf
 from util_vcf import read_score
@@ -44,7 +44,7 @@ def check(got, want, exact, rtol=1e-12):
     if exact:
         assert np.array_equal(bits(a[ok]), bits(b[ok]))
     else:
-        assert np.all(np.abs(a[ok] - b[ok]) <= rtol * np.maximum(np.abs(b[ok]), 1e-3))
+        assert score_excess(a, b, want, rtol) <= 1.0
     assert got.warnings == want["warn"]
 
 
@@ -157,9 +157,9 @@ def check_lists(got, gt, n, lists, offs, exact, rtol, threads=1, **pol):
         if exact:
             assert np.array_equal(bits(a[ok]), bits(b[ok]))
         elif ok.any():
-            dev = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-3)
-            worst = max(worst, float(dev.max()))
-            assert dev.max() <= rtol, (k, dev.max())
+            ex = score_excess(a, b, want, rtol)
+            worst = max(worst, ex * rtol)
+            assert ex <= 1.0, (k, ex)
     return worst
 
 
@@ -339,7 +339,7 @@ def test_multi_variant_shards_combine(nb, mode, monkeypatch):
         a, b = sc, want["scores"]
         assert np.array_equal(np.isnan(a), np.isnan(b))
         ok = np.isfinite(b)
-        assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(np.abs(b[ok]), 1e-3))
+        assert score_excess(a, b, want) <= 1.0
 
 
 @pytest.mark.parametrize("parts", ["2", "3", "7"])
