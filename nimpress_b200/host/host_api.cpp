@@ -1,5 +1,6 @@
 // host_api.cpp -- C ABI of libnimpress_host.so (include/nimpress_host.h) and the command line.
 #include <cstring>
+#include <unistd.h>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -343,7 +344,8 @@ int nph_main(int argc, char **argv) {
         std::cerr << e.what() << "\n" << "Usage:\n  nimpress [options] <scoredef> <genotypes.vcf>\n";
         return 1;
     }
-    if (pos[0].find(',') != std::string::npos) {            // several score files, one pass (not a reference feature)
+    // several score files, one pass (not a reference feature) -- unless the whole argument names a file, as it would for the reference
+    if (pos[0].find(',') != std::string::npos && access(pos[0].c_str(), F_OK) != 0) {
         std::vector<std::string> paths;
         for (size_t a = 0; a <= pos[0].size();) { size_t b = pos[0].find(',', a); if (b == std::string::npos) b = pos[0].size(); if (b > a) paths.push_back(pos[0].substr(a, b - a)); a = b + 1; }
         std::vector<const char *> cp;

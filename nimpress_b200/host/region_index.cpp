@@ -109,7 +109,11 @@ uint64_t RegionIndex::query_start(int ref, int64_t beg0, int64_t end0) const {
         while (w > 0 && R.ioff[w] == 0) w--;
         if (R.ioff[w] != 0) return R.ioff[w];
         uint64_t first = NONE;                                      // nothing before either: the first chunk of the contig
-        for (const auto &kv : R.bins) for (const auto &ch : kv.second.chunks) first = std::min(first, ch.first);
+        const uint32_t meta_bin = ((1u << (3 * (depth_ + 1))) - 1u) / 7u + 1u;   // 37450 for depth 5: its "chunks" are record counts, not offsets
+        for (const auto &kv : R.bins) {
+            if (kv.first == meta_bin) continue;
+            for (const auto &ch : kv.second.chunks) first = std::min(first, ch.first);
+        }
         return first;
     }
     // CSI (htslib hts_itr_query): the lower bound comes from the loffset of the deepest bin containing beg

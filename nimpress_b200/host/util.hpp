@@ -1,6 +1,7 @@
 // util.hpp -- small string / number helpers that mirror the Nim stdlib calls the reference makes
 // (strip(leading=false), split('\t'), parseFloat, parseInt, `$`(float)).
 #pragma once
+#include <cctype>
 #include <charconv>
 #include <cstring>
 #include <cmath>
@@ -43,6 +44,14 @@ inline std::vector<std::string> split_char(const std::string &s, char sep) {
 // Nim parseFloat: the whole string, "nan"/"inf" spellings accepted, else ValueError
 inline double parse_float_nim(const std::string &s, const char *what) {
     if (s.empty()) throw InputError(std::string("invalid float (empty): ") + what);
+    // strtod takes more than Nim's parseFloat does: leading white space, hex floats (0x1p3), nan(chars)
+    {
+        const unsigned char c0 = (unsigned char)s[0];
+        bool bad = isspace(c0) != 0;
+        for (size_t i = 0; i + 1 < s.size() && !bad; i++)
+            if ((s[i] == '0' && (s[i + 1] == 'x' || s[i + 1] == 'X')) || s[i] == '(') bad = true;
+        if (bad) throw InputError("invalid float: " + s + " (" + what + ")");
+    }
     char *end = nullptr;
     double v = std::strtod(s.c_str(), &end);
     if (end == s.c_str() || *end) throw InputError("invalid float: " + s + " (" + what + ")");
@@ -50,7 +59,7 @@ inline double parse_float_nim(const std::string &s, const char *what) {
 }
 
 inline int64_t parse_int_nim(const std::string &s, const char *what) {
-    if (s.empty()) throw InputError(std::string("invalid integer (empty): ") + what);
+    if (s.empty() || isspace((unsigned char)s[0])) throw InputError(std::string("invalid integer: '") + s + "' (" + what + ")");
     char *end = nullptr;
     long long v = std::strtoll(s.c_str(), &end, 10);
     if (end == s.c_str() || *end) throw InputError("invalid integer: " + s + " (" + what + ")");

@@ -74,7 +74,7 @@ private:
             else {
                 bsize = (size_t)(hdr[16] | (hdr[17] << 8)) + 1;
                 const size_t xlen = (size_t)(hdr[10] | (hdr[11] << 8));
-                if (bsize < 12 + xlen + 8) err = "BGZF: bad block size";
+                if (xlen < 6 || bsize < 12 + xlen + 8) err = "BGZF: bad block size";      // xlen < 6: no room for the BC subfield we just read
                 else {
                     const size_t rest = bsize - 18;                 // remaining extra fields + deflate data + CRC32 + ISIZE
                     if (s.in.size() < rest + 16) s.in.resize(std::max<size_t>(rest + 16, (1 << 16) + 64));   // + the decoder's read-ahead
@@ -827,6 +827,19 @@ bool VariantSource::use_regions(const std::unordered_map<std::string, std::vecto
             est += std::max<int64_t>(c1 - c0, 0) + (64 << 10);
         }
         if (est * 8 > in->file_size()) { index_.reset(); return false; }
+    }
+    // The pass below walks the regions in header-contig order and only ever seeks forward.  htslib merely
+    // requires each contig's records to be contiguous, so a file may hold its contig blocks in another order
+    // than its header names them (and index fine): the regions' first records must then be visited in FILE
+    // order, which the rank-ordered walk cannot do -- stream such a file instead of silently missing loci.
+    {
+        uint64_t last = 0;
+        for (const Region &r : merged) {
+            const uint64_t v0 = index_->query_start(r.ref, r.beg0, r.end0);
+            if (v0 == RegionIndex::NONE) continue;
+            if (v0 < last) { index_.reset(); return false; }
+            last = v0;
+        }
     }
     regions_ = std::move(merged);
     region_ = 0; filtering_ = true; positioned_ = false;

@@ -481,3 +481,79 @@ def test_stale_index_is_not_used(api, tmp_path, monkeypatch):
     os.utime(d["bcf"], (st.st_atime + 100, st.st_mtime + 100))           # data "modified" after the index was made
     k, e, nrec, seeks = plan_indexed(api, str(sparse), d["bcf"])
     assert seeks == 0 and nrec == len(d["records"])
+
+
+def test_index_with_contig_blocks_out_of_header_order(api, tmp_path, monkeypatch):
+    """htslib only requires each contig's records to be contiguous: a file may hold its contig blocks in another
+    order than its header lists them, and index fine.  The index-driven pass walks contigs in header order and
+    only seeks forward, so such a file is streamed instead (round-1 advisor finding: its loci on the later-named,
+    earlier-stored contig came back ABSENT)."""
+    import util_bcf
+    from util_bcf import write_bcf, write_vcf
+    monkeypatch.setattr(util_bcf, "INDEX_BLOCK", 1500)
+    monkeypatch.setenv("NIMPRESS_FORCE_INDEX", "1")
+    rng = np.random.default_rng(21)
+    n = 5
+    samples = [f"s{i}" for i in range(n)]
+    g = lambda: ((rng.integers(0, 2, size=(n, 2)) + 1) << 1).astype(np.int8)
+    recs = []
+    for c in ("chr2", "chr1"):                                 # file order: chr2's block first
+        for p in range(1000, 400000, 900):
+            recs.append(dict(contig=c, pos=p, ref="A", alts=["C"], filter="PASS", gt=g()))
+    vcf, bcf = str(tmp_path / "p.vcf.gz"), str(tmp_path / "p.bcf")
+    write_vcf(vcf, samples, recs, contigs=["chr1", "chr2"], compress="bgzf", index="tbi")
+    write_bcf(bcf, samples, recs, ["chr1", "chr2"], index=True)
+    ents = [("chr1", 1000, "A", "C"), ("chr1", 300700, "A", "C"), ("chr2", 1900, "A", "C"), ("chr2", 399700, "A", "A"), ("chr2", 5, "A", "C")]
+    sc = tmp_path / "p.score"
+    sc.write_text("x\nd\nc\nhs37d5\n0\n" + "\n".join(f"{c}\t{p}\t{r}\t{e}\t0.1\t0.2" for c, p, r, e in ents) + "\n")
+    for f in (vcf, bcf):
+        rc, kind, ea, _ = plan(api, str(sc), f)
+        k2, e2, nrec, seeks = plan_indexed(api, str(sc), f)
+        assert rc == 0 and list(kind) == [0, 0, 0, 0, 2], (f, kind)
+        assert np.array_equal(kind, k2) and np.array_equal(ea, e2), (f, kind, k2)
+    # one contig only: the index is still used
+    sc1 = tmp_path / "p1.score"
+    sc1.write_text("x\nd\nc\nhs37d5\n0\n" + "\n".join(f"{c}\t{p}\t{r}\t{e}\t0.1\t0.2" for c, p, r, e in ents[:2]) + "\n")
+    k2, e2, nrec, seeks = plan_indexed(api, str(sc1), bcf)
+    assert list(k2) == [0, 0] and seeks > 0
+
+
+def test_malformed_bgzf_extra_field_is_rejected(api, tmp_path):
+    """A BGZF header claiming XLEN < 6 while carrying the BC subfield (round-1 advisor finding: the pool's reader
+    underflowed `xlen - 6` and read before its buffer): the file must be refused, not read."""
+    import struct
+    import zlib
+    payload = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts0\n1\t5\t.\tA\tC\t.\tPASS\t.\tGT\t0/1\n"
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = co.compress(payload) + co.flush()
+    for xlen in (0, 2, 5):
+        bsize = 18 + len(body) + 8 - 1
+        hdr = b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\x00\xff" + struct.pack("<H", xlen) + b"BC" + struct.pack("<HH", 2, bsize)
+        blk = hdr + body + struct.pack("<II", zlib.crc32(payload), len(payload))
+        f = tmp_path / f"bad{xlen}.vcf.gz"
+        f.write_bytes(blk + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+        sc = tmp_path / "s.score"
+        sc.write_text("x\nd\nc\nhs37d5\n0\n1\t5\tA\tC\t0.1\t0.2\n")
+        kind = np.zeros(4, np.int32); ea = np.zeros(4, np.int32)
+        nr, ns = C.c_int64(), C.c_int64()
+        L = api.load_host_library()
+        p = api._Params(0, 0, 3, 0, 0, 0, 0, 0, 100, 0.05, 0.001)
+        rc = L.nph_plan(os.fsencode(str(sc)), os.fsencode(str(f)), None, C.byref(p), kind.ctypes.data, ea.ctypes.data, 4, C.byref(nr), C.byref(ns))
+        assert rc != 0, xlen                                  # an error code, not a crash and not a silent read
+
+
+def test_score_fields_are_parsed_as_strictly_as_nim(api, tmp_path):
+    """strtod / strtoll accept what Nim's parseFloat / parseInt raise ValueError on: leading blanks, hex floats,
+    nan(...).  Such score files must fail like the reference instead of scoring."""
+    d = tmp_path
+    (d / "v.vcf").write_text("##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts0\n1\t5\t.\tA\tC\t.\tPASS\t.\tGT\t0/1\n")
+    good = "x\nd\nc\nhs37d5\n0\n1\t5\tA\tC\t0.1\t0.2\n"
+    for bad in (good.replace("0.1", "0x1p-3"), good.replace("0.1", " 0.1"), good.replace("0.2", "nan(7)"), good.replace("\t5\t", "\t 5\t"),
+                good.replace("hs37d5\n0\n", "hs37d5\n 0\n")):
+        sc = d / "b.score"
+        sc.write_text(bad)
+        rc = plan(api, str(sc), str(d / "v.vcf"))[0]
+        assert rc == -3, (bad, rc)
+    sc = d / "g.score"
+    sc.write_text(good.replace("0.2", "nan"))
+    assert plan(api, str(sc), str(d / "v.vcf"))[0] == 0
