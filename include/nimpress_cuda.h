@@ -43,6 +43,7 @@
  *   NPC_MULTI=0 | 1          npc_score_resident_multi: never / always the tensor-core contraction (default: >= 3 definitions)
  *   NPC_MULTI_PARTS=<n>      split of a tile's entry range over work units in the contraction (default: chosen from the tile count)
  *   NPC_TIMING=1             phase wall times of npc_score_resident_multi on stderr
+ *   NPC_TRACE=1              keep %globaltimer stamps of the tile kernel's CTA 0 (npc_trace)
  */
 #ifndef NIMPRESS_CUDA_H
 #define NIMPRESS_CUDA_H
@@ -272,6 +273,18 @@ int64_t npc_multi_contractions(const npc_ctx *ctx);
  * other ploidy) kernels and the split count/accumulate calls are always exact. */
 int npc_set_exact_order(npc_ctx *ctx, int32_t on);
 
+/* FORMAT/DS rows instead of hard calls (NOT in the reference, which reads GT only --
+ * src/nimpress.nim:384 -- and lists dosage input under "Future", README.md:162-165).  The context must
+ * have been created with ploidy = 1, gt_width = 4: a row is n_samples BCF floats, the expected dosage of
+ * the ALT allele (missing 0x7F800001, vector_end 0x7F800002 and NaN = no call).  Raw dosage = ds for
+ * eaidx 1, 2 - ds for eaidx 0; everything after that is the reference's logic on a real-valued dosage:
+ * tallies (npc_locus.neff then holds the IEEE-754 bits of the fp64 sum of called dosages, added in the
+ * fixed order npc_dosage.cuh defines), --maxmis, locus / sample imputation, scores[s] += fl(d*beta) in
+ * score-row order.  All npc_score_block* / npc_score_resident calls then take such rows; the split
+ * count / accumulate calls and npc_score_resident_multi's contraction do not (the latter scores one by
+ * one). */
+int npc_set_dosage_rows(npc_ctx *ctx, int32_t on);
+
 /* Which kernels npc_score_block* uses for this context: shape[0] = 2 for the fused tile kernel in
  * its default mode, 1 in exact-order mode (int8 diploid cohorts that fit one resident pass),
  * 0 for the count/decide/accumulate sequence; then grid (tile kernel: sample slabs * 1000 + row
@@ -279,6 +292,10 @@ int npc_set_exact_order(npc_ctx *ctx, int32_t on);
  * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + decider warps, dynamic
  * shared-memory bytes. */
 int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
+/* NPC_TRACE=1 at npc_create: %globaltimer stamps (ns) of CTA 0 of the last tile-kernel launch -- launch start, code
+ * tables ready, first tile counted, last tile counted, last tile accumulated, sums stored -- for the launch-floor
+ * analysis of short launches (profiles/). */
+int npc_trace(npc_ctx *ctx, uint64_t out[8]);
 /* ---- utilities (tests / bench) ----------------------------------------------------------- */
 
 /* Deterministic synthetic cohort written straight into device memory: int8 diploid GT rows

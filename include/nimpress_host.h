@@ -56,6 +56,9 @@ typedef struct {
     int64_t mincs;
     double  maxmis;
     double  afmisp;
+    int32_t use_ds;         /* 1: score FORMAT/DS (fp32 expected ALT dosage, biallelic effect alleles) instead of FORMAT/GT --
+                               npc_set_dosage_rows; not in the reference (README.md:162-165 "Future") */
+    int32_t reserved;
 } nph_params;
 
 typedef struct nph_result nph_result;

@@ -51,7 +51,8 @@ class _Params(C.Structure):
     _fields_ = [("imp_locus", C.c_int32), ("imp_missing", C.c_int32), ("imp_sample", C.c_int32),
                 ("ignorefilt", C.c_int32), ("use_cov", C.c_int32), ("device", C.c_int32),
                 ("exact_order", C.c_int32), ("device_mask", C.c_int32),
-                ("mincs", C.c_int64), ("maxmis", C.c_double), ("afmisp", C.c_double)]
+                ("mincs", C.c_int64), ("maxmis", C.c_double), ("afmisp", C.c_double),
+                ("use_ds", C.c_int32), ("reserved", C.c_int32)]
 
 
 _host = None
@@ -142,13 +143,13 @@ class Result:
 
 def run(score_path, genotype_path, bed_path=None, imp_locus=ImputeMethodLocus.ps, imp_missing=ImputeMethodMissing.homref,
         imp_sample=ImputeMethodSample.int_ps, maxmis=0.05, afmisp=0.001, mincs=100, ignorefilt=False, device=0,
-        exact_order=False, devices=None):
+        exact_order=False, devices=None, dosage=False):
     """nph_compute_polygenic_scores -> Result (scores, per-locus records, WARN text).  devices: list of CUDA
     device indices to split the score rows over (npc_reduce combines their partial sums)."""
     L = load_host_library()
     mask = sum(1 << int(d) for d in set(devices)) if devices else 0
     p = _Params(int(imp_locus), int(imp_missing), int(imp_sample), int(ignorefilt), int(bed_path is not None), device,
-                int(bool(exact_order)), mask, int(mincs), float(maxmis), float(afmisp))
+                int(bool(exact_order)), mask, int(mincs), float(maxmis), float(afmisp), int(bool(dosage)), 0)
     h = C.c_void_p()
     rc = L.nph_compute_polygenic_scores(os.fsencode(score_path), os.fsencode(genotype_path),
                                         os.fsencode(bed_path) if bed_path else None, C.byref(p), C.byref(h))

@@ -15,6 +15,7 @@
 #include "npc_fused5.cuh"
 #include "npc_multi.cuh"
 #include "npc_reduce.cuh"
+#include "npc_dosage.cuh"
 
 using namespace npc;
 
@@ -59,11 +60,18 @@ struct npc_ctx {
     int64_t slab_stride = 0;
     int64_t slab_rows = 0;
     cudaEvent_t ev_slab = nullptr;          // last scoring launch that read the slab
-    ull *d_fcounts = nullptr;               // [max_rows] arrivals | nmiss | neff words of the fused kernel
+    ull *d_fcounts = nullptr;               // [2][max_rows] arrivals | nmiss | neff words of the fused kernel: a double buffer, each launch
+                                            // clears the half the next one uses (pair kernel)
+    int fcounts_half = 0;
+    int64_t fcounts_dirty[2] = { 0, 0 };    // words of each half written since it was last cleared
+    ull *d_trace = nullptr;                 // NPC_TRACE: 8 %globaltimer stamps of the last pair-kernel launch
     uint8_t *d_multi_scratch = nullptr;     // arena of npc_score_resident_multi's contraction
     size_t multi_scratch_bytes = 0;
     bool multi_attr_set = false;
     int64_t multi_contractions = 0;         // npc_score_resident_multi calls served by the tensor-core contraction
+    // FORMAT/DS rows (npc_dosage.cuh): fp32 dosages, one per sample
+    bool ds = false;
+    double *d_ds_part = nullptr;            // [max_rows][n_blocks] block sums of the tally pass
     // cross-GPU combine (npc_reduce.cuh)
     cudaEvent_t ev_reduce = nullptr;        // "this context's partial sums are final"
     ull *d_nloci_total = nullptr;           // combined nloci, next to d_out (the combined scores)
@@ -105,10 +113,10 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_trace); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
     if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->ev_reduce) cudaEventDestroy(ctx->ev_reduce);
-    cudaFree(ctx->d_nloci_total); cudaFree(ctx->d_bridge); cudaFree(ctx->d_gather);
+    cudaFree(ctx->d_nloci_total); cudaFree(ctx->d_bridge); cudaFree(ctx->d_gather); cudaFree(ctx->d_ds_part);
     if (ctx->comm && g_nccl.lib) g_nccl.CommDestroy(ctx->comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -194,7 +202,12 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, ex != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
         if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     }
-    if (c->fast.ok || c->exact_cfg.ok) NPC_CUDA(c, cudaMalloc(&c->d_fcounts, (size_t)std::max<int64_t>(c->max_rows, 1) * sizeof(ull)));
+    if (c->fast.ok || c->exact_cfg.ok) {
+        const size_t words = 2 * (size_t)std::max<int64_t>(c->max_rows, 1);
+        NPC_CUDA(c, cudaMalloc(&c->d_fcounts, words * sizeof(ull)));
+        NPC_CUDA(c, cudaMemset(c->d_fcounts, 0, words * sizeof(ull)));
+        if (env_int("NPC_TRACE", 0)) { NPC_CUDA(c, cudaMalloc(&c->d_trace, 8 * sizeof(ull))); NPC_CUDA(c, cudaMemset(c->d_trace, 0, 8 * sizeof(ull))); }
+    }
     if (c->fast.ok && c->fast.Gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(c->fast.Gr - 1) * (size_t)c->n * sizeof(double)));
     c->exact = env_int("NPC_EXACT", 0) != 0;
     return NPC_OK;
@@ -304,6 +317,15 @@ extern "C" int npc_reset(npc_ctx *ctx) {
 extern "C" int64_t npc_launch_count(const npc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int64_t npc_multi_contractions(const npc_ctx *ctx) { return ctx ? ctx->multi_contractions : 0; }
 
+extern "C" int npc_trace(npc_ctx *ctx, uint64_t out[8]) {
+    if (!ctx || !out) return NPC_EINVAL;
+    if (!ctx->d_trace) return fail(ctx, NPC_ESTATE, "npc_trace: set NPC_TRACE=1 before npc_create");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    NPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NPC_CUDA(ctx, cudaMemcpy(out, ctx->d_trace, 8 * sizeof(ull), cudaMemcpyDeviceToHost));
+    return NPC_OK;
+}
+
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!ctx || !shape) return NPC_EINVAL;
     const npc_ctx::TileCfg &t = ctx->exact ? ctx->exact_cfg : ctx->fast;
@@ -311,6 +333,14 @@ extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!t.ok) return NPC_OK;
     shape[0] = ctx->exact ? 1 : 2; shape[1] = t.Gs * 1000 + (ctx->exact ? 1 : t.Gr); shape[2] = t.nc; shape[3] = t.K;
     shape[4] = F4_R; shape[5] = t.Sr * 1000 + t.Sc; shape[6] = t.L * 100 + t.A; shape[7] = (int32_t)t.smem;
+    return NPC_OK;
+}
+
+extern "C" int npc_set_dosage_rows(npc_ctx *ctx, int32_t on) {
+    if (!ctx) return NPC_EINVAL;
+    if (on && (ctx->width != 4 || ctx->ploidy != 1))
+        return fail(ctx, NPC_EINVAL, "npc_set_dosage_rows: create the context with ploidy 1 and gt_width 4 (one fp32 DS value per sample)");
+    ctx->ds = on != 0;
     return NPC_OK;
 }
 
@@ -410,12 +440,23 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
     if (n_rows == 0) return NPC_OK;
     int rc = ensure_log(c, n_rows);
     if (rc) return rc;
-    NPC_CUDA(c, cudaMemsetAsync(c->d_fcounts, 0, n_rows * sizeof(ull), c->stream));
+    const int64_t half_words = std::max<int64_t>(c->max_rows, 1);
+    ull *counts = c->d_fcounts, *counts_next = nullptr;
+    int64_t n_zero = 0;
+    if (t.ver == 5) {                                  // double buffer: this launch clears the words the next one uses
+        counts = c->d_fcounts + (size_t)c->fcounts_half * half_words;
+        counts_next = c->d_fcounts + (size_t)(c->fcounts_half ^ 1) * half_words;
+        n_zero = c->fcounts_dirty[c->fcounts_half ^ 1];
+        c->fcounts_dirty[c->fcounts_half ^ 1] = 0;
+        c->fcounts_dirty[c->fcounts_half] = n_rows;
+        c->fcounts_half ^= 1;
+    } else NPC_CUDA(c, cudaMemsetAsync(c->d_fcounts, 0, n_rows * sizeof(ull), c->stream));
     const int64_t tiles = (n_rows + F4_R - 1) / F4_R;
     const int gr = exact ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(t.Gr, tiles / 16));   // >= 16 tiles per row group
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
-    P.sums = c->d_sums; P.counts = c->d_fcounts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
+    P.sums = c->d_sums; P.counts = counts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
+    P.counts_next = counts_next; P.n_zero = n_zero; P.trace = c->d_trace;
     P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
     P.Gs = t.Gs; P.Gr = gr; P.partials = c->d_partials;
     P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
@@ -431,7 +472,36 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
     return NPC_OK;
 }
 
+// FORMAT/DS rows: tally pass (block sums + missing counts), decide, accumulate in row order
+static int launch_dosage(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
+    if (n_rows == 0) return NPC_OK;
+    int rc = ensure_log(c, n_rows);
+    if (rc) return rc;
+    const int64_t n_blocks = std::max<int64_t>((c->n + DS_BLOCK - 1) / DS_BLOCK, 1);
+    if (!c->d_ds_part) NPC_CUDA(c, cudaMalloc(&c->d_ds_part, (size_t)std::max<int64_t>(c->max_rows, 1) * (size_t)n_blocks * sizeof(double)));
+    NPC_CUDA(c, cudaMemsetAsync(c->d_counts, 0, n_rows * sizeof(ull), c->stream));
+    if (c->n) {
+        for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {
+            const int64_t nr = std::min<int64_t>(65535, n_rows - r0);
+            k_count_ds<<<dim3((unsigned)((n_blocks + 7) / 8), (unsigned)nr), 256, 0, c->stream>>>(gt, row_stride, d_rows + r0, c->n, n_blocks,
+                                                                                               c->d_ds_part + r0 * n_blocks, c->d_counts + r0);
+            c->launches++;
+        }
+    }
+    k_decide_ds<<<(unsigned)((n_rows + 127) / 128), 128, 0, c->stream>>>(d_rows, n_rows, c->d_ds_part, c->n ? n_blocks : 0, c->d_counts, c->pol, c->n,
+                                                                        c->d_rowp, c->d_log + c->log_len, c->d_nloci);
+    c->launches++;
+    c->log_len += n_rows;
+    if (c->n) {
+        k_accum_ds<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(gt, row_stride, c->d_rowp, n_rows, c->n, c->d_sums);
+        c->launches++;
+    }
+    NPC_CUDA(c, cudaGetLastError());
+    return NPC_OK;
+}
+
 static int launch_block(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
+    if (c->ds) return launch_dosage(c, gt, row_stride, d_rows, n_rows);
     if (c->exact ? c->exact_cfg.ok : c->fast.ok) return launch_fused(c, c->exact ? c->exact_cfg : c->fast, c->exact, gt, row_stride, d_rows, n_rows);
     int rc = launch_count(c, gt, row_stride, d_rows, n_rows, c->d_counts);
     if (rc) return rc;
@@ -498,6 +568,7 @@ extern "C" int npc_count_block_device(npc_ctx *ctx, const void *gt_dev, int64_t 
     int rc = check_block(ctx, gt_dev, row_stride, n_gt_rows, rows, n_rows);
     if (rc) return rc;
     if (!counts_dev) return fail(ctx, NPC_EINVAL, "counts_dev is NULL");
+    if (ctx->ds) return fail(ctx, NPC_EUNSUPPORTED, "the split count / accumulate calls take hard-call (GT) rows only");
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));
     const npc_row *d_rows;
     if ((rc = upload_rows(ctx, rows, n_rows, rows_on_device, &d_rows))) return rc;
@@ -510,6 +581,7 @@ extern "C" int npc_accumulate_block_device(npc_ctx *ctx, const void *gt_dev, int
     int rc = check_block(ctx, gt_dev, row_stride, n_gt_rows, rows, n_rows);
     if (rc) return rc;
     if (!counts_dev) return fail(ctx, NPC_EINVAL, "counts_dev is NULL");
+    if (ctx->ds) return fail(ctx, NPC_EUNSUPPORTED, "the split count / accumulate calls take hard-call (GT) rows only");
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));
     const npc_row *d_rows;
     if ((rc = upload_rows(ctx, rows, n_rows, rows_on_device, &d_rows))) return rc;

@@ -28,6 +28,13 @@ struct FusedParams {
     // > 0 = test, then sleep this many ns.  A suspended try_wait wakes every few dozen cycles and costs
     // ~4 issue slots per wake-up; four such warps take a quarter of an SM's issue bandwidth.
     uint32_t aux_sleep_ns;
+    // pair kernel: the tally words of the NEXT launch (the other half of a double buffer), cleared by this one so
+    // that no memset sits between launches; n_zero words.  nullptr: the caller cleared `counts` itself.
+    ull *counts_next;
+    int64_t n_zero;
+    // NPC_TRACE: %globaltimer stamps of CTA 0 (launch start, tables ready, first tile counted, last tile counted,
+    // last tile accumulated, sums stored), for the low-n launch-floor analysis; nullptr = off
+    ull *trace;
 };
 
 constexpr int FUSED_CNT_BITS = 28;

@@ -60,6 +60,11 @@ struct Fused5Smem {
     }
 };
 
+__device__ __forceinline__ ull globaltimer_ns() {
+    ull t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // dosage code of one sample from its two allele codes (allele+1, 0 = missing): 0, 1, 2 or 3 = missing
 __device__ __forceinline__ uint32_t f5_code(int ca, int cb, int T) {
     if (ca == 0 || cb == 0) return 3u;
@@ -115,20 +120,19 @@ k_fused_pair(const FusedParams P) {
         for (int s = 0; s < Sc; s++) { mbar_init(bar_cnt + 8u * s, NC); mbar_init(bar_lut + 8u * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // pair tables [T-1 (3 = no match)][row parity q][66*c0 + c1 + 4*c2 + 16*c3], c_k the allele code of byte k of
-    // the word (sample 0 = bytes 0,1; sample 1 = bytes 2,3); the six unused entries of a table are never read
-    for (uint32_t i = threadIdx.x; i < F5_NT * 2u * 256u; i += blockDim.x) {
-        const int cc = (int)(i & 255u), q = (int)((i >> 8) & 1u), Tm = (int)(i >> 9);
-        const int T = Tm < 3 ? Tm + 1 : 99;
-        const int c0 = cc & 3, c1 = (cc >> 2) & 3, c2 = (cc >> 4) & 3, c3 = cc >> 6;
-        const uint32_t s0 = f5_code(c0, c1, T), s1 = f5_code(c2, c3, T);
-        reinterpret_cast<uint32_t *>(smem + M.code + (uint32_t)(Tm * 2 + q) * F5_TAB_BYTES)[66 * c0 + c1 + 4 * c2 + 16 * c3] =
-            f5_sample_entry(s0, q, 0) + f5_sample_entry(s1, q, 1);
-    }
     for (uint32_t i = threadIdx.x; i < (uint32_t)Sc * cnt_slot / 4u; i += blockDim.x)
         reinterpret_cast<uint32_t *>(smem + M.cnt)[i] = 0u;
-    for (uint32_t i = threadIdx.x; i < (uint32_t)Sr * R * (uint32_t)P.slab_stride / 16u; i += blockDim.x)
-        reinterpret_cast<uint4 *>(smem + M.data)[i] = make_uint4(0, 0, 0, 0);
+    // Raw ring: the TMA copies write bytes [0, slab_bytes) of a stage row; only the cells past them -- read by the
+    // lanes that own no chunk -- must hold something harmless (zero = "missing", and those lanes' tallies are not
+    // published).  Zeroing just that tail instead of the whole ring takes ~1 us off every launch.
+    {
+        const uint32_t tail16 = ((uint32_t)P.slab_stride - slab_bytes) / 16u;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)Sr * R * tail16; i += blockDim.x)
+            reinterpret_cast<uint4 *>(smem + M.data + (i / tail16) * (uint32_t)P.slab_stride + slab_bytes)[i % tail16] = make_uint4(0, 0, 0, 0);
+    }
+    if (P.counts_next)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_zero; i += (int64_t)gridDim.x * blockDim.x) P.counts_next[i] = 0ull;
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[0] = globaltimer_ns();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
@@ -259,6 +263,20 @@ k_fused_pair(const FusedParams P) {
         }
     } else {
         // ================= consumers ===========================================================
+        // The code tables are the consumers' alone: they build them while the producer's first copies are in
+        // flight, then meet on a named barrier of their own.
+        // pair tables [T-1 (3 = no match)][row parity q][66*c0 + c1 + 4*c2 + 16*c3], c_k the allele code of byte k of
+        // the word (sample 0 = bytes 0,1; sample 1 = bytes 2,3); the six unused entries of a table are never read
+        for (uint32_t i = threadIdx.x; i < F5_NT * 2u * 256u; i += (uint32_t)NC * 32u) {
+            const int cc = (int)(i & 255u), q = (int)((i >> 8) & 1u), Tm = (int)(i >> 9);
+            const int T = Tm < 3 ? Tm + 1 : 99;
+            const int c0 = cc & 3, c1 = (cc >> 2) & 3, c2 = (cc >> 4) & 3, c3 = cc >> 6;
+            const uint32_t s0 = f5_code(c0, c1, T), s1 = f5_code(c2, c3, T);
+            reinterpret_cast<uint32_t *>(smem + M.code + (uint32_t)(Tm * 2 + q) * F5_TAB_BYTES)[66 * c0 + c1 + 4 * c2 + 16 * c3] =
+                f5_sample_entry(s0, q, 0) + f5_sample_entry(s1, q, 1);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");
+        if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1] = globaltimer_ns();
         uint32_t cell[K], tailor[K], cnt_off[K];
         bool own[K];
         int valid[K];
@@ -354,6 +372,7 @@ k_fused_pair(const FusedParams P) {
                 if (lane == 0) { mbar_arrive(bar_rempty + 8u * sr); mbar_arrive(bar_cnt + 8u * sc); }
                 if (++sr == Sr) { sr = 0; ph_r ^= 1u; }
                 if (++sc == Sc) sc = 0;
+                if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (i == 0 || i == nt - 1)) P.trace[i == 0 ? 2 : 3] = globaltimer_ns();
             }
             if (i >= L) {
                 mbar_wait(bar_lut + 8u * sa, ph_a);
@@ -393,6 +412,7 @@ k_fused_pair(const FusedParams P) {
                 if (++sa == Sc) { sa = 0; ph_a ^= 1u; }
             }
         }
+        if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[4] = globaltimer_ns();
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int64_t g = c0 + cell[k];
@@ -400,6 +420,7 @@ k_fused_pair(const FusedParams P) {
             for (int e = 0; e < 8; e++)
                 if (e < valid[k]) sums_out[g * 8 + e] = acc[k][e];
         }
+        if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[5] = globaltimer_ns();
     }
 }
 

@@ -212,8 +212,10 @@ __device__ __forceinline__ bool locus_value(const Policy &p, const npc_row &row,
     return true;
 }
 
-__device__ __forceinline__ void decide_row(const Policy &p, const npc_row &row, ull nmiss_u, ull neff_u,
-                                           int64_t n_local, RowP &out, npc_locus &rec) {
+// neff: the effect-allele tally as the reference holds it, a double (an exact integer for GT rows, a real
+// number for FORMAT/DS rows, npc_dosage.cuh); neff_rec: what the locus record reports for it
+__device__ __forceinline__ void decide_row_real(const Policy &p, const npc_row &row, ull nmiss_u, double neff, long long neff_rec,
+                                                int64_t n_local, RowP &out, npc_locus &rec) {
     const double qnan = __longlong_as_double(0x7FF8000000000000LL);
     out.c0 = out.c1 = out.c2 = out.cm = 0.0;
     out.beta = row.beta; out.eaidx = row.eaidx; out.gt_row = row.gt_row; out.pad = 0;
@@ -231,9 +233,9 @@ __device__ __forceinline__ void decide_row(const Policy &p, const npc_row &row, 
         if (p.imp_missing == NPC_MISSING_HOMREF) { v = row.ref_is_ea ? 2.0 : 0.0; used = constant = true; }
     } else {
         rec.eaidx = row.eaidx;
-        const double nmiss = (double)nmiss_u, neff = (double)neff_u;
+        const double nmiss = (double)nmiss_u;
         const double ngt = (double)(p.n_total - (int64_t)nmiss_u);
-        rec.ngt = p.n_total - (int64_t)nmiss_u; rec.nmiss = (int64_t)nmiss_u; rec.neff = (int64_t)neff_u;
+        rec.ngt = p.n_total - (int64_t)nmiss_u; rec.nmiss = (int64_t)nmiss_u; rec.neff = neff_rec;
         const double missingrate = __ddiv_rn(nmiss, (double)p.n_total);  // :565
         if (missingrate > p.maxmis) {                                    // :566-571
             klass = NPC_CLASS_MAXMIS;
@@ -259,6 +261,11 @@ __device__ __forceinline__ void decide_row(const Policy &p, const npc_row &row, 
     if (constant) out.c0 = __dmul_rn(v, row.beta);
     out.mode = !used ? MODE_SKIP : constant ? MODE_CONST : MODE_DECODE;
     rec.klass = klass; rec.used = used ? 1 : 0; rec.imputed = v;
+}
+
+__device__ __forceinline__ void decide_row(const Policy &p, const npc_row &row, ull nmiss_u, ull neff_u,
+                                           int64_t n_local, RowP &out, npc_locus &rec) {
+    decide_row_real(p, row, nmiss_u, (double)neff_u, (long long)neff_u, n_local, out, rec);
 }
 
 __global__ void __launch_bounds__(128)

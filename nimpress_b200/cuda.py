@@ -80,7 +80,9 @@ def load_library():
         "npc_combined_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "npc_launch_count": (i64, [vp]),
         "npc_kernel_shape": (C.c_int, [vp, C.POINTER(i32 * 8)]),
+        "npc_trace": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "npc_set_exact_order": (C.c_int, [vp, i32]),
+        "npc_set_dosage_rows": (C.c_int, [vp, i32]),
         "npc_synth_fill_device": (C.c_int, [vp, vp, i64, i64, i64, C.c_uint64, vp, vp, vp]),
         "npc_version": (C.c_int, []),
     }
@@ -151,6 +153,9 @@ class Engine:
 
     def set_exact_order(self, on=True):
         self._ck(self.L.npc_set_exact_order(self.h, int(bool(on))))
+
+    def set_dosage_rows(self, on=True):
+        self._ck(self.L.npc_set_dosage_rows(self.h, int(bool(on))))
 
     def set_cohort_size(self, n_total):
         self._ck(self.L.npc_set_cohort_size(self.h, int(n_total)))
@@ -320,6 +325,11 @@ class Engine:
             d["row_groups"], d["grid"] = d["grid"] % 1000, d["grid"] // 1000
             d["grid"] *= d["row_groups"]
         return d
+
+    def trace(self):
+        a = (C.c_uint64 * 8)()
+        self._ck(self.L.npc_trace(self.h, C.byref(a)))
+        return list(a)
 
     @property
     def launches(self):

@@ -136,6 +136,8 @@ std::string make_warnings(const ScoreFile &score, const Matcher &M, const std::v
             const double missingrate = (double)L.nmiss / (double)n;
             w += "WARN Locus " + span + " has " + format_float_nim(missingrate * 100) +
                  "% of samples missing a genotype. This exceeds the missingness threshold; imputing all dosages at this locus.\n";
+        } else if (p.use_ds) {
+            // dosage rows: the tally is a real number, the reference's exact binomial test is not defined on it
         } else if (!std::isnan(e.eaf) && binom_test(L.neff, (n - L.nmiss) * 2, e.eaf) < p.afmisp) {
             w += "WARN Variant " + id + " cohort EAF is " + format_float_nim((double)L.neff / (double)((n - L.nmiss) * 2)) + " in " +
                  std::to_string(n) + " samples.  This is highly unlikely given polygenic score EAF of " + format_float_nim(e.eaf) + "\n";
@@ -220,6 +222,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             const int64_t launch_rows = std::max<int64_t>(v.block_rows, 32768);
             v.ctx.ck(npc_create2(&v.ctx.h, dev_ids[d], n, ploidy, gt_width, launch_rows, 3, v.block_rows), "npc_create");
             v.ctx.ck(npc_set_policy(v.ctx.h, &pol), "npc_set_policy");
+            if (p.use_ds) v.ctx.ck(npc_set_dosage_rows(v.ctx.h, 1), "npc_set_dosage_rows");
             if (p.exact_order) v.ctx.ck(npc_set_exact_order(v.ctx.h, 1), "npc_set_exact_order");
             v.ctx.ck(npc_reset(v.ctx.h), "npc_reset");
             int64_t slab_want = want;
@@ -311,7 +314,10 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             else {
                 // BCF with the context's layout: the GT payload goes from the inflated blocks straight into the pinned row
                 const bool direct = vcf.load_gt_into(rec, dst, gt_width, ploidy);
-                if (!rec.has_gt || !rec.gt) throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + " has no GT field");
+                if (!rec.has_gt || !rec.gt)
+                    throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + (p.use_ds ? " has no DS field" : " has no GT field"));
+                if (p.use_ds && (rec.ploidy != 1 || rec.gt_width != 4))
+                    throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + ": FORMAT/DS with several values per sample is not supported");
                 if (!direct) {
                     if (rec.ploidy > ploidy || rec.gt_width > gt_width)
                         throw LayoutOverflow{ std::max(rec.gt_width, gt_width), std::max(rec.ploidy, ploidy) };
@@ -324,7 +330,11 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             v.staged++;
         }
         for (int k = 0; k < S; k++) for (int64_t i : ps[k].M->match_last())
-            if (ps[k].M->kind[i] == NPC_KIND_GT) ps[k].slab_row[i] = rec_row[S == 1 ? dev_of(i) : 0];
+            if (ps[k].M->kind[i] == NPC_KIND_GT) {
+                if (p.use_ds && ps[k].M->eaidx[i] > 1)
+                    throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + ": FORMAT/DS rows take the REF or the first ALT as effect allele");
+                ps[k].slab_row[i] = rec_row[S == 1 ? dev_of(i) : 0];
+            }
         for (int d = 0; d < D; d++) if (devs[d].slot >= 0 && devs[d].staged == devs[d].block_rows) flush_stage(devs[d]);
     }
     for (int k = 0; k < S; k++) {
@@ -399,10 +409,12 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
 bool compute_polygenic_scores_multi(const std::vector<const ScoreFile *> &scores, const std::string &genotype_path,
                                     const GenomeIntervals &cov, const ScoreParams &p, std::vector<ScoreResult> &outs) {
     int width = 1, ploidy = 2;                      // BCF's usual GT layout: int8, diploid
+    if (p.use_ds) { width = 4; ploidy = 1; }        // FORMAT/DS: one float per sample
     bool seekable = true;                           // first try the index-driven pass (needs <file>.tbi / .csi)
     for (int attempt = 0; attempt < 6; attempt++) {
         std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path, seekable);
         if (!vcf) return false;
+        vcf->set_dosage_mode(p.use_ds);
         try {
             run_pass(scores, *vcf, genotype_path, seekable, cov, p, width, ploidy, outs);
             return true;

@@ -27,6 +27,7 @@ struct ScoreParams {
     int device = 0;                        // CUDA device (not a reference option)
     std::vector<int> devices;              // several GPUs: the score rows are split into contiguous ranges, one per device (empty: `device`)
     bool exact_order = false;              // npc_set_exact_order: bit-for-bit reference summation order
+    bool use_ds = false;                   // score FORMAT/DS (fp32 expected ALT dosage) instead of FORMAT/GT -- not a reference option
 };
 
 struct ScoreResult {

@@ -24,6 +24,7 @@ static ScoreParams to_params(const nph_params *p) {
     q.ignorefilt = p->ignorefilt != 0; q.use_cov = p->use_cov != 0; q.device = p->device; q.exact_order = p->exact_order != 0;
     q.mincs = p->mincs; q.maxmis = p->maxmis; q.afmisp = p->afmisp;
     for (int d = 0; d < 32; d++) if (((uint32_t)p->device_mask >> d) & 1u) q.devices.push_back(d);
+    q.use_ds = p->use_ds != 0;
     return q;
 }
 
@@ -185,6 +186,7 @@ int nph_read_gt(const char *genotype_path, uint8_t *out, int64_t row_bytes, int6
     try {
         std::unique_ptr<VariantSource> vcf = open_variant_source(genotype_path);
         if (!vcf) return NPH_EOPEN_VCF;
+        if (const char *e = getenv("NIMPRESS_READ_DS")) if (*e && *e != '0') vcf->set_dosage_mode(true);   // tests: FORMAT/DS instead of GT
         VariantRecord rec;
         int64_t k = 0;
         *n_samples = vcf->n_samples();
@@ -263,6 +265,8 @@ static const char *USAGE =
     "  --devices=<list>   Several CUDA devices, e.g. 0-7 or 0,2,3: the score file is split into\n"
     "                     contiguous ranges, one per device, and the partial sums are combined\n"
     "                     in range order (not a reference option).\n"
+    "  --dosage           Score FORMAT/DS (expected ALT-allele dosage, one float per sample) instead of\n"
+    "                     FORMAT/GT (not a reference option: the reference lists it under Future).\n"
     "  --exact-order      Add every locus to the running sums in score-file order, bit for bit\n"
     "                     like the reference (default: sum tiles of four loci first; same\n"
     "                     products, scores equal to ~1e-15 relative) (not a reference option).\n";
@@ -309,7 +313,7 @@ static void print_result(const nph_result *r) {
 }
 
 int nph_main(int argc, char **argv) {
-    nph_params p = { NPC_LOCUS_PS, NPC_MISSING_HOMREF, NPC_SAMPLE_INT_PS, 0, 0, 0, 0, 0, 100, 0.05, 0.001 };
+    nph_params p = { NPC_LOCUS_PS, NPC_MISSING_HOMREF, NPC_SAMPLE_INT_PS, 0, 0, 0, 0, 0, 100, 0.05, 0.001, 0, 0 };
     std::string cov, pos[2];
     int npos = 0;
     try {
@@ -335,6 +339,7 @@ int nph_main(int argc, char **argv) {
             else if (is("--device")) p.device = (int)parse_int_nim(val("--device"), "--device");
             else if (a == "--ignorefilt") p.ignorefilt = 1;
             else if (a == "--exact-order") p.exact_order = 1;
+            else if (a == "--dosage") p.use_ds = 1;
             else if (a.size() > 1 && a[0] == '-') throw InputError("unknown option " + a);
             else if (npos < 2) pos[npos++] = a;
             else throw InputError("too many arguments");

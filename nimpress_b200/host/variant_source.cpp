@@ -426,7 +426,7 @@ public:
         for (const char *q = col[8], *qe = col[8] + len[8]; q <= qe; k++) {
             const char *t = (const char *)memchr(q, ':', qe - q);
             size_t l = (t ? t : qe) - q;
-            if (l == 2 && q[0] == 'G' && q[1] == 'T') gt_idx = k;
+            if (l == 2 && (dosage_ ? (q[0] == 'D' && q[1] == 'S') : (q[0] == 'G' && q[1] == 'T'))) gt_idx = k;
             if (!t) break;
             q = t + 1;
         }
@@ -442,6 +442,33 @@ public:
         gt_loaded_ = true;
         const char *p = gt_p_, *end = line_.data() + line_.size();
         const int64_t n = n_samples();
+        if (dosage_) {                                   // DS sub-field of every sample -> BCF floats ("." = missing)
+            gt_.resize((size_t)n * 4);
+            int maxv = 1;
+            for (int64_t i = 0; i < n; i++) {
+                const char *s = p <= end ? p : end, *se = end;
+                if (p <= end) {
+                    const char *t = (const char *)memchr(p, '\t', end - p);
+                    se = t ? t : end;
+                    p = t ? t + 1 : end + 1;
+                }
+                for (int f = 0; f < gt_idx_ && s < se; f++) {
+                    const char *t = (const char *)memchr(s, ':', se - s);
+                    s = t ? t + 1 : se;
+                }
+                const char *fe = (const char *)memchr(s, ':', se - s);
+                if (!fe) fe = se;
+                if (memchr(s, ',', fe - s)) maxv = 2;             // Number=A with several ALTs: the caller refuses
+                uint32_t bits = 0x7F800001u;
+                if (s < fe && !(fe - s == 1 && *s == '.')) {
+                    const float v = (float)parse_float_nim(std::string(s, fe - s), "FORMAT/DS");
+                    memcpy(&bits, &v, 4);
+                }
+                memcpy(gt_.data() + 4 * i, &bits, 4);
+            }
+            rec.ploidy = maxv; rec.gt_width = 4; rec.gt = gt_.data();
+            return;
+        }
         // fast path: every sample is "a/b" or "a|b" with one-character alleles and GT the first
         // sub-field -- written straight as int8 (allele+1)<<1|phased (htslib vcf_parse_format)
         if (gt_idx_ == 0 && p <= end) {
@@ -602,7 +629,7 @@ public:
             const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
             const size_t bytes = (size_t)n_sample_ * len * esz;
             if (q + bytes > qe) throw InputError("BCF: FORMAT field overruns the record");
-            if (key == gt_key_ && (type == 1 || type == 2 || type == 3)) {
+            if (wanted(key, type)) {
                 if ((int64_t)n_sample_ != n_samples()) throw InputError("BCF: record sample count differs from header");
                 rec.has_gt = true; rec.gt = q; rec.gt_width = (int)esz; rec.ploidy = (int)len;
             }
@@ -640,7 +667,7 @@ public:
             const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
             const size_t bytes = (size_t)n_sample_ * len * esz;
             if (bytes > left) throw InputError("BCF: FORMAT field overruns the record");
-            if (key == gt_key_ && (type == 1 || type == 2 || type == 3)) {
+            if (wanted(key, type)) {
                 if ((int64_t)n_sample_ != n_samples()) throw InputError("BCF: record sample count differs from header");
                 gt_done_ = true;
                 rec.has_gt = true; rec.gt_width = (int)esz; rec.ploidy = (int)len;
@@ -752,6 +779,12 @@ private:
         }
         auto it = seen.find("GT");
         gt_key_ = it == seen.end() ? -1 : it->second;
+        it = seen.find("DS");
+        ds_key_ = it == seen.end() ? -1 : it->second;
+    }
+    // the FORMAT field the caller reads: GT (typed ints) or, in dosage mode, DS (floats)
+    bool wanted(int32_t key, int type) const {
+        return dosage_ ? (key == ds_key_ && type == 5) : (key == gt_key_ && (type == 1 || type == 2 || type == 3));
     }
     std::unique_ptr<InflateStream> in_;
     std::vector<std::string> contigs_, dict_;
@@ -774,11 +807,11 @@ private:
             const size_t esz = type == 1 ? 1 : type == 2 ? 2 : type == 3 ? 4 : type == 5 ? 4 : type == 7 ? 1 : 0;
             const size_t bytes = (size_t)n_sample_ * len * esz;
             if (q + bytes > qe) throw InputError("BCF: FORMAT field overruns the record");
-            if (key == gt_key_ && (type == 1 || type == 2 || type == 3)) { rec.has_gt = true; rec.gt = q; rec.gt_width = (int)esz; rec.ploidy = (int)len; }
+            if (wanted(key, type)) { rec.has_gt = true; rec.gt = q; rec.gt_width = (int)esz; rec.ploidy = (int)len; }
             q += bytes;
         }
     }
-    int32_t gt_key_ = -1;
+    int32_t gt_key_ = -1, ds_key_ = -1;
     size_t indiv_left_ = 0;
     uint32_t n_fmt_ = 0, n_sample_ = 0;
     bool gt_done_ = true;

@@ -98,6 +98,10 @@ public:
         load_gt(rec);
         return false;
     }
+    // FORMAT/DS instead of FORMAT/GT (not a reference feature: README.md:162-165 lists dosage input under "Future"):
+    // load_gt / load_gt_into then deliver one BCF float per value, gt_width = 4, ploidy = values per sample.
+    virtual void set_dosage_mode(bool on) { dosage_ = on; }
+    bool dosage_mode() const { return dosage_; }
     const std::vector<std::string> &samples() const { return samples_; }
     int64_t n_samples() const { return (int64_t)samples_.size(); }
 protected:
@@ -109,6 +113,7 @@ protected:
     virtual bool index_names_contigs() const { return true; }         // text VCF: the index must carry the contig names
     std::vector<std::string> samples_;
     std::unique_ptr<RegionIndex> index_;
+    bool dosage_ = false;
 private:
     struct Region { int ref; int64_t beg0, end0; };                   // 0-based half open
     std::vector<Region> regions_;

@@ -539,6 +539,46 @@ static void tally_alleles(const double *raw, int64_t n, double *ngt, double *nmi
     *ngt = g; *nmiss = m; *neff = e;
 }
 
+/* FORMAT/DS rows -- NOT IN THE REFERENCE (it reads GT only, :384; dosage input is "Future" in README.md:162-165):
+ * parity unpinned.  Raw dosage = ds (effect allele = ALT) or 2 - ds (effect allele = REF); BCF float missing /
+ * vector_end / NaN = no call.  neffectallele is a real-valued sum, so its ORDER is part of the definition
+ * (nimpress_b200/csrc/npc_dosage.cuh): chunks of 8 samples left to right from +0.0; 32 consecutive chunk sums
+ * combined by the butterfly v[i] += v[i ^ o], o = 16, 8, 4, 2, 1; the blocks of 256 samples left to right. */
+static int ds_is_missing(uint32_t bits) {
+    return bits == 0x7F800001u || bits == 0x7F800002u || (bits & 0x7FFFFFFFu) > 0x7F800000u;
+}
+static void get_raw_dosages_ds(double *raw, const float *ds, int64_t n, int eaidx) {
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t bits;
+        memcpy(&bits, &ds[i], 4);
+        if (ds_is_missing(bits)) raw[i] = NAN;
+        else raw[i] = eaidx == 0 ? 2.0 - (double)ds[i] : (double)ds[i];
+    }
+}
+static void tally_dosages_ds(const double *raw, int64_t n, double *ngt, double *nmiss, double *neff) {
+    double g = 0.0, m = 0.0, total = 0.0;
+    for (int64_t b0 = 0; b0 < n; b0 += 256) {
+        double v[32];
+        for (int c = 0; c < 32; c++) {
+            double s = 0.0;
+            for (int k = 0; k < 8; k++) {
+                int64_t i = b0 + c * 8 + k;
+                if (i >= n) break;
+                if (isnan(raw[i])) m += 1.0;
+                else { g += 1.0; s = s + raw[i]; }
+            }
+            v[c] = s;
+        }
+        for (int o = 16; o; o >>= 1) {
+            double w[32];
+            for (int c = 0; c < 32; c++) w[c] = v[c] + v[c ^ o];
+            memcpy(v, w, sizeof v);
+        }
+        total = total + v[0];
+    }
+    *ngt = g; *nmiss = m; *neff = total;
+}
+
 /* imputeLocusDosages (:417-447) */
 static int impute_locus(double *dos, int64_t n, double eaf, int ref_is_ea, int method, double *value) {
     if (method == ORC_LOCUS_IGNORE) return 0;
@@ -574,9 +614,18 @@ typedef struct {
 
 /* the tail of getImputedDosages once the record (or its absence) is known: :536-585.
  * gts == NULL means "no record".  filter_fail: FILTER not in {".","PASS"} and !ignorefilt. */
+static int locus_after_lookup_any(double *dos, int64_t n, const int32_t *gts, const float *ds, int ploidy, int eaidx,
+                                  int filter_fail, const char *filter_str, double eaf, int ref_is_ea,
+                                  const orc_params *p, const locus_label *lab, sbuf *warn, orc_locus *rec);
 static int locus_after_lookup(double *dos, int64_t n, const int32_t *gts, int ploidy, int eaidx,
                               int filter_fail, const char *filter_str, double eaf, int ref_is_ea,
                               const orc_params *p, const locus_label *lab, sbuf *warn, orc_locus *rec) {
+    return locus_after_lookup_any(dos, n, gts, NULL, ploidy, eaidx, filter_fail, filter_str, eaf, ref_is_ea, p, lab, warn, rec);
+}
+/* ds != NULL: a FORMAT/DS row (gts is then only a "record present" flag) */
+static int locus_after_lookup_any(double *dos, int64_t n, const int32_t *gts, const float *ds, int ploidy, int eaidx,
+                                  int filter_fail, const char *filter_str, double eaf, int ref_is_ea,
+                                  const orc_params *p, const locus_label *lab, sbuf *warn, orc_locus *rec) {
     char fb[64], fb2[64];
     rec->eaidx = -1; rec->ngt = rec->nmiss = rec->neff = -1; rec->imputed = NAN;
     if (!gts) {                                                             /* :536-551 */
@@ -604,10 +653,16 @@ static int locus_after_lookup(double *dos, int64_t n, const int32_t *gts, int pl
                       lab->contig, (long long)lab->pos, lab->refseq, lab->easeq, filter_str ? filter_str : "");
         return impute_locus(dos, n, eaf, ref_is_ea, p->imp_locus, &rec->imputed);
     }
-    get_raw_dosages(dos, gts, n, ploidy, eaidx);                            /* :561 */
     double ngt, nmiss, neff;
-    tally_alleles(dos, n, &ngt, &nmiss, &neff);                             /* :563 */
-    rec->ngt = (int64_t)ngt; rec->nmiss = (int64_t)nmiss; rec->neff = (int64_t)neff;
+    if (ds) {
+        get_raw_dosages_ds(dos, ds, n, eaidx);
+        tally_dosages_ds(dos, n, &ngt, &nmiss, &neff);
+        rec->ngt = (int64_t)ngt; rec->nmiss = (int64_t)nmiss; memcpy(&rec->neff, &neff, 8);   /* the fp64 sum's bits */
+    } else {
+        get_raw_dosages(dos, gts, n, ploidy, eaidx);                        /* :561 */
+        tally_alleles(dos, n, &ngt, &nmiss, &neff);                         /* :563 */
+        rec->ngt = (int64_t)ngt; rec->nmiss = (int64_t)nmiss; rec->neff = (int64_t)neff;
+    }
     double missingrate = nmiss / (double)n;                                 /* :565 */
     if (missingrate > p->maxmis) {                                          /* :566-571 */
         rec->klass = ORC_CLASS_MAXMIS;
@@ -619,7 +674,7 @@ static int locus_after_lookup(double *dos, int64_t n, const int32_t *gts, int pl
         }
         return impute_locus(dos, n, eaf, ref_is_ea, p->imp_locus, &rec->imputed);
     }
-    if (!p->skip_aftest && !isnan(eaf) &&                                   /* :573-579 */
+    if (!ds && !p->skip_aftest && !isnan(eaf) &&                            /* :573-579 */
         orc_binom_test((int64_t)neff, (n - (int64_t)nmiss) * 2, eaf) < p->afmisp && lab->contig) {
         orc_format_float(neff / (double)((n - (int64_t)nmiss) * 2), fb, sizeof fb);
         orc_format_float(eaf, fb2, sizeof fb2);
@@ -748,11 +803,13 @@ static void *matrix_range(void *arg) {
             const int32_t *g = NULL;
             if (row->kind == ORC_CLASS_FILTER) g = wide;      /* a FILTER-failed record is never decoded (:553-558) */
             else if (row->kind != ORC_CLASS_ABSENT && row->gt_row >= 0) {
-                widen_row(wide, (const char *)j->gt + row->gt_row * j->row_stride, j->gt_width, n, j->ploidy);
+                if (j->gt_width != -4) widen_row(wide, (const char *)j->gt + row->gt_row * j->row_stride, j->gt_width, n, j->ploidy);
                 g = wide;
             }
-            used = locus_after_lookup(dos, n, g, j->ploidy, row->eaidx, row->kind == ORC_CLASS_FILTER, NULL,
-                                      row->eaf, row->ref_is_ea, j->p, &lab, NULL, rec);
+            const float *dsrow = j->gt_width == -4 && g && row->kind != ORC_CLASS_FILTER
+                                     ? (const float *)((const char *)j->gt + row->gt_row * j->row_stride) : NULL;
+            used = locus_after_lookup_any(dos, n, g, dsrow, j->ploidy, row->eaidx, row->kind == ORC_CLASS_FILTER, NULL,
+                                          row->eaf, row->ref_is_ea, j->p, &lab, NULL, rec);
         }
         rec->used = used;
         if (used) {
@@ -769,8 +826,8 @@ int orc_score_matrix(const void *gt, int32_t gt_width, int64_t n_samples, int32_
                      int64_t row_stride, const orc_row *rows, int64_t n_rows,
                      const orc_params *p, double offset, int32_t n_threads,
                      double *scores_out, orc_locus *loci_out, int64_t *nloci_used_out) {
-    if (gt_width != 1 && gt_width != 2 && gt_width != 4) return -3;
-    if (ploidy < 1) return -3;
+    if (gt_width != 1 && gt_width != 2 && gt_width != 4 && gt_width != -4) return -3;   /* -4: fp32 FORMAT/DS rows (ploidy 1) */
+    if (ploidy < 1 || (gt_width == -4 && ploidy != 1)) return -3;
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n_rows) n_threads = n_rows > 0 ? (int32_t)n_rows : 1;
     orc_params pp = *p;

@@ -116,6 +116,8 @@ def score_matrix(gt, n_samples, ploidy, rows, offset=0.0, threads=1, **kw):
     """In-memory path.  gt: 2-D integer array [n_gt_rows, >= n_samples*ploidy] of dtype int8/16/32
     (C-contiguous rows).  rows: ROW_DTYPE array in processing order."""
     gt = np.asarray(gt)
+    if gt.dtype == np.float32:                          # FORMAT/DS rows (not in the reference: parity unpinned)
+        return score_matrix_ds(gt, n_samples, rows, offset, threads, **kw)
     assert gt.ndim == 2 and gt.dtype in (np.int8, np.int16, np.int32) and gt.strides[1] == gt.itemsize
     rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
     p = params(**kw)
@@ -125,6 +127,23 @@ def score_matrix(gt, n_samples, ploidy, rows, offset=0.0, threads=1, **kw):
     rc = lib().orc_score_matrix(gt.ctypes.data, gt.itemsize, n_samples, ploidy, gt.strides[0], rows.ctypes.data,
                                 len(rows), C.byref(p), float(offset), threads, scores.ctypes.data,
                                 loci.ctypes.data, C.byref(used))
+    if rc:
+        raise RuntimeError(f"oracle rc={rc}")
+    return dict(scores=scores, loci=loci, nloci=used.value, abs_floor=abs_floor(rows["beta"], used.value))
+
+
+def score_matrix_ds(ds, n_samples, rows, offset=0.0, threads=1, **kw):
+    """FORMAT/DS rows: ds float32 [n_rows, >= n_samples], one expected ALT dosage per sample (BCF float
+    missing / NaN = no call).  loci["neff"] holds the bits of the fp64 dosage sum."""
+    ds = np.asarray(ds)
+    assert ds.ndim == 2 and ds.dtype == np.float32 and ds.strides[1] == 4
+    rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+    p = params(**kw)
+    scores = np.zeros(n_samples, dtype=np.float64)
+    loci = np.zeros(len(rows), dtype=LOCUS_DTYPE)
+    used = C.c_int64(0)
+    rc = lib().orc_score_matrix(ds.ctypes.data, -4, n_samples, 1, ds.strides[0], rows.ctypes.data, len(rows), C.byref(p),
+                                float(offset), threads, scores.ctypes.data, loci.ctypes.data, C.byref(used))
     if rc:
         raise RuntimeError(f"oracle rc={rc}")
     return dict(scores=scores, loci=loci, nloci=used.value, abs_floor=abs_floor(rows["beta"], used.value))

@@ -557,3 +557,31 @@ def test_score_fields_are_parsed_as_strictly_as_nim(api, tmp_path):
     sc = d / "g.score"
     sc.write_text(good.replace("0.2", "nan"))
     assert plan(api, str(sc), str(d / "v.vcf"))[0] == 0
+
+
+def test_reader_delivers_format_ds(api, tmp_path, monkeypatch):
+    """Dosage mode of the readers (FORMAT/DS, one float per sample; not a reference feature): VCF text and BCF
+    hand out the same BCF float bits, "." / absent values as the float missing sentinel, and a field placed after
+    other FORMAT fields is found."""
+    rng = np.random.default_rng(3)
+    n = 7
+    samples = [f"s{i}" for i in range(n)]
+    recs = []
+    for k in range(12):
+        ds = np.round(rng.uniform(0, 2, n), 3).astype(np.float32)
+        ds[rng.random(n) < 0.2] = np.nan
+        recs.append(dict(contig="1", pos=100 + 10 * k, ref="A", alts=["C"], filter="PASS", ds=ds,
+                         gt=((rng.integers(0, 2, size=(n, 2)) + 1) << 1).astype(np.int8)))
+    vcf, bcf = str(tmp_path / "d.vcf.gz"), str(tmp_path / "d.bcf")
+    write_vcf(vcf, samples, recs, contigs=["1"], compress="bgzf")
+    write_bcf(bcf, samples, recs, ["1"], extra_fmt=True)
+    monkeypatch.setenv("NIMPRESS_READ_DS", "1")
+    want = np.stack([r["ds"] for r in recs]).copy().view(np.uint32)
+    want[~np.isfinite(np.stack([r["ds"] for r in recs]))] = 0x7F800001
+    for f in (vcf, bcf):
+        got, ns, w, pl = read_gt(api, f, 4 * n)
+        assert (ns, w, pl) == (n, 4, 1) and got.shape[0] == len(recs)
+        assert np.array_equal(got.view(np.uint32).reshape(len(recs), n), want), f
+    monkeypatch.delenv("NIMPRESS_READ_DS")
+    got, ns, w, pl = read_gt(api, bcf, 2 * n)                    # GT still there
+    assert (w, pl) == (1, 2) and np.array_equal(got.view(np.int8).reshape(len(recs), n, 2), np.stack([r["gt"] for r in recs]))

@@ -47,12 +47,18 @@ def write_vcf(path, samples, records, contigs=None, filters=("FAIL",), crlf=Fals
     lines += [f"##contig=<ID={c}>" for c in (contigs or [])]
     lines += ['##INFO=<ID=END,Number=1,Type=Integer,Description="End">',
               '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">',
-              '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth">']
+              '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth">',
+              '##FORMAT=<ID=DS,Number=A,Type=Float,Description="Expected ALT dosage">']
     lines.append("\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + list(samples)))
     for r in records:
         g = np.asarray(r["gt"])
         width = g.dtype.itemsize
         fmt = r.get("format", "GT")
+        if "ds" in r:                                      # GT:DS, floats printed so that float32(text) is the value ("." = missing)
+            cols = [r["contig"], str(r["pos"]), ".", r["ref"], ",".join(r["alts"]) if r["alts"] else ".", ".", r["filter"], r.get("info", "."), "GT:DS"]
+            cols += [gt_text(g[i], width) + ":" + ("." if not np.isfinite(r["ds"][i]) else repr(float(np.float32(r["ds"][i])))) for i in range(len(samples))]
+            lines.append("\t".join(cols))
+            continue
         cols = [r["contig"], str(r["pos"]), ".", r["ref"], ",".join(r["alts"]) if r["alts"] else ".", ".", r["filter"],
                 r.get("info", "."), fmt]
         if fmt == "GT":
@@ -115,7 +121,7 @@ def _typed_ints(vals):
 def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf", with_idx=False, extra_fmt=False, index=None):
     """BCF2.2.  Dictionary of strings: PASS, then FILTERs, INFO END, FORMAT GT, FORMAT DP (header order,
     or explicit IDX= when with_idx, deliberately permuted)."""
-    ids = ["PASS"] + list(filters) + ["END", "GT", "DP"]
+    ids = ["PASS"] + list(filters) + ["END", "GT", "DP", "DS"]
     idx = {s: i for i, s in enumerate(ids)}
     if with_idx:                                           # shuffle the dictionary through IDX=
         perm = [0] + list(range(len(ids) - 1, 0, -1))
@@ -127,7 +133,8 @@ def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf
     lines += [f"##contig=<ID={c}>" for c in contigs]
     lines += [f'##INFO=<ID=END,Number=1,Type=Integer,Description="End"{tag("END")}>',
               f'##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype"{tag("GT")}>',
-              f'##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth"{tag("DP")}>']
+              f'##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth"{tag("DP")}>',
+              f'##FORMAT=<ID=DS,Number=A,Type=Float,Description="Expected ALT dosage"{tag("DS")}>']
     lines.append("\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + list(samples)))
     text = ("\n".join(lines) + "\n").encode() + b"\0"
     out = bytearray(b"BCF\2\2" + struct.pack("<I", len(text)) + text)
@@ -147,7 +154,7 @@ def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf
             n_info = 1
         flt = [] if r["filter"] == "." else [idx[f] for f in r["filter"].split(";")]
         shared = struct.pack("<iiif", cidx[r["contig"]], r["pos"] - 1, rlen, float("nan"))
-        n_fmt = 2 if extra_fmt else 1
+        n_fmt = (2 if extra_fmt else 1) + (1 if "ds" in r else 0)
         shared += struct.pack("<II", (len(alleles) << 16) | n_info, (n_fmt << 24) | n)
         shared += _desc(0, 7)                              # ID: empty string
         for a in alleles:
@@ -158,6 +165,11 @@ def write_bcf(path, samples, records, contigs, filters=("FAIL",), compress="bgzf
             indiv += _typed_int(idx["DP"]) + _desc(1, 1) + bytes([7] * n)
         t = {1: 1, 2: 2, 4: 3}[g.dtype.itemsize]
         indiv += _typed_int(idx["GT"]) + _desc(g.shape[1], t) + g.tobytes()
+        if "ds" in r:                                      # one float per sample; NaN in the input = BCF float missing
+            d = np.asarray(r["ds"], dtype=np.float32).copy()
+            bits = d.view(np.uint32)
+            bits[~np.isfinite(d)] = 0x7F800001
+            indiv += _typed_int(idx["DS"]) + _desc(1, 5) + bits.tobytes()
         out += struct.pack("<II", len(shared), len(indiv)) + shared + indiv
         spans.append((rec_start, len(out)))
     data = bytes(out)
