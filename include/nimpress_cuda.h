@@ -306,6 +306,9 @@ int npc_synth_fill_device(npc_ctx *ctx, void *gt_dev, int64_t row_stride, int64_
                           const int32_t *alt_code_dev);
 
 int npc_version(void);
+/* Create the CUDA context of `device` (driver initialisation + primary context: most of a short run's start-up),
+ * so that a host can do it on a thread of its own while it parses its inputs. */
+int npc_warmup(int device);
 
 #ifdef __cplusplus
 }

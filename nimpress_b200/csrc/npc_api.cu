@@ -64,6 +64,7 @@ struct npc_ctx {
                                             // clears the half the next one uses (pair kernel)
     int fcounts_half = 0;
     int64_t fcounts_dirty[2] = { 0, 0 };    // words of each half written since it was last cleared
+    unsigned int *d_done = nullptr;         // per sample slab: row groups that have stored their partial sums (pair kernel)
     ull *d_trace = nullptr;                 // NPC_TRACE: 8 %globaltimer stamps of the last pair-kernel launch
     uint8_t *d_multi_scratch = nullptr;     // arena of npc_score_resident_multi's contraction
     size_t multi_scratch_bytes = 0;
@@ -98,7 +99,12 @@ static int fail(npc_ctx *ctx, int code, const char *msg) {
     return code;
 }
 
-extern "C" int npc_version(void) { return 100; }
+extern "C" int npc_version(void) { return 200; }
+
+extern "C" int npc_warmup(int device) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { cudaGetLastError(); return NPC_ECUDA; }
+    return NPC_OK;
+}
 
 extern "C" const char *npc_last_error(const npc_ctx *ctx) {
     return ctx ? ctx->err.c_str() : g_create_error.c_str();
@@ -113,7 +119,7 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_trace); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_trace); cudaFree(ctx->d_done); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
     if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->ev_reduce) cudaEventDestroy(ctx->ev_reduce);
     cudaFree(ctx->d_nloci_total); cudaFree(ctx->d_bridge); cudaFree(ctx->d_gather); cudaFree(ctx->d_ds_part);
@@ -128,7 +134,11 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-static const void *tile_kernel(int ver, int K, bool exact) {
+static const void *tile_kernel(int ver, int K, bool exact, int width = 1) {
+    if (ver == 5 && width == 2) {
+        if (K == 1) return exact ? (const void *)k_fused_pair<1, true, 2> : (const void *)k_fused_pair<1, false, 2>;
+        return exact ? (const void *)k_fused_pair<2, true, 2> : (const void *)k_fused_pair<2, false, 2>;
+    }
     if (ver == 5) {
         if (K == 1) return exact ? (const void *)k_fused_pair<1, true> : (const void *)k_fused_pair<1, false>;
         return exact ? (const void *)k_fused_pair<2, true> : (const void *)k_fused_pair<2, false>;
@@ -149,11 +159,13 @@ static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg
     if (K != 1 && K != 2) K = nch <= 512 ? 1 : 2;
     const int64_t nc = (nch + 32 * K - 1) / (32 * K);
     if (nc > 16) return false;                        // cohort too wide for one resident pass
-    const int slab = (int)(nc * 32 * K * 16);
+    const int W = c->width;                            // 1 or 2 (int16 GT: pair kernel only)
+    const int slab = (int)(nc * 32 * K * 16 * W);
     int Sr = env_int("NPC_TILE_SR", 0), Sc = env_int("NPC_TILE_SC", 0), L = env_int("NPC_TILE_L", 0), A = env_int("NPC_TILE_A", 2);
     const int ver = env_int("NPC_TILE_V", 5) == 4 ? 4 : 5;
+    if (W != 1 && ver != 5) return false;
     auto smem_of = [&](int sr, int sc) {
-        return ver == 5 ? (int)Fused5Smem::make(sr, sc, slab, (int)nc, K).total : (int)Fused4Smem::make(sr, sc, slab).total;
+        return ver == 5 ? (int)Fused5Smem::make(sr, sc, slab, (int)nc, K, W).total : (int)Fused4Smem::make(sr, sc, slab).total;
     };
     if (Sr <= 0) Sr = std::max(2, std::min(8, (112 * 1024) / (F4_R * slab)));
     if (Sc <= 0) {
@@ -178,7 +190,7 @@ static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg
 // order: Gr = 1.  NPC_TILE_{K,SR,SC,L,A,GR} override for tuning; NPC_FUSED=0 forces the two-kernel path.
 static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     c->fast.ok = c->exact_cfg.ok = false;
-    if (c->width != 1 || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
+    if ((c->width != 1 && c->width != 2) || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
     c->num_sms = prop.multiProcessorCount;
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
     const int64_t C = (c->n + 7) / 8;
@@ -199,13 +211,15 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     for (int ex = 0; ex < 2; ex++) {
         const npc_ctx::TileCfg &t = ex ? c->exact_cfg : c->fast;
         if (!t.ok) continue;
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, ex != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, ex != 0, c->width), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
         if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     }
     if (c->fast.ok || c->exact_cfg.ok) {
         const size_t words = 2 * (size_t)std::max<int64_t>(c->max_rows, 1);
         NPC_CUDA(c, cudaMalloc(&c->d_fcounts, words * sizeof(ull)));
         NPC_CUDA(c, cudaMemset(c->d_fcounts, 0, words * sizeof(ull)));
+        NPC_CUDA(c, cudaMalloc(&c->d_done, 1024 * sizeof(unsigned int)));
+        NPC_CUDA(c, cudaMemset(c->d_done, 0, 1024 * sizeof(unsigned int)));
         if (env_int("NPC_TRACE", 0)) { NPC_CUDA(c, cudaMalloc(&c->d_trace, 8 * sizeof(ull))); NPC_CUDA(c, cudaMemset(c->d_trace, 0, 8 * sizeof(ull))); }
     }
     if (c->fast.ok && c->fast.Gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(c->fast.Gr - 1) * (size_t)c->n * sizeof(double)));
@@ -456,14 +470,14 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
     P.sums = c->d_sums; P.counts = counts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
-    P.counts_next = counts_next; P.n_zero = n_zero; P.trace = c->d_trace;
+    P.counts_next = counts_next; P.n_zero = n_zero; P.trace = c->d_trace; P.done = c->d_done;
     P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
     P.Gs = t.Gs; P.Gr = gr; P.partials = c->d_partials;
     P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
     void *args[] = { &P };
-    NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
+    NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
     c->launches++;
-    if (gr > 1) {
+    if (gr > 1 && t.ver != 5) {                        // the pair kernel adds its row groups' partial sums itself
         k_add_partials<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_sums, c->d_partials, c->n, gr - 1);
         c->launches++;
         NPC_CUDA(c, cudaGetLastError());

@@ -42,7 +42,7 @@ constexpr int F5_GROUP = 3;                   // (warp, chunk) pairs per tally c
 struct Fused5Smem {
     uint32_t code, vtab, vrow, bars, cnt, rflags, rtb, reaidx, idx, data, total;
     __host__ __device__ static int groups(int nc, int K) { return (nc * K + F5_GROUP - 1) / F5_GROUP; }
-    __host__ __device__ static Fused5Smem make(int Sr, int Sc, int slab_stride, int nc, int K) {
+    __host__ __device__ static Fused5Smem make(int Sr, int Sc, int slab_stride, int nc, int K, int W = 1) {
         Fused5Smem m;
         uint32_t o = 0;
         m.code = o;   o += F5_NT * 2u * F5_TAB_BYTES;                    // first: 1024-byte aligned
@@ -53,7 +53,7 @@ struct Fused5Smem {
         m.rflags = o; o += (uint32_t)Sr * 4u;                   o = (o + 127u) & ~127u;
         m.rtb = o;    o += (uint32_t)Sr * 16u;                  o = (o + 127u) & ~127u;
         m.reaidx = o; o += (uint32_t)Sr * 16u;                  o = (o + 127u) & ~127u;
-        m.idx = o;    o += (uint32_t)Sc * (uint32_t)(slab_stride / 2);  o = (o + 127u) & ~127u;
+        m.idx = o;    o += (uint32_t)Sc * (uint32_t)(slab_stride / (2 * W));  o = (o + 127u) & ~127u;   // one byte per sample per tile
         m.data = o;   o += (uint32_t)Sr * F5_R * (uint32_t)slab_stride;
         m.total = o;
         return m;
@@ -85,15 +85,30 @@ __device__ __forceinline__ uint32_t f5_slow_code(uint32_t h, int eaidx) {
 __device__ __forceinline__ uint32_t f5_pair_entry(uint32_t w, uint32_t table) {
     return lds_u32(__dp4a(w & 0x06060606u, F5_PACK_W, table));             // table + 4 * (66*c0 + c1 + 4*c2 + 16*c3)
 }
+// int16 GT: a sample is one 32-bit word (two halfwords, each < 8 on the fast path, so their high bytes are zero);
+// (w0 | w1 << 8) & 0x06060606 has bytes [c0(s0), c0(s1), c1(s0), c1(s1)] * 2 -- the same table, other weights
+constexpr uint32_t F5_PACK_W16 = 0x20020884u;
+__device__ __forceinline__ uint32_t f5_pair_entry16(uint32_t w0, uint32_t w1, uint32_t table) {
+    return lds_u32(__dp4a((w0 | (w1 << 8)) & 0x06060606u, F5_PACK_W16, table));
+}
+__device__ __forceinline__ uint32_t f5_slow_code16(uint32_t word, int eaidx) {
+    int16_t a[2] = { (int16_t)(word & 0xFFFF), (int16_t)(word >> 16) };
+    int d; bool miss;
+    decode_sample<int16_t>(a, 2, eaidx, d, miss);
+    return miss ? 3u : (uint32_t)d;
+}
 
-template <int K, bool EXACT>
+// W = bytes per stored allele value: 1 (int8, the usual BCF GT) or 2 (int16: records with more than 63 alleles)
+template <int K, bool EXACT, int W = 1>
 __global__ void __launch_bounds__(640, 1)         // <= 16 consumer warps + producer + publisher + <= 2 deciders
 k_fused_pair(const FusedParams P) {
     constexpr int R = F5_R;
+    constexpr uint32_t CELL = 16u * W;                 // bytes of a chunk (8 diploid samples) in a raw row
+    constexpr uint32_t HI_MASK = W == 1 ? 0xF8F8F8F8u : 0xFFF8FFF8u;   // any value >= 8 (ALT3.., sentinels) leaves the fast path
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Sr = P.Sr, Sc = P.Sc, L = P.L, NC = P.nc, A = P.A;
     const int NG = Fused5Smem::groups(NC, K);
-    const Fused5Smem M = Fused5Smem::make(Sr, Sc, P.slab_stride, NC, K);
+    const Fused5Smem M = Fused5Smem::make(Sr, Sc, P.slab_stride, NC, K, W);
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar_full = sb + M.bars, bar_rempty = bar_full + 8u * Sr, bar_cnt = bar_rempty + 8u * Sr, bar_lut = bar_cnt + 8u * Sc;
     uint32_t *s_rflags = reinterpret_cast<uint32_t *>(smem + M.rflags);
@@ -113,7 +128,7 @@ k_fused_pair(const FusedParams P) {
     const int64_t q_ = C / Gs, rem = C % Gs;
     const int64_t c0 = (int64_t)slab_id * q_ + min((int64_t)slab_id, rem);
     const int nch = (int)(q_ + ((int64_t)slab_id < rem ? 1 : 0));
-    const uint32_t slab_bytes = (uint32_t)nch * 16u;
+    const uint32_t slab_bytes = (uint32_t)nch * CELL;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Sr; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_rempty + 8u * s, NC); }
@@ -133,6 +148,11 @@ k_fused_pair(const FusedParams P) {
     if (P.counts_next)
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_zero; i += (int64_t)gridDim.x * blockDim.x) P.counts_next[i] = 0ull;
     if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[0] = globaltimer_ns();
+    npc_row first_meta;                                  // producer: the first 32 rows' metadata, in flight across the barrier
+    if (warp == NC) {
+        const int64_t r = row_lo + lane;
+        if (r < min(P.n_rows, (tile_lo + n_tiles) * R)) first_meta = P.rows[r];
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
@@ -144,11 +164,7 @@ k_fused_pair(const FusedParams P) {
         constexpr int G = 32 / R;                                    // tiles per metadata group
         int s = 0; uint32_t ph = 0;
         const int64_t row_hi = min(P.n_rows, (tile_lo + n_tiles) * R);      // this group's rows: [row_lo, row_hi)
-        npc_row nxt;
-        {
-            const int64_t r = row_lo + lane;
-            if (r < row_hi) nxt = P.rows[r];
-        }
+        npc_row nxt = first_meta;
         for (int64_t t0 = 0; t0 < n_tiles; t0 += G) {
             const npc_row cur = nxt;
             const int64_t my_row = row_lo + t0 * R + lane;
@@ -174,7 +190,7 @@ k_fused_pair(const FusedParams P) {
                 __syncwarp();
                 if (mine && is_gt)
                     tma_load_1d(sb + M.data + (uint32_t)(s * R + (lane % R)) * (uint32_t)P.slab_stride,
-                                P.gt + (int64_t)cur.gt_row * P.row_stride + c0 * 16, slab_bytes, bar_full + 8u * s, pol);
+                                P.gt + (int64_t)cur.gt_row * P.row_stride + c0 * CELL, slab_bytes, bar_full + 8u * s, pol);
                 if (++s == Sr) { s = 0; ph ^= 1u; }
             }
         }
@@ -288,13 +304,13 @@ k_fused_pair(const FusedParams P) {
             const int64_t g = c0 + jc;
             valid[k] = jc < nch ? (int)min((int64_t)8, P.n - g * 8) : 0;
             own[k] = jc < nch;
-            tailor[k] = (jc < nch && valid[k] < 8) ? 0xF8u : 0u;
+            tailor[k] = (jc < nch && valid[k] < 8) ? 0xF8u : 0u;          // a set bit of HI_MASK: the cohort's last, partial chunk decodes exactly
             cnt_off[k] = (uint32_t)((warp * K + k) / F5_GROUP) * 256u + (uint32_t)lane * 4u;
 #pragma unroll
             for (int e = 0; e < 8; e++) acc[k][e] = (e < valid[k] && grp == 0) ? P.sums[g * 8 + e] : 0.0;
         }
         double *sums_out = grp == 0 ? P.sums : P.partials + (int64_t)(grp - 1) * P.n;
-        const uint32_t slab = (uint32_t)P.slab_stride, islab = slab >> 1;
+        const uint32_t slab = (uint32_t)P.slab_stride, islab = slab / (2u * W);
         const int nt = (int)n_tiles;
         int sr = 0, sc = 0, sa = 0;
         uint32_t ph_r = 0, ph_a = 0;
@@ -308,24 +324,25 @@ k_fused_pair(const FusedParams P) {
                 const uint32_t cnt_base = sb + M.cnt + (uint32_t)sc * cnt_slot;
 #pragma unroll
                 for (int k = 0; k < K; k++) {
-                    uint4 w[R];
+                    uint32_t ww[R][4 * W];                       // the chunk's raw words, row by row
                     uint32_t hi_bits = tailor[k];
 #pragma unroll
-                    for (int r = 0; r < R; r++) {                // all loads of the tile first: 4 independent LDS.128
-                        w[r] = lds_v4(d0 + r * slab + cell[k] * 16u);
-                        hi_bits |= (w[r].x | w[r].y) | (w[r].z | w[r].w);
-                    }
-                    uint32_t A4[4], B4[4];                       // per word: entries of rows (0,1) / rows (2,3) added
-                    if (flags == 0xFu && (hi_bits & 0xF8F8F8F8u) == 0u) {
-                        // common case, straight line: every row has genotypes and all 64 bytes are < 8:
-                        // 16 independent pair lookups
-                        const uint32_t ww[R][4] = { { w[0].x, w[0].y, w[0].z, w[0].w }, { w[1].x, w[1].y, w[1].z, w[1].w },
-                                                    { w[2].x, w[2].y, w[2].z, w[2].w }, { w[3].x, w[3].y, w[3].z, w[3].w } };
+                    for (int r = 0; r < R; r++)                  // all loads of the tile first: independent LDS.128
+#pragma unroll
+                        for (int h = 0; h < W; h++) {
+                            const uint4 v = lds_v4(d0 + r * slab + cell[k] * CELL + 16u * h);
+                            ww[r][4 * h] = v.x; ww[r][4 * h + 1] = v.y; ww[r][4 * h + 2] = v.z; ww[r][4 * h + 3] = v.w;
+                            hi_bits |= (v.x | v.y) | (v.z | v.w);
+                        }
+                    uint32_t A4[4], B4[4];                       // per sample pair: entries of rows (0,1) / rows (2,3) added
+                    if (flags == 0xFu && (hi_bits & HI_MASK) == 0u) {
+                        // common case, straight line: every row has genotypes and every value is < 8: 16 independent pair lookups
                         uint32_t e[R][4];
 #pragma unroll
                         for (int r = 0; r < R; r++)
 #pragma unroll
-                            for (int j = 0; j < 4; j++) e[r][j] = f5_pair_entry(ww[r][j], tb[r]);
+                            for (int j = 0; j < 4; j++)
+                                e[r][j] = W == 1 ? f5_pair_entry(ww[r][j], tb[r]) : f5_pair_entry16(ww[r][(2 * j) % (4 * W)], ww[r][(2 * j + 1) % (4 * W)], tb[r]);
 #pragma unroll
                         for (int j = 0; j < 4; j++) { A4[j] = e[0][j] + e[1][j]; B4[j] = e[2][j] + e[3][j]; }
                     } else {
@@ -334,12 +351,14 @@ k_fused_pair(const FusedParams P) {
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             if (!((flags >> r) & 1u)) continue;
-                            const uint32_t ww[4] = { w[r].x, w[r].y, w[r].z, w[r].w };
-                            uint32_t e[4];
-                            const uint32_t row_hi = (((ww[0] | ww[1]) | (ww[2] | ww[3])) & 0xF8F8F8F8u) | tailor[k] | ((flags >> (4 + r)) & 1u);
+                            uint32_t e[4], any = 0u;
+#pragma unroll
+                            for (int j = 0; j < 4 * W; j++) any |= ww[r][j];
+                            const uint32_t row_hi = (any & HI_MASK) | tailor[k] | ((flags >> (4 + r)) & 1u);
                             if (row_hi == 0u) {
 #pragma unroll
-                                for (int j = 0; j < 4; j++) e[j] = f5_pair_entry(ww[j], tb[r]);
+                                for (int j = 0; j < 4; j++)
+                                    e[j] = W == 1 ? f5_pair_entry(ww[r][j], tb[r]) : f5_pair_entry16(ww[r][(2 * j) % (4 * W)], ww[r][(2 * j + 1) % (4 * W)], tb[r]);
                             } else {                             // exact decode, same entry format
                                 const int vk = own[k] ? valid[k] : 8;
                                 const int ea = s_reaidx[sr * R + r];
@@ -348,7 +367,9 @@ k_fused_pair(const FusedParams P) {
                                     e[j] = 0u;
 #pragma unroll
                                     for (int s = 0; s < 2; s++)
-                                        if (2 * j + s < vk) e[j] += f5_sample_entry(f5_slow_code((ww[j] >> (16 * s)) & 0xFFFFu, ea), r & 1, s);
+                                        if (2 * j + s < vk)
+                                            e[j] += f5_sample_entry(W == 1 ? f5_slow_code((ww[r][j] >> (16 * s)) & 0xFFFFu, ea)
+                                                                           : f5_slow_code16(ww[r][(2 * j + s) % (4 * W)], ea), r & 1, s);
                                 }
                             }
 #pragma unroll
@@ -419,6 +440,32 @@ k_fused_pair(const FusedParams P) {
 #pragma unroll
             for (int e = 0; e < 8; e++)
                 if (e < valid[k]) sums_out[g * 8 + e] = acc[k][e];
+        }
+        if (P.Gr > 1) {
+            // The row groups of this sample slab accumulate into separate vectors (group 0 into sums, group g > 0 into
+            // partials[g-1]).  The group that finishes LAST adds them, in group (= score-file) order whichever group it
+            // is: sums[s] = ((sums[s] + p_1[s]) + p_2[s]) + ...  Every consumer thread owns the same cells in every group.
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");
+            volatile uint32_t *s_last = s_rflags;                   // the producer is done with its flags: every tile was consumed
+            if (threadIdx.x == 0) *s_last = atomicAdd(&P.done[slab_id], 1u) == (unsigned)P.Gr - 1u ? 1u : 0u;
+            asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");
+            if (*s_last) {
+                __threadfence();
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const int64_t g = c0 + cell[k];
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        if (e < valid[k]) {
+                            const int64_t si = g * 8 + e;
+                            double a = __ldcg(P.sums + si);
+                            for (int q = 1; q < P.Gr; q++) a = __dadd_rn(a, __ldcg(P.partials + (int64_t)(q - 1) * P.n + si));
+                            P.sums[si] = a;
+                        }
+                }
+                if (threadIdx.x == 0) P.done[slab_id] = 0u;          // ready for the next launch
+            }
         }
         if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[5] = globaltimer_ns();
     }

@@ -85,6 +85,7 @@ def load_library():
         "npc_set_dosage_rows": (C.c_int, [vp, i32]),
         "npc_synth_fill_device": (C.c_int, [vp, vp, i64, i64, i64, C.c_uint64, vp, vp, vp]),
         "npc_version": (C.c_int, []),
+        "npc_warmup": (C.c_int, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the symbol is missing

@@ -165,6 +165,12 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
     outs.assign(S, ScoreResult());
 
     PhaseTimer timer;
+    // CUDA driver + context creation is most of a short run's start-up (~0.5-1 s): start it now, on threads of its
+    // own, while the score entries are indexed and the genotype file's index is consulted
+    std::vector<int> warm_ids = p.devices.empty() ? std::vector<int>{ p.device } : p.devices;
+    std::vector<std::thread> warm;
+    for (int d : warm_ids) warm.emplace_back([d] { npc_warmup(d); });
+    struct Joiner { std::vector<std::thread> &t; ~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); } } joiner{ warm };
     int64_t n_lookup = 0;
     {   // entries with the same (contig, pos, ref, ea) settle on the same record: count keys once
         std::unordered_map<std::string, int> keys;
@@ -230,6 +236,8 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             v.ctx.ck(npc_resident_reserve(v.ctx.h, slab_want, &v.slab_cap), "npc_resident_reserve");
         } catch (const std::exception &e) { v.err = e.what(); }
     };
+    for (auto &x : warm) if (x.joinable()) x.join();
+    timer.mark("CUDA context (overlapped)");
     if (D == 1) open_dev(0);
     else {                                            // CUDA context creation dominates: one thread per device
         std::vector<std::thread> th;

@@ -399,3 +399,49 @@ def test_c_abi_error_paths(nb):
     with pytest.raises(nb.NpcError, match="staging ring"):
         e0.stage_acquire()
     e0.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n", [9, 4099, 100003])
+def test_int16_rows_through_the_fused_kernel(nb, n, mode):
+    """int16 GT storage (records with more than 63 alleles; the reference treats every width alike,
+    src/nimpress.nim:381-391): diploid int16 cohorts run the fused pair kernel too -- a sample is one 32-bit word,
+    two samples per table lookup -- with alleles beyond ALT2, sentinels and the cohort's partial last chunk on the
+    exact decode.  Parity unpinned by the reference (no int16 fixture); the oracle widens like htslib."""
+    rng = np.random.default_rng(1600 + n)
+    V = 44
+    gt = random_cohort(rng, n, V, width=2, miss_rate=0.03, n_alt=2, sentinel_rate=0.003)
+    gt[5:9] = random_cohort(rng, n, 4, width=2, miss_rate=0.02, n_alt=90, sentinel_rate=0.01)[:, :gt.shape[1]]   # allele numbers an int8 cannot hold
+    rows = random_rows(rng, V, n_rows=70, n_alt=3)
+    eng = nb.Engine(n, ploidy=2, gt_width=2, max_rows_per_block=128, n_slots=2)
+    eng.set_policy(); eng.set_exact_order(mode == "exact"); eng.reset()
+    eng.score_host(gt, rows)
+    got = eng.finish(offset=0.5)
+    shape = eng.kernel_shape
+    eng.close()
+    assert shape["fused"] == (1 if mode == "exact" else 2), shape          # not the two-kernel sequence
+    assert_parity(got, oracle(gt, n, rows, offset=0.5), exact=mode == "exact")
+
+
+def test_int16_full_sample_width_500k(nb):
+    """The bench shard's sample width in int16 storage: the int8 synthetic cohort widened on the host, 256 variants."""
+    import torch
+    n, V, seed = 500_000, 256, 0x6E696D70
+    rng = np.random.default_rng(seed + 16)
+    af_thr = (rng.uniform(0.01, 0.5, size=V) * 65536).astype(np.uint32)
+    ms_thr = (rng.uniform(0, 0.1, size=V) * (1 << 24)).astype(np.uint32)
+    stride8 = -(-2 * n // 128) * 128
+    host8 = np.zeros((V, stride8), np.int8)
+    orc.synth_fill(host8, n, 0, seed, af_thr, ms_thr, np.ones(V, np.int32))
+    host16 = host8.astype(np.int16)
+    rows = random_rows(rng, V, n_rows=V, kinds=(0.9, 0.04, 0.03, 0.03), shuffle_gt=False)
+    want = oracle(host16, n, rows)
+    eng = nb.Engine(n, ploidy=2, gt_width=2, max_rows_per_block=V)
+    eng.set_policy(); eng.reset()
+    d = torch.from_numpy(host16.view(np.uint8).reshape(V, -1)).cuda()
+    eng.score_block_device(d, d.shape[1], V, rows)
+    got = eng.finish()
+    shape = eng.kernel_shape
+    eng.close()
+    assert shape["fused"] == 2 and shape["grid"] == 148, shape
+    assert_parity(got, want, exact=False)
