@@ -64,7 +64,6 @@ struct npc_ctx {
                                             // clears the half the next one uses (pair kernel)
     int fcounts_half = 0;
     int64_t fcounts_dirty[2] = { 0, 0 };    // words of each half written since it was last cleared
-    unsigned int *d_done = nullptr;         // per sample slab: row groups that have stored their partial sums (pair kernel)
     ull *d_trace = nullptr;                 // NPC_TRACE: 8 %globaltimer stamps of the last pair-kernel launch
     uint8_t *d_multi_scratch = nullptr;     // arena of npc_score_resident_multi's contraction
     size_t multi_scratch_bytes = 0;
@@ -119,7 +118,7 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_sums); cudaFree(ctx->d_out); cudaFree(ctx->d_nloci); cudaFree(ctx->d_counts);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_trace); cudaFree(ctx->d_done); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_trace); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
     if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->ev_reduce) cudaEventDestroy(ctx->ev_reduce);
     cudaFree(ctx->d_nloci_total); cudaFree(ctx->d_bridge); cudaFree(ctx->d_gather); cudaFree(ctx->d_ds_part);
@@ -218,8 +217,6 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         const size_t words = 2 * (size_t)std::max<int64_t>(c->max_rows, 1);
         NPC_CUDA(c, cudaMalloc(&c->d_fcounts, words * sizeof(ull)));
         NPC_CUDA(c, cudaMemset(c->d_fcounts, 0, words * sizeof(ull)));
-        NPC_CUDA(c, cudaMalloc(&c->d_done, 1024 * sizeof(unsigned int)));
-        NPC_CUDA(c, cudaMemset(c->d_done, 0, 1024 * sizeof(unsigned int)));
         if (env_int("NPC_TRACE", 0)) { NPC_CUDA(c, cudaMalloc(&c->d_trace, 8 * sizeof(ull))); NPC_CUDA(c, cudaMemset(c->d_trace, 0, 8 * sizeof(ull))); }
     }
     if (c->fast.ok && c->fast.Gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(c->fast.Gr - 1) * (size_t)c->n * sizeof(double)));
@@ -470,14 +467,17 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
     FusedParams P;
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
     P.sums = c->d_sums; P.counts = counts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
-    P.counts_next = counts_next; P.n_zero = n_zero; P.trace = c->d_trace; P.done = c->d_done;
+    P.counts_next = counts_next; P.n_zero = n_zero; P.trace = c->d_trace;
     P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
     P.Gs = t.Gs; P.Gr = gr; P.partials = c->d_partials;
     P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
     void *args[] = { &P };
     NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
     c->launches++;
-    if (gr > 1 && t.ver != 5) {                        // the pair kernel adds its row groups' partial sums itself
+    // Row groups > 1: a second, wide kernel adds the groups' partial sums in group order.  (Folding this into the tile
+    // kernel -- the last group of a slab to finish adds them -- was measured in round 2: one CTA per slab doing
+    // Gr - 1 dependent L2 reads per sample took 12 us where this kernel takes ~4, launch included.)
+    if (gr > 1) {
         k_add_partials<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_sums, c->d_partials, c->n, gr - 1);
         c->launches++;
         NPC_CUDA(c, cudaGetLastError());

@@ -35,9 +35,6 @@ struct FusedParams {
     // NPC_TRACE: %globaltimer stamps of CTA 0 (launch start, tables ready, first tile counted, last tile counted,
     // last tile accumulated, sums stored), for the low-n launch-floor analysis; nullptr = off
     ull *trace;
-    // pair kernel, Gr > 1: done[slab] counts the row groups of a sample slab that have stored their partial sums; the
-    // last one adds them in group order itself (and clears the counter), so no second kernel follows the launch
-    unsigned int *done;
 };
 
 constexpr int FUSED_CNT_BITS = 28;

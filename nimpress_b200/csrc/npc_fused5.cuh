@@ -441,32 +441,6 @@ k_fused_pair(const FusedParams P) {
             for (int e = 0; e < 8; e++)
                 if (e < valid[k]) sums_out[g * 8 + e] = acc[k][e];
         }
-        if (P.Gr > 1) {
-            // The row groups of this sample slab accumulate into separate vectors (group 0 into sums, group g > 0 into
-            // partials[g-1]).  The group that finishes LAST adds them, in group (= score-file) order whichever group it
-            // is: sums[s] = ((sums[s] + p_1[s]) + p_2[s]) + ...  Every consumer thread owns the same cells in every group.
-            __threadfence();
-            asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");
-            volatile uint32_t *s_last = s_rflags;                   // the producer is done with its flags: every tile was consumed
-            if (threadIdx.x == 0) *s_last = atomicAdd(&P.done[slab_id], 1u) == (unsigned)P.Gr - 1u ? 1u : 0u;
-            asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");
-            if (*s_last) {
-                __threadfence();
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const int64_t g = c0 + cell[k];
-#pragma unroll
-                    for (int e = 0; e < 8; e++)
-                        if (e < valid[k]) {
-                            const int64_t si = g * 8 + e;
-                            double a = __ldcg(P.sums + si);
-                            for (int q = 1; q < P.Gr; q++) a = __dadd_rn(a, __ldcg(P.partials + (int64_t)(q - 1) * P.n + si));
-                            P.sums[si] = a;
-                        }
-                }
-                if (threadIdx.x == 0) P.done[slab_id] = 0u;          // ready for the next launch
-            }
-        }
         if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[5] = globaltimer_ns();
     }
 }

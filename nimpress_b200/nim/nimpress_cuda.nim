@@ -76,4 +76,15 @@ proc npc_kernel_shape*(ctx: NpcCtx; shape: ptr array[8, int32]): cint
 proc npc_synth_fill_device*(ctx: NpcCtx; gtDev: pointer; rowStride, v0, nRows: int64; seed: uint64;
                             afThr16Dev, missThr24Dev: ptr uint32; altCodeDev: ptr int32): cint
 proc npc_version*(): cint
+proc npc_warmup*(device: cint): cint
+proc npc_create2*(ctx: ptr NpcCtx; device: cint; nSamples: int64; ploidy, gtWidth: int32;
+                  maxRowsPerBlock: int64; nSlots: int32; stagingRows: int64): cint
+proc npc_set_dosage_rows*(ctx: NpcCtx; on: int32): cint
+proc npc_trace*(ctx: NpcCtx; stamps: ptr array[8, uint64]): cint
+# several GPUs: one process (npc_reduce) or one process per GPU over NCCL (npc_comm_*)
+proc npc_reduce*(ctxs: ptr NpcCtx; nCtx: int32; offset: ptr float64; scoresOut: ptr float64; nlociOut: ptr int64): cint
+proc npc_comm_unique_id*(id128: ptr uint8): cint
+proc npc_comm_init*(ctx: NpcCtx; id128: ptr uint8; rank, world: int32): cint
+proc npc_comm_combine*(ctx: NpcCtx; offset: ptr float64; scoresOut: ptr float64; nlociOut: ptr int64): cint
+proc npc_combined_device_ptr*(ctx: NpcCtx; scoresDev: ptr ptr float64; nlociDev: ptr ptr int64): cint
 {.pop.}

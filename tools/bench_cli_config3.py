@@ -88,7 +88,7 @@ def main():
     with open(score, "w") as f:
         f.write("config3 slice\nsynthetic\ncitation\nhs37d5\n0.125\n")
         for v in range(V):
-            f.write(f"1\t{positions[v]}\tA\t{'A' if ref_is_ea[v] else 'C'}\t{beta[v]!r}\t{round(float(af[v]), 4)!r}\n")
+            f.write(f"1\t{positions[v]}\tA\t{'A' if ref_is_ea[v] else 'C'}\t{float(beta[v])!r}\t{round(float(af[v]), 4)!r}\n")
     threads = os.cpu_count() or 4
     pool = ThreadPoolExecutor(threads)
     stride = 2 * n
