@@ -73,6 +73,7 @@ struct npc_ctx {
     bool ds = false;
     double *d_ds_part = nullptr;            // [max_rows][n_blocks] block sums of the tally pass
     // cross-GPU combine (npc_reduce.cuh)
+    cudaEvent_t ev_multi = nullptr;         // npc_score_resident_multi: orders its copy-stream work against the compute stream
     cudaEvent_t ev_reduce = nullptr;        // "this context's partial sums are final"
     ull *d_nloci_total = nullptr;           // combined nloci, next to d_out (the combined scores)
     double *d_bridge = nullptr;             // npc_reduce without peer access: [n_ctx - 1][n] copies of the other partials
@@ -121,6 +122,7 @@ extern "C" void npc_destroy(npc_ctx *ctx) {
     cudaFree(ctx->d_rows); cudaFree(ctx->d_rowp); cudaFree(ctx->d_log); cudaFree(ctx->d_fcounts); cudaFree(ctx->d_trace); if (ctx->slab_owned) cudaFree(ctx->d_slab); cudaFree(ctx->d_partials); cudaFree(ctx->d_multi_scratch);
     if (ctx->ev_slab) cudaEventDestroy(ctx->ev_slab);
     if (ctx->ev_reduce) cudaEventDestroy(ctx->ev_reduce);
+    if (ctx->ev_multi) cudaEventDestroy(ctx->ev_multi);
     cudaFree(ctx->d_nloci_total); cudaFree(ctx->d_bridge); cudaFree(ctx->d_gather); cudaFree(ctx->d_ds_part);
     if (ctx->comm && g_nccl.lib) g_nccl.CommDestroy(ctx->comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -739,7 +741,9 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     const int64_t R = row0[S];
     std::vector<npc_row> erows;
     std::vector<int32_t> ent((size_t)R, -1), score_of((size_t)R, 0);
-    std::vector<int32_t> head((size_t)c->slab_rows, -1), next, last_score, repeats;   // per slab row: chain of its entries
+    // per slab row: the entry of effect alleles 0..3 directly, a chain only for rarer alleles
+    std::vector<int32_t> direct((size_t)c->slab_rows * 4, -1), head, next, last_score, repeats;
+    erows.reserve((size_t)std::min<int64_t>(R, c->slab_rows * 2));
     for (int k = 0; k < S; k++)
         for (int64_t i = 0; i < n_rows[k]; i++) {
             const npc_row &r = rows[k][i];
@@ -748,13 +752,19 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
             if (r.kind != NPC_KIND_GT || r.gt_row < 0) continue;
             if (r.gt_row >= c->slab_rows) return fail(c, NPC_EINVAL, "npc_score_resident_multi: gt_row outside the resident slab");
             if (r.eaidx < 0 || r.eaidx > 62) return 1;               // no int8 code can match: leave it to the general path
-            int32_t e = head[r.gt_row];
-            while (e >= 0 && erows[e].eaidx != r.eaidx) e = next[e];
+            int32_t e;
+            if (r.eaidx < 4) e = direct[(size_t)r.gt_row * 4 + r.eaidx];
+            else {
+                if (head.empty()) head.assign((size_t)c->slab_rows, -1);
+                e = head[r.gt_row];
+                while (e >= 0 && erows[e].eaidx != r.eaidx) e = next[e];
+            }
             if (e < 0) {
                 e = (int32_t)erows.size();
                 npc_row er = r; er.kind = NPC_KIND_GT;
-                erows.push_back(er); next.push_back(head[r.gt_row]); last_score.push_back(-1); repeats.push_back(0);
-                head[r.gt_row] = e;
+                erows.push_back(er); last_score.push_back(-1); repeats.push_back(0); next.push_back(-1);
+                if (r.eaidx < 4) direct[(size_t)r.gt_row * 4 + r.eaidx] = e;
+                else { next[e] = head[r.gt_row]; head[r.gt_row] = e; }
             }
             ent[j] = e;
             if (last_score[e] != k) { last_score[e] = k; repeats[e] = 0; }
@@ -814,20 +824,27 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     cudaStream_t st = c->stream;
     mark("scratch arena");
     NPC_CUDA(c, cudaMemcpyAsync(d_erows, erows.data(), E * sizeof(npc_row), cudaMemcpyHostToDevice, st));
-    NPC_CUDA(c, cudaMemcpyAsync(d_entry_row, entry_row.data(), Ep * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    NPC_CUDA(c, cudaMemcpyAsync(d_entry_pat, entry_pat.data(), Ep * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    for (int k = 0; k < S; k++) if (n_rows[k])
-        NPC_CUDA(c, cudaMemcpyAsync(d_all + row0[k], rows[k], n_rows[k] * sizeof(npc_row), cudaMemcpyHostToDevice, st));
-    NPC_CUDA(c, cudaMemcpyAsync(d_ent, ent.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    NPC_CUDA(c, cudaMemcpyAsync(d_score_of, score_of.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    NPC_CUDA(c, cudaMemcpyAsync(d_row0, row0.data(), (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    NPC_CUDA(c, cudaMemsetAsync(d_nloci, 0, S * sizeof(ull), st));
     for (int s = 0; s < c->n_slots; s++) NPC_CUDA(c, cudaStreamWaitEvent(st, c->ev_h2d[s], 0));   // every upload has landed
 
-    // ---- tallies once per entry, decisions per definition (the same k_decide as every path) ------
+    // ---- tallies once per entry: launched first, so that the pass over the slab (the long pole) runs while the host
+    // pushes the row tables of every definition through the copy stream
     int rc = launch_count(c, c->d_slab, c->slab_stride, d_erows, E, d_ecounts);
     if (rc) return rc;
-    mark("tally kernel");
+    cudaStream_t cs = c->copy_stream;
+    if (!c->ev_multi) NPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_multi, cudaEventDisableTiming));
+    NPC_CUDA(c, cudaMemcpyAsync(d_entry_row, entry_row.data(), Ep * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    NPC_CUDA(c, cudaMemcpyAsync(d_entry_pat, entry_pat.data(), Ep * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    for (int k = 0; k < S; k++) if (n_rows[k])
+        NPC_CUDA(c, cudaMemcpyAsync(d_all + row0[k], rows[k], n_rows[k] * sizeof(npc_row), cudaMemcpyHostToDevice, cs));
+    NPC_CUDA(c, cudaMemcpyAsync(d_ent, ent.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    NPC_CUDA(c, cudaMemcpyAsync(d_score_of, score_of.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    NPC_CUDA(c, cudaMemcpyAsync(d_row0, row0.data(), (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+    NPC_CUDA(c, cudaMemsetAsync(d_nloci, 0, S * sizeof(ull), cs));
+    NPC_CUDA(c, cudaEventRecord(c->ev_multi, cs));
+    NPC_CUDA(c, cudaStreamWaitEvent(st, c->ev_multi, 0));
+    mark("tally kernel + row tables H2D");
+
+    // ---- decisions per definition (the same k_decide as every path) -----------------------------
     if (R) {
         k_multi_gather<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(d_ent, R, d_ecounts, d_counts);
         c->launches++;
@@ -844,10 +861,13 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     std::vector<ull> nloci(S);
     NPC_CUDA(c, cudaMemcpyAsync(scale.data(), d_scale, S * sizeof(MultiScale), cudaMemcpyDeviceToHost, st));
     NPC_CUDA(c, cudaMemcpyAsync(nloci.data(), d_nloci, S * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    for (int k = 0; k < S; k++) if (loci_out && loci_out[k] && n_rows[k])
-        NPC_CUDA(c, cudaMemcpyAsync(loci_out[k], d_log + row0[k], n_rows[k] * sizeof(npc_locus), cudaMemcpyDeviceToHost, st));
+    NPC_CUDA(c, cudaEventRecord(c->ev_multi, st));
     NPC_CUDA(c, cudaStreamSynchronize(st));
-    mark("decide + scale + log D2H");
+    // the per-locus records go home on the copy stream while the contraction runs
+    NPC_CUDA(c, cudaStreamWaitEvent(cs, c->ev_multi, 0));
+    for (int k = 0; k < S; k++) if (loci_out && loci_out[k] && n_rows[k])
+        NPC_CUDA(c, cudaMemcpyAsync(loci_out[k], d_log + row0[k], n_rows[k] * sizeof(npc_locus), cudaMemcpyDeviceToHost, cs));
+    mark("decide + scale");
     std::vector<int32_t> fexp(S, 0);
     int rps = npc::MC_DIGITS;
     for (int k = 0; k < S; k++) {
@@ -906,6 +926,7 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
         mark("scores D2H");
     }
     NPC_CUDA(c, cudaEventRecord(c->ev_slab, st));
+    NPC_CUDA(c, cudaStreamSynchronize(cs));                                // the records have landed
     for (int k = 0; k < S; k++) if (nloci_out) nloci_out[k] = (int64_t)nloci[k];
     return 0;
 }
