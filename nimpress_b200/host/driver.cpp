@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <future>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 
@@ -110,6 +113,26 @@ struct PhaseTimer {
     }
 };
 
+// CUDA driver + primary-context creation is most of a short run's start-up (~1 s per process on the boxes seen):
+// it is started once per device on a thread of its own as soon as a scoring call begins -- while the inputs are
+// opened, indexed and, when there is a .tbi / .csi, consulted -- and waited for only where a context is needed.
+std::mutex g_warm_mutex;
+std::map<int, std::shared_future<void>> g_warm;
+void start_warm(int device) {
+    std::lock_guard<std::mutex> g(g_warm_mutex);
+    if (!g_warm.count(device)) g_warm[device] = std::async(std::launch::async, [device] { npc_warmup(device); }).share();
+}
+void wait_warm(int device) {
+    std::shared_future<void> f;
+    {
+        std::lock_guard<std::mutex> g(g_warm_mutex);
+        auto it = g_warm.find(device);
+        if (it == g_warm.end()) return;
+        f = it->second;
+    }
+    f.wait();
+}
+
 struct LayoutOverflow { int width, ploidy; };      // a matched record does not fit the context's GT layout
 struct SlabOverflow {};                            // several score files, and their matched rows exceed device memory
 struct NoIndex {};                                 // the index-driven pass is not possible / not worthwhile: stream the file
@@ -165,12 +188,6 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
     outs.assign(S, ScoreResult());
 
     PhaseTimer timer;
-    // CUDA driver + context creation is most of a short run's start-up (~0.5-1 s): start it now, on threads of its
-    // own, while the score entries are indexed and the genotype file's index is consulted
-    std::vector<int> warm_ids = p.devices.empty() ? std::vector<int>{ p.device } : p.devices;
-    std::vector<std::thread> warm;
-    for (int d : warm_ids) warm.emplace_back([d] { npc_warmup(d); });
-    struct Joiner { std::vector<std::thread> &t; ~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); } } joiner{ warm };
     int64_t n_lookup = 0;
     {   // entries with the same (contig, pos, ref, ea) settle on the same record: count keys once
         std::unordered_map<std::string, int> keys;
@@ -236,8 +253,8 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             v.ctx.ck(npc_resident_reserve(v.ctx.h, slab_want, &v.slab_cap), "npc_resident_reserve");
         } catch (const std::exception &e) { v.err = e.what(); }
     };
-    for (auto &x : warm) if (x.joinable()) x.join();
-    timer.mark("CUDA context (overlapped)");
+    for (int d : dev_ids) wait_warm(d);
+    timer.mark("CUDA context (waited for)");
     if (D == 1) open_dev(0);
     else {                                            // CUDA context creation dominates: one thread per device
         std::vector<std::thread> th;
@@ -416,6 +433,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
 
 bool compute_polygenic_scores_multi(const std::vector<const ScoreFile *> &scores, const std::string &genotype_path,
                                     const GenomeIntervals &cov, const ScoreParams &p, std::vector<ScoreResult> &outs) {
+    for (int d : (p.devices.empty() ? std::vector<int>{ p.device } : p.devices)) start_warm(d);
     int width = 1, ploidy = 2;                      // BCF's usual GT layout: int8, diploid
     if (p.use_ds) { width = 4; ploidy = 1; }        // FORMAT/DS: one float per sample
     bool seekable = true;                           // first try the index-driven pass (needs <file>.tbi / .csi)
