@@ -1,3 +1,11 @@
+// stats.cpp -- the statistics behind the reference's AF-mismatch WARN lines.
+//
+// lbinom / dbinom / betacf / betai / pbinom below (up to `count_tail`) TRANSLITERATE src/nimpress.nim:51-152 into C++,
+// operation for operation: the WARN lines print p-value-dependent decisions, so these functions must return the
+// reference's doubles bit for bit (the Numerical-Recipes continued fraction included) and there is no second way to
+// write them.  The same text exists once more in oracle/nimpress_oracle.c, which is the checker.  What is new here is
+// binom_test's evaluation: the reference enumerates all n + 1 outcomes (:155-188); `count_tail` finds the same
+// integration limits by bisection on the monotone tails (tested equal to the enumeration, tests/test_host_cpu.py).
 #include "stats.hpp"
 
 #include <algorithm>
