@@ -445,3 +445,29 @@ def test_int16_full_sample_width_500k(nb):
     eng.close()
     assert shape["fused"] == 2 and shape["grid"] == 148, shape
     assert_parity(got, want, exact=False)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_pair_table_every_code_combination(nb, mode):
+    """The pair lookup of the fused kernel (npc_fused5.cuh) indexes a table by the four allele codes of two samples:
+    every one of the 4^4 combinations of {missing, REF, ALT1, ALT2} -- with either phase bit -- in every word position
+    of a chunk, for effect alleles REF, ALT1, ALT2 (a table each), ALT3 and ALT7 (the no-match table) and in both row
+    parities of a tile, against the oracle."""
+    rng = np.random.default_rng(44)
+    combos = np.array([[a, b, c, d] for a in range(4) for b in range(4) for c in range(4) for d in range(4)], dtype=np.int64)   # [256, 4]
+    V = 24
+    n = 2 * 256 * 4                                            # every combination in each of the 4 word positions
+    gt = np.zeros((V, 2 * n), dtype=np.int8)
+    for v in range(V):
+        perm = np.concatenate([rng.permutation(256) for _ in range(4)])
+        codes = combos[perm].reshape(-1)                       # allele codes of consecutive samples, 2 per sample
+        raw = (codes << 1) | rng.integers(0, 2, size=codes.size)
+        gt[v] = np.roll(raw.reshape(-1, 4), v % 4, axis=0).reshape(-1).astype(np.int8)     # shift word positions row by row
+    rows = np.zeros(40, dtype=nb.ROW_DTYPE)
+    rows["gt_row"] = rng.integers(0, V, size=40)
+    rows["eaidx"] = np.tile([0, 1, 2, 3, 7], 8)
+    rows["beta"] = np.round(rng.normal(0, 0.3, 40), 4)
+    rows["eaf"] = np.round(rng.uniform(0.05, 0.5, 40), 4)
+    rows["ref_is_ea"] = rows["eaidx"] == 0
+    got = run_engine(nb, gt, n, rows, offset=0.0, policy=dict(maxmis=1.0), mode=mode)
+    assert_parity(got, oracle(gt, n, rows, policy=dict(maxmis=1.0)), exact=mode == "exact")

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--samples", type=int, default=500_000)
     ap.add_argument("--variants", type=int, default=8192)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--width", type=int, default=2, choices=[2, 4], help="2: int16 (fused pair kernel); 4: int32 (generic two-kernel sequence)")
     args = ap.parse_args()
     import torch
     import nimpress_b200 as nb
@@ -34,10 +35,11 @@ def main():
                          torch.from_numpy(miss_thr.view(np.int32)).to(dev), torch.from_numpy(alt).to(dev))
     torch.cuda.synchronize()
     e8.close()
-    g16 = g8.to(torch.int16)                          # values 0..5: the same numbers, two bytes each
+    W = args.width
+    g16 = g8.to(torch.int16 if W == 2 else torch.int32)   # values 0..5: the same numbers, W bytes each
     del g8
-    stride16 = g16.shape[1] * 2
-    eng = nb.Engine(n, ploidy=2, gt_width=2, max_rows_per_block=V, n_slots=0)
+    stride16 = g16.shape[1] * W
+    eng = nb.Engine(n, ploidy=2, gt_width=W, max_rows_per_block=V, n_slots=0)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
@@ -58,8 +60,8 @@ def main():
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
-    alg = 4.0 * n * V + 32.0 * V + 16.0 * n
-    print(json.dumps(dict(workload=f"{V} variants x {n} samples, int16 diploid GT (4 B/genotype), one launch", launch_ms=t * 1e3,
+    alg = 2.0 * W * n * V + 32.0 * V + 16.0 * n
+    print(json.dumps(dict(workload=f"{V} variants x {n} samples, int{8 * W} diploid GT ({2 * W} B/genotype), one call", launch_ms=t * 1e3,
                           genotypes_per_s=n * V / t, achieved_gbs=alg / t / 1e9, peak_gbs=peak, roofline_frac=alg / t / 1e9 / peak,
                           kernel_shape=eng.kernel_shape, nloci=eng.finish(want_loci=False)["nloci"])))
     eng.close()
