@@ -465,6 +465,7 @@ def b200_arm(args):
                 "launch_ms": launch_ms, "rows_per_launch": launch_rows, "launches_per_step": len(launch_events) // args.steps,
                 "kernel": {2: ("k_fused_pair" if tile_ver == 5 else "k_fused_tile4") + " (count+decide+accumulate, one persistent launch per block)",
                            1: ("k_fused_pair" if tile_ver == 5 else "k_fused_tile4") + " in exact-order mode (one persistent launch per block)",
+                           3: "k_count_i8x2 + k_decide, then k_fused_pair in decided mode per sample slab (cohort too wide for one resident pass)",
                            0: "k_count_i8x2 + k_decide + k_accum_i8x2 sequence"}[shape["fused"]],
                 "algorithmic_bytes_per_launch": alg_bytes}
 

@@ -286,7 +286,9 @@ int npc_set_exact_order(npc_ctx *ctx, int32_t on);
 int npc_set_dosage_rows(npc_ctx *ctx, int32_t on);
 
 /* Which kernels npc_score_block* uses for this context: shape[0] = 2 for the fused tile kernel in
- * its default mode, 1 in exact-order mode (int8 diploid cohorts that fit one resident pass),
+ * its default mode, 1 in exact-order mode (int8 / int16 diploid cohorts that fit one resident pass),
+ * 3 for cohorts too wide for that (> ~1.2 M samples per GPU: tally + decide over all samples, then the
+ * tile kernel in "decided" mode once per slab of the sample axis),
  * 0 for the count/decide/accumulate sequence; then grid (tile kernel: sample slabs * 1000 + row
  * groups), consumer warps, chunks per thread, rows
  * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + decider warps, dynamic

@@ -52,6 +52,11 @@ struct npc_ctx {
     };
     TileCfg fast;                           // default: sample slabs x row groups, tile-wise summation
     TileCfg exact_cfg;                      // npc_set_exact_order: 1-D grid, reference summation order
+    // cohorts too wide for one resident pass (> ~1.2 M samples): tally + decide over all samples first, then the tile
+    // kernel in "decided" mode over wide_slabs slabs of wide_n samples each (both shapes: default / exact order)
+    TileCfg wide, wide_exact;
+    int64_t wide_n = 0;
+    int wide_slabs = 0;
     bool exact = false;
     int num_sms = 0;
     double *d_partials = nullptr;           // [fast.Gr - 1][n] partial sums of row groups 1..
@@ -151,8 +156,8 @@ static const void *tile_kernel(int ver, int K, bool exact, int width = 1) {
 // Launch shape of the tile kernel for `gr` row groups: Gs sample slabs (one CTA each), K chunks per
 // consumer thread, a raw ring of Sr stages (~110 KB of loads in flight per SM), the rest of shared
 // memory as index-ring slots, lag L = Sc - 1 tiles, A decider warps.
-static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg &t) {
-    const int64_t C = (c->n + 7) / 8;
+static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg &t, int64_t n_samples = -1) {
+    const int64_t C = ((n_samples < 0 ? c->n : n_samples) + 7) / 8;
     const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
     if (gs < 1) return false;
     const int64_t nch = (C + gs - 1) / gs;
@@ -209,13 +214,21 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     }
     tile_config(c, best_gr, max_smem, c->fast);
     tile_config(c, 1, max_smem, c->exact_cfg);
-    for (int ex = 0; ex < 2; ex++) {
-        const npc_ctx::TileCfg &t = ex ? c->exact_cfg : c->fast;
+    if (!c->fast.ok && c->width == 1 && env_int("NPC_TILE_V", 5) != 4) {
+        // too wide: the fewest equal slabs (multiples of 1024 samples) the tile kernel can hold
+        for (int S = 2; S <= 64 && !c->wide.ok; S++) {
+            const int64_t ns = ((c->n + S - 1) / S + 1023) / 1024 * 1024;
+            if (tile_config(c, 1, max_smem, c->wide, ns) && tile_config(c, 1, max_smem, c->wide_exact, ns)) { c->wide_n = ns; c->wide_slabs = (int)((c->n + ns - 1) / ns); }
+            else c->wide.ok = c->wide_exact.ok = false;
+        }
+    }
+    for (int ex = 0; ex < 4; ex++) {
+        const npc_ctx::TileCfg &t = ex == 0 ? c->fast : ex == 1 ? c->exact_cfg : ex == 2 ? c->wide : c->wide_exact;
         if (!t.ok) continue;
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, ex != 0, c->width), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, (ex & 1) != 0, c->width), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
         if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     }
-    if (c->fast.ok || c->exact_cfg.ok) {
+    if (c->fast.ok || c->exact_cfg.ok || c->wide.ok) {
         const size_t words = 2 * (size_t)std::max<int64_t>(c->max_rows, 1);
         NPC_CUDA(c, cudaMalloc(&c->d_fcounts, words * sizeof(ull)));
         NPC_CUDA(c, cudaMemset(c->d_fcounts, 0, words * sizeof(ull)));
@@ -341,10 +354,11 @@ extern "C" int npc_trace(npc_ctx *ctx, uint64_t out[8]) {
 
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     if (!ctx || !shape) return NPC_EINVAL;
-    const npc_ctx::TileCfg &t = ctx->exact ? ctx->exact_cfg : ctx->fast;
+    const bool wide = !(ctx->exact ? ctx->exact_cfg.ok : ctx->fast.ok) && ctx->wide.ok;
+    const npc_ctx::TileCfg &t = wide ? (ctx->exact ? ctx->wide_exact : ctx->wide) : ctx->exact ? ctx->exact_cfg : ctx->fast;
     memset(shape, 0, 8 * sizeof(int32_t));
     if (!t.ok) return NPC_OK;
-    shape[0] = ctx->exact ? 1 : 2; shape[1] = t.Gs * 1000 + (ctx->exact ? 1 : t.Gr); shape[2] = t.nc; shape[3] = t.K;
+    shape[0] = wide ? 3 : ctx->exact ? 1 : 2; shape[1] = t.Gs * 1000 + (ctx->exact ? 1 : t.Gr); shape[2] = t.nc; shape[3] = t.K;
     shape[4] = F4_R; shape[5] = t.Sr * 1000 + t.Sc; shape[6] = t.L * 100 + t.A; shape[7] = (int32_t)t.smem;
     return NPC_OK;
 }
@@ -473,6 +487,7 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
     P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
     P.Gs = t.Gs; P.Gr = gr; P.partials = c->d_partials;
     P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
+    P.decided = nullptr;
     void *args[] = { &P };
     NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
     c->launches++;
@@ -485,6 +500,39 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
         NPC_CUDA(c, cudaGetLastError());
     }
     c->log_len += n_rows;
+    return NPC_OK;
+}
+
+// Cohorts too wide for one resident pass: tally + decide over all samples (the two kernels of the generic sequence),
+// then the tile kernel in "decided" mode once per slab of the sample axis -- it decodes and accumulates, the deciders
+// read the rows' contributions from d_rowp.  The slab is read twice (4 B/genotype), the second time at the tile
+// kernel's rate instead of k_accum's.
+static int launch_wide(npc_ctx *c, bool exact, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
+    if (n_rows == 0) return NPC_OK;
+    int rc = launch_count(c, gt, row_stride, d_rows, n_rows, c->d_counts);
+    if (rc) return rc;
+    if ((rc = ensure_log(c, n_rows))) return rc;
+    k_decide<<<(unsigned)((n_rows + 127) / 128), 128, 0, c->stream>>>(d_rows, n_rows, c->d_counts, c->pol, c->n, c->d_rowp,
+                                                                      c->d_log + c->log_len, c->d_nloci);
+    c->launches++;
+    NPC_CUDA(c, cudaGetLastError());
+    c->log_len += n_rows;
+    const npc_ctx::TileCfg &t = exact ? c->wide_exact : c->wide;
+    for (int s = 0; s < c->wide_slabs; s++) {
+        const int64_t s0 = (int64_t)s * c->wide_n, ns = std::min<int64_t>(c->wide_n, c->n - s0);
+        if (ns <= 0) break;
+        FusedParams P;
+        memset(&P, 0, sizeof(P));
+        P.gt = gt + s0 * 2; P.row_stride = row_stride; P.n = ns; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
+        P.sums = c->d_sums + s0; P.counts = c->d_fcounts; P.log = nullptr; P.nloci = c->d_nloci;
+        P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
+        P.Gs = t.Gs; P.Gr = 1; P.partials = nullptr;
+        P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
+        P.decided = c->d_rowp;
+        void *args[] = { &P };
+        NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
+        c->launches++;
+    }
     return NPC_OK;
 }
 
@@ -519,6 +567,7 @@ static int launch_dosage(npc_ctx *c, const uint8_t *gt, int64_t row_stride, cons
 static int launch_block(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
     if (c->ds) return launch_dosage(c, gt, row_stride, d_rows, n_rows);
     if (c->exact ? c->exact_cfg.ok : c->fast.ok) return launch_fused(c, c->exact ? c->exact_cfg : c->fast, c->exact, gt, row_stride, d_rows, n_rows);
+    if (c->wide.ok && env_int("NPC_WIDE", 1)) return launch_wide(c, c->exact, gt, row_stride, d_rows, n_rows);
     int rc = launch_count(c, gt, row_stride, d_rows, n_rows, c->d_counts);
     if (rc) return rc;
     return launch_decide_accum(c, gt, row_stride, d_rows, n_rows, c->d_counts);

@@ -35,6 +35,10 @@ struct FusedParams {
     // NPC_TRACE: %globaltimer stamps of CTA 0 (launch start, tables ready, first tile counted, last tile counted,
     // last tile accumulated, sums stored), for the low-n launch-floor analysis; nullptr = off
     ull *trace;
+    // pair kernel, cohorts too wide for one resident pass: the rows were tallied and decided beforehand (k_count_* +
+    // k_decide over ALL samples) and this launch covers one slab of the sample axis: no tallies are published, the
+    // deciders take the rows' contributions from decided[row] instead of polling the grid.  nullptr: the normal mode.
+    const RowP *decided;
 };
 
 constexpr int FUSED_CNT_BITS = 28;

@@ -199,7 +199,7 @@ k_fused_pair(const FusedParams P) {
         // per tile: sum the per-lane counters of every group (and clear them), reduce over the lanes, one
         // 64-bit RED per row: tallies and arrival count in the same word, so the data is the flag
         int s = 0; uint32_t ph = 0;
-        for (int64_t t = 0; t < n_tiles; t++) {
+        for (int64_t t = 0; t < (P.decided ? 0 : n_tiles); t++) {
             mbar_wait_sleep(bar_cnt + 8u * s, ph, P.aux_sleep_ns);
             const uint32_t base = sb + M.cnt + (uint32_t)s * cnt_slot + (uint32_t)lane * 4u;
             uint32_t d01 = 0, m01 = 0, d23 = 0, m23 = 0;             // 16-bit halves: row a | row b
@@ -242,7 +242,11 @@ k_fused_pair(const FusedParams P) {
             }
             double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // a dropped row adds +0.0: the identity
             int used = 0;
-            if (have) {
+            if (have && P.decided) {
+                const RowP rp = P.decided[my_row];
+                if (rp.mode == MODE_DECODE) { v0 = rp.c0; v1 = rp.c1; v2 = rp.c2; v3 = rp.cm; }
+                else if (rp.mode == MODE_CONST) { v0 = v1 = v2 = v3 = rp.c0; }
+            } else if (have) {
                 const ull *word = P.counts + my_row;
                 ull v = ld_relaxed_gpu_u64(word);
                 while ((v >> 56) != (ull)Gs) { __nanosleep(500); v = ld_relaxed_gpu_u64(word); }      // all slabs of this row group
@@ -254,7 +258,7 @@ k_fused_pair(const FusedParams P) {
                 else if (rp.mode == MODE_CONST) { v0 = v1 = v2 = v3 = rp.c0; }
             }
             vrow[lane * 4 + 0] = v0; vrow[lane * 4 + 1] = v1; vrow[lane * 4 + 2] = v2; vrow[lane * 4 + 3] = v3;
-            if (slab_id == 0) {
+            if (slab_id == 0 && !P.decided) {
                 used = __reduce_add_sync(0xffffffffu, used);
                 if (lane == 0 && used) atomicAdd(P.nloci, (ull)used);
             }
@@ -379,7 +383,7 @@ k_fused_pair(const FusedParams P) {
                     // tallies of rows (0,1) / (2,3): the low 24 bits of the sums over the chunk's four words (four
                     // 6-bit fields: d_a, d_b, m_a, m_b); whatever the code bytes add up to stays in the top byte
                     const uint32_t SA = (A4[0] + A4[1]) + (A4[2] + A4[3]), SB = (B4[0] + B4[1]) + (B4[2] + B4[3]);
-                    if (own[k]) {
+                    if (own[k] && !P.decided) {
                         red_shared_add_u32(cnt_base + cnt_off[k], SA);
                         red_shared_add_u32(cnt_base + cnt_off[k] + 128u, SB);
                     }

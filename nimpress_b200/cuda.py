@@ -322,7 +322,7 @@ class Engine:
         d["decider_warps"], d["lag"] = d["lag"] % 100, d["lag"] // 100
         d["raw_stages"], d["index_tiles"] = d["stages"] // 1000, d["stages"] % 1000
         del d["stages"]
-        if d["fused"] in (1, 2):                 # tile kernel: grid = sample slabs x (max) row groups
+        if d["fused"] in (1, 2, 3):              # tile kernel: grid = sample slabs x (max) row groups
             d["row_groups"], d["grid"] = d["grid"] % 1000, d["grid"] // 1000
             d["grid"] *= d["row_groups"]
         return d

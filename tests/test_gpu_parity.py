@@ -471,3 +471,42 @@ def test_pair_table_every_code_combination(nb, mode):
     rows["ref_is_ea"] = rows["eaidx"] == 0
     got = run_engine(nb, gt, n, rows, offset=0.0, policy=dict(maxmis=1.0), mode=mode)
     assert_parity(got, oracle(gt, n, rows, policy=dict(maxmis=1.0)), exact=mode == "exact")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cohort_wider_than_one_resident_pass(nb, mode):
+    """1,300,000 samples on one GPU: more than the tile kernel keeps resident (~1.2 M).  The rows are tallied and
+    decided over all samples first, then the tile kernel runs in "decided" mode once per slab of the sample axis
+    (kernel_shape fused = 3): per-locus records equal, scores bit-equal in exact-order mode."""
+    import torch
+    n, V, seed = 1_300_000, 48, 0x6E696D70
+    rng = np.random.default_rng(seed + 3)
+    af_thr = (rng.uniform(0.01, 0.5, size=V) * 65536).astype(np.uint32)
+    ms_thr = (rng.uniform(0, 0.1, size=V) * (1 << 24)).astype(np.uint32)
+    alt = np.ones(V, np.int32)
+    stride = -(-2 * n // 128) * 128
+    host = np.zeros((V, stride), np.int8)
+    orc.synth_fill(host, n, 0, seed, af_thr, ms_thr, alt)
+    rows = random_rows(rng, V, n_rows=V + 9, kinds=(0.85, 0.05, 0.05, 0.05))
+    want = orc.score_matrix(host, n, 2, rows.astype(orc.ROW_DTYPE), offset=0.25, threads=8)
+    eng = nb.Engine(n, max_rows_per_block=128)
+    eng.set_policy(); eng.set_exact_order(mode == "exact"); eng.reset()
+    d = torch.from_numpy(host.view(np.uint8)).cuda()
+    eng.score_block_device(d, stride, V, rows)
+    got = eng.finish(offset=0.25)
+    shape = eng.kernel_shape
+    eng.close()
+    assert shape["fused"] == 3, shape
+    # threads=8 in the oracle adds per-thread partial sums: compare the scores at the re-association tolerance, the records exactly
+    assert_parity(got, want, exact=False)
+    if mode == "exact":
+        # bit-equality of the chain: samples whose imputed values do not depend on the cohort tallies
+        pol = dict(maxmis=1.0, imp_sample="ps")
+        a = orc.score_matrix(host[:, :2 * 4096].copy(), 4096, 2, rows.astype(orc.ROW_DTYPE), offset=0.25, **pol)
+        eng = nb.Engine(n, max_rows_per_block=128)
+        eng.set_policy(**pol); eng.set_exact_order(True); eng.reset()
+        eng.score_block_device(d, stride, V, rows)
+        b = eng.finish(offset=0.25)
+        eng.close()
+        ok = ~np.isnan(a["scores"])
+        assert np.array_equal(bits(a["scores"][ok]), bits(b["scores"][:4096][ok]))

@@ -125,6 +125,21 @@ def test_host_devices_split(api, tmp_path, monkeypatch, exact):
             assert score_excess(got.scores, want["scores"], want) <= 1.0
 
 
+def test_more_contexts_than_score_rows(api, tmp_path, monkeypatch):
+    """Five contexts, three score rows (one of them absent from the file): ranges may be empty; the result is the oracle's."""
+    rng = np.random.default_rng(79)
+    d = make_dataset(str(tmp_path), rng, n=50, V=30)
+    lines = open(d["score"]).read().split("\n")
+    small = tmp_path / "small.score"
+    small.write_text("\n".join(lines[:5] + lines[5:7] + ["1\t999999999\tA\tC\t0.25\t0.1"]) + "\n")
+    want = orc.compute_scores_files(str(small), d["vcf"])
+    monkeypatch.setenv("NIMPRESS_SPLIT", "5")
+    got = api.run(str(small), d["bcf"])
+    assert got.devices == 5 and got.nloci == want["nloci"] and got.warnings == want["warn"]
+    assert_loci_equal(got.loci, want["loci"])
+    assert np.array_equal(np.isnan(got.scores), np.isnan(want["scores"])) and score_excess(got.scores, want["scores"], want) <= 1.0
+
+
 def test_cli_devices_option(api, tmp_path, monkeypatch, capfd):
     """`nimpress --devices=<list>` prints what the single-device run prints, to the last digit that the
     re-association leaves alone (compared as floats, 1e-12 relative + floor); bad lists are usage errors."""
