@@ -259,6 +259,10 @@ int npc_comm_unique_id(uint8_t *id128);
 int npc_comm_init(npc_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world);
 int npc_comm_combine(npc_ctx *ctx, const double *offset, double *scores_out, int64_t *nloci_out);
 int npc_combined_device_ptr(npc_ctx *ctx, double **scores_dev, int64_t **nloci_dev);
+/* Sample-sharded cohorts over NCCL: sums counts_dev[n_rows][2] (what npc_count_block_device wrote on each rank's
+ * slab of the samples) over the ranks, in place, on the context's stream -- exact integers, any order.  Then
+ * npc_set_cohort_size(total) + npc_accumulate_block_device; every rank keeps the scores of its own samples. */
+int npc_comm_sum_counts(npc_ctx *ctx, int64_t *counts_dev, int64_t n_rows);
 
 /* Kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t npc_launch_count(const npc_ctx *ctx);

@@ -1155,6 +1155,16 @@ extern "C" int npc_comm_combine(npc_ctx *ctx, const double *offset, double *scor
     return NPC_OK;
 }
 
+extern "C" int npc_comm_sum_counts(npc_ctx *ctx, int64_t *counts_dev, int64_t n_rows) {
+    if (!ctx || !counts_dev || n_rows < 0) return NPC_EINVAL;
+    if (!ctx->comm) return fail(ctx, NPC_ESTATE, "npc_comm_sum_counts: npc_comm_init was not called");
+    NPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_rows == 0) return NPC_OK;
+    const int r = g_nccl.AllReduce(counts_dev, counts_dev, (size_t)n_rows * 2, NCCL_UINT64, NCCL_SUM, ctx->comm, ctx->stream);
+    if (r) { ctx->err = std::string("NCCL: ") + g_nccl.GetErrorString(r); return NPC_ECUDA; }
+    return NPC_OK;
+}
+
 extern "C" int npc_combined_device_ptr(npc_ctx *ctx, double **scores_dev, int64_t **nloci_dev) {
     if (!ctx) return NPC_EINVAL;
     NPC_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -78,6 +78,7 @@ def load_library():
         "npc_comm_init": (C.c_int, [vp, vp, i32, i32]),
         "npc_comm_combine": (C.c_int, [vp, C.POINTER(f64), vp, pi64]),
         "npc_combined_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "npc_comm_sum_counts": (C.c_int, [vp, vp, i64]),
         "npc_launch_count": (i64, [vp]),
         "npc_kernel_shape": (C.c_int, [vp, C.POINTER(i32 * 8)]),
         "npc_trace": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
@@ -297,6 +298,9 @@ class Engine:
         nloci = C.c_int64()
         self._ck(self.L.npc_comm_combine(self.h, off, scores.ctypes.data, C.byref(nloci)))
         return scores, nloci.value
+
+    def comm_sum_counts(self, counts_dev, n_rows):
+        self._ck(self.L.npc_comm_sum_counts(self.h, _ptr(counts_dev), int(n_rows)))
 
     def combined_device_ptr(self):
         a, b = C.c_void_p(), C.c_void_p()

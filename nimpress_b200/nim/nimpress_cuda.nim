@@ -86,5 +86,6 @@ proc npc_reduce*(ctxs: ptr NpcCtx; nCtx: int32; offset: ptr float64; scoresOut: 
 proc npc_comm_unique_id*(id128: ptr uint8): cint
 proc npc_comm_init*(ctx: NpcCtx; id128: ptr uint8; rank, world: int32): cint
 proc npc_comm_combine*(ctx: NpcCtx; offset: ptr float64; scoresOut: ptr float64; nlociOut: ptr int64): cint
+proc npc_comm_sum_counts*(ctx: NpcCtx; countsDev: ptr int64; nRows: int64): cint
 proc npc_combined_device_ptr*(ctx: NpcCtx; scoresDev: ptr ptr float64; nlociDev: ptr ptr int64): cint
 {.pop.}

@@ -59,6 +59,28 @@ def main():
         # NCCL ids are single use: a fresh one per communicator
         ident = [nb.Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
+    # ---- sample-sharded: every rank holds a slab of the samples for every row; the integer tallies are summed over
+    # NCCL (npc_comm_sum_counts) before the decision, nothing floating-point crosses ranks, scores are concatenated
+    s_lo, s_hi = n * rank // world // 8 * 8, (n * (rank + 1) // world // 8 * 8 if rank + 1 < world else n)
+    sub = np.ascontiguousarray(gt[:, 2 * s_lo:2 * s_hi])
+    pad = (-sub.shape[1]) % 16
+    sub = np.pad(sub, ((0, 0), (0, pad)))
+    ident = [nb.Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    eng = nb.Engine(s_hi - s_lo, max_rows_per_block=512, n_slots=0, device=local)
+    eng.set_policy(); eng.reset(); eng.comm_init(ident[0], rank, world); eng.set_cohort_size(n)
+    d_gt = torch.from_numpy(sub.view(np.uint8)).cuda()
+    counts = torch.zeros((len(rows), 2), dtype=torch.int64, device="cuda")
+    eng.count_block_device(d_gt, d_gt.shape[1], V, rows, counts)
+    eng.comm_sum_counts(counts, len(rows))
+    eng.accumulate_block_device(d_gt, d_gt.shape[1], V, rows, counts)
+    got = eng.finish(offset=-0.25)
+    want = orc.score_matrix(gt, n, 2, rows.astype(orc.ROW_DTYPE), offset=-0.25)
+    assert got["nloci"] == want["nloci"]
+    assert_loci_equal(got["loci"], want["loci"])
+    a, b = got["scores"], want["scores"][s_lo:s_hi]
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(bits(a[~np.isnan(a)]), bits(b[~np.isnan(b)])), "sample-sharded scores differ"
+    eng.close()
     dist.barrier()
     if rank == 0:
         print("nccl combine ok: %d ranks, %d samples, %d rows" % (world, n, len(rows)))
