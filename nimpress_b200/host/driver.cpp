@@ -253,16 +253,22 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             v.ctx.ck(npc_resident_reserve(v.ctx.h, slab_want, &v.slab_cap), "npc_resident_reserve");
         } catch (const std::exception &e) { v.err = e.what(); }
     };
-    for (int d : dev_ids) wait_warm(d);
-    timer.mark("CUDA context (waited for)");
-    if (D == 1) open_dev(0);
-    else {                                            // CUDA context creation dominates: one thread per device
-        std::vector<std::thread> th;
-        for (int d = 0; d < D; d++) th.emplace_back(open_dev, d);
-        for (auto &t : th) t.join();
-    }
-    for (int d = 0; d < D; d++) if (!devs[d].err.empty()) throw std::runtime_error(devs[d].err);
-    timer.mark("GPU context + buffers");
+    // A device is opened when its first row arrives (or at the end, for its constant rows): contexts come up one after
+    // the other inside the driver (~1 s each), and a sorted file reaches the later ranges later -- the first device's
+    // rows stream while the others' contexts are still being created.
+    std::vector<uint8_t> opened(D, 0);
+    double waited_ms = 0.0;
+    auto ensure_open = [&](int d) {
+        if (opened[d]) return;
+        const auto t0 = std::chrono::steady_clock::now();
+        wait_warm(dev_ids[d]);
+        open_dev(d);
+        waited_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (!devs[d].err.empty()) throw std::runtime_error(devs[d].err);
+        opened[d] = 1;
+    };
+    ensure_open(0);
+    timer.mark("first GPU context + buffers");
 
     auto flush_stage = [&](Dev &v) {
         if (v.slot < 0) return;
@@ -323,6 +329,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
         for (int d = 0; d < D; d++) {
             rec_row[d] = -1;
             if (!((need_dev >> d) & 1u)) continue;
+            ensure_open(d);
             Dev &v = devs[d];
             if (v.slab_base + v.staged >= v.slab_cap) {             // slab full: score its rows, start over
                 if (S > 1) throw SlabOverflow();
@@ -373,6 +380,8 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
     // ---- score the slab(s), collect results ----------------------------------------------------
     std::vector<std::vector<npc_locus>> logs(S);
     std::vector<std::vector<int64_t>> order(S);          // entry index of every log record
+    for (int d = 0; d < D; d++) ensure_open(d);
+    if (timer.on && D > 1) fprintf(stderr, "[nimpress timing] waited for GPU contexts + buffers, all devices %8.1f ms\n", waited_ms);
     if (S == 1) {
         for (int d = 0; d < D; d++) score_round(d, true);
         outs[0].scores.assign(n, 0.0);
