@@ -525,12 +525,16 @@ static int launch_wide(npc_ctx *c, bool exact, const uint8_t *gt, int64_t row_st
         memset(&P, 0, sizeof(P));
         P.gt = gt + s0 * 2; P.row_stride = row_stride; P.n = ns; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
         P.sums = c->d_sums + s0; P.counts = c->d_fcounts; P.log = nullptr; P.nloci = c->d_nloci;
-        P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
+        // ONE decider warp: in this mode the local "tile counted" barrier is the deciders' only gate, and a warp that
+        // takes every A-th group of 8 tiles would wait on a ring slot's barrier 8*A tiles apart -- with 8*A > Sc it
+        // skips a phase of that slot and the parity test passes a whole ring turn early (in the normal mode the poll
+        // of the grid-wide tally word is the real gate, so the early pass is harmless there)
+        P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = 1; P.nc = t.nc; P.slab_stride = t.slab;
         P.Gs = t.Gs; P.Gr = 1; P.partials = nullptr;
         P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
         P.decided = c->d_rowp;
         void *args[] = { &P };
-        NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
+        NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs), dim3((t.nc + 2 + 1) * 32), args, t.smem, c->stream));
         c->launches++;
     }
     return NPC_OK;
@@ -824,8 +828,13 @@ static int multi_contract(npc_ctx *c, int32_t S, const npc_row *const *rows, con
     const int32_t n_kb = (int32_t)((E + npc::MC_ENT - 1) / npc::MC_ENT);
     const int64_t Ep = (int64_t)n_kb * npc::MC_ENT;
     std::vector<int32_t> entry_row((size_t)Ep, erows[0].gt_row);
-    std::vector<uint32_t> entry_pat((size_t)Ep, 0xFEFEFEFEu);
-    for (int64_t e = 0; e < E; e++) { entry_row[e] = erows[e].gt_row; entry_pat[e] = 0x01010101u * (uint32_t)((erows[e].eaidx + 1) << 1); }
+    // low byte: (eaidx + 1) << 1, the byte an allele of the effect allele carries; bits 8..: byte offset of the entry's pair table.
+    // Padding entries: a pattern no allele byte equals (0xFE) and the no-match table.
+    std::vector<uint32_t> entry_pat((size_t)Ep, 0xFEu | ((uint32_t)(3 * npc::MC_TAB_STRIDE) << 8));
+    for (int64_t e = 0; e < E; e++) {
+        entry_row[e] = erows[e].gt_row;
+        entry_pat[e] = (uint32_t)((erows[e].eaidx + 1) << 1) | ((uint32_t)(std::min(erows[e].eaidx, 3) * npc::MC_TAB_STRIDE) << 8);
+    }
 
     mark("entries (host)");
     const int64_t n_tiles = (c->n + npc::MC_N - 1) / npc::MC_N;

@@ -40,7 +40,7 @@
 //                (:643-649) -> coalesced stores; two accumulators (2 x 256 TMEM columns) so the
 //                epilogue of tile t overlaps the main loop of tile t+1
 #pragma once
-#include "npc_fused4.cuh"
+#include "npc_fused5.cuh"   // the pair index (F5_PACK_W) and the shared PTX helpers
 
 namespace npc {
 
@@ -66,12 +66,17 @@ constexpr int MC_OFF_EPI = MC_OFF_RAW + MC_RS * MC_RAW_STAGE;
 constexpr int MC_OFF_BAR = MC_OFF_EPI + 4 * 32 * MC_EPI_PITCH * 4;
 constexpr int MC_NBAR = 2 * MC_RS + 2 * MC_BS + 2 * MC_AS + 2 * MC_TS;
 constexpr int MC_OFF_TMEM = MC_OFF_BAR + MC_NBAR * 8;
-constexpr int MC_SMEM = MC_OFF_TMEM + 16 + 1024;          // + slack to align the base to 1024 (swizzle atom)
+// converters' pair tables (round 2): [T-1 (3 = no allele matches)][66*c0 + c1 + 4*c2 + 16*c3] -> bytes {d(s0), d(s1), m(s0), m(s1)} of
+// the two samples of a raw word, the index of npc_fused5.cuh; tables 1216 bytes apart (1152 + half a bank row, so that the
+// same combination under two effect alleles falls into different banks)
+constexpr int MC_TAB_STRIDE = 1216;
+constexpr int MC_OFF_TAB = (MC_OFF_TMEM + 16 + 127) & ~127;
+constexpr int MC_SMEM = MC_OFF_TAB + 4 * MC_TAB_STRIDE + 1024;   // + slack to align the base to 1024 (swizzle atom)
 
 struct MultiParams {
     const uint8_t *gt; int64_t row_stride; int64_t n;
     const int32_t *entry_row;                // [n_kb*64] slab row of each entry (padding entries: any valid row)
-    const uint32_t *entry_pat;               // [n_kb*64] (eaidx+1)<<1 in all four bytes
+    const uint32_t *entry_pat;               // [n_kb*64] low byte: (eaidx+1)<<1; bits 8..: byte offset of the entry's pair table (min(eaidx, 3) * MC_TAB_STRIDE)
     const uint8_t *A;                        // [n_kb][16 KB] digit tiles, already in the swizzled smem layout
     int32_t n_kb, n_scores;
     int32_t rps, parts;                      // rows per score: 7 digits, or 8 = 7 digits + NaN counter; parts: see below
@@ -182,6 +187,13 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
         for (int i = 0; i < MC_TS; i++) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < 4 * 256; i += MC_THREADS) {
+        const int cc = i & 255, Tm = i >> 8, T = Tm < 3 ? Tm + 1 : 99;
+        const int c0 = cc & 3, c1 = (cc >> 2) & 3, c2 = (cc >> 4) & 3, c3 = cc >> 6;
+        const uint32_t s0 = f5_code(c0, c1, T), s1 = f5_code(c2, c3, T);
+        const uint32_t e = (s0 == 3u ? 0u : s0) | ((s1 == 3u ? 0u : s1) << 8) | ((s0 == 3u ? 1u : 0u) << 16) | ((s1 == 3u ? 1u : 0u) << 24);
+        sts_u32(base + MC_OFF_TAB + Tm * MC_TAB_STRIDE + 4 * (66 * c0 + c1 + 4 * c2 + 16 * c3), e);
+    }
     if (warp == MC_W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -277,9 +289,20 @@ __global__ void __launch_bounds__(MC_THREADS, 1) k_multi_contract(const __grid_c
                     for (int j = 0; j < 8; j++) w[j] = lds_v2(stage + (g + 8 * j) * MC_PITCH + q * 8);   // entry g + 8j of the k-block
                     const uint32_t any = ((w[0].x | w[0].y) | (w[1].x | w[1].y)) | ((w[2].x | w[2].y) | (w[3].x | w[3].y)) |
                                          ((w[4].x | w[4].y) | (w[5].x | w[5].y)) | ((w[6].x | w[6].y) | (w[7].x | w[7].y));
-                    if ((any & 0x80808080u) == 0u) {                     // no sentinel, no invalid code in the 32 samples: one test, straight-line
+                    if ((any & 0xF8F8F8F8u) == 0u) {
+                        // every allele is REF, ALT1, ALT2 or missing: two samples per table lookup (the pair index of the fused
+                        // kernel), the entry's bytes are the two dosages and the two missing flags
+                        const uint32_t tab0 = base + MC_OFF_TAB;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) convert4_fast(w[j].x, w[j].y, pat[j], D[j], M[j]);
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t tb = tab0 + (pat[j] >> 8);
+                            const uint32_t e01 = lds_u32(__dp4a(w[j].x & 0x06060606u, F5_PACK_W, tb)), e23 = lds_u32(__dp4a(w[j].y & 0x06060606u, F5_PACK_W, tb));
+                            D[j] = __byte_perm(e01, e23, 0x5410);
+                            M[j] = __byte_perm(e01, e23, 0x7632);
+                        }
+                    } else if ((any & 0x80808080u) == 0u) {              // more alleles, but no sentinel and no invalid code: byte-wise SWAR compares
+#pragma unroll
+                        for (int j = 0; j < 8; j++) convert4_fast(w[j].x, w[j].y, (pat[j] & 0xFFu) * 0x01010101u, D[j], M[j]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; j++) convert4_exact(w[j].x, w[j].y, (int)((pat[j] & 0xFFu) >> 1) - 1, D[j], M[j]);

@@ -473,13 +473,14 @@ def test_pair_table_every_code_combination(nb, mode):
     assert_parity(got, oracle(gt, n, rows, policy=dict(maxmis=1.0)), exact=mode == "exact")
 
 
+@pytest.mark.parametrize("n", [1_300_000, 2_000_000])
 @pytest.mark.parametrize("mode", MODES)
-def test_cohort_wider_than_one_resident_pass(nb, mode):
-    """1,300,000 samples on one GPU: more than the tile kernel keeps resident (~1.2 M).  The rows are tallied and
+def test_cohort_wider_than_one_resident_pass(nb, mode, n):
+    """1,300,000 / 2,000,000 samples on one GPU: more than the tile kernel keeps resident (~1.2 M).  The rows are tallied and
     decided over all samples first, then the tile kernel runs in "decided" mode once per slab of the sample axis
     (kernel_shape fused = 3): per-locus records equal, scores bit-equal in exact-order mode."""
     import torch
-    n, V, seed = 1_300_000, 48, 0x6E696D70
+    V, seed = 48, 0x6E696D70
     rng = np.random.default_rng(seed + 3)
     af_thr = (rng.uniform(0.01, 0.5, size=V) * 65536).astype(np.uint32)
     ms_thr = (rng.uniform(0, 0.1, size=V) * (1 << 24)).astype(np.uint32)
