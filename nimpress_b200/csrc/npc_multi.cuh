@@ -67,9 +67,11 @@ constexpr int MC_OFF_BAR = MC_OFF_EPI + 4 * 32 * MC_EPI_PITCH * 4;
 constexpr int MC_NBAR = 2 * MC_RS + 2 * MC_BS + 2 * MC_AS + 2 * MC_TS;
 constexpr int MC_OFF_TMEM = MC_OFF_BAR + MC_NBAR * 8;
 // converters' pair tables (round 2): [T-1 (3 = no allele matches)][66*c0 + c1 + 4*c2 + 16*c3] -> bytes {d(s0), d(s1), m(s0), m(s1)} of
-// the two samples of a raw word, the index of npc_fused5.cuh; tables 1216 bytes apart (1152 + half a bank row, so that the
-// same combination under two effect alleles falls into different banks)
-constexpr int MC_TAB_STRIDE = 1216;
+// the two samples of a raw word, the index of npc_fused5.cuh.  Tables are 1184 bytes apart = 1152 + a QUARTER of a bank row:
+// a warp's lookup mixes entries (lanes g) with effect allele REF and ALT1, i.e. tables 0 and 1, and the 16 REF / ALT1
+// combinations of a table sit in banks {7..14, 23..30} -- a set that a 16-bank shift maps onto itself (measured: 1.63
+// wavefronts per lookup with a 64-byte shift) and an 8-bank shift maps onto its complement
+constexpr int MC_TAB_STRIDE = 1184;
 constexpr int MC_OFF_TAB = (MC_OFF_TMEM + 16 + 127) & ~127;
 constexpr int MC_SMEM = MC_OFF_TAB + 4 * MC_TAB_STRIDE + 1024;   // + slack to align the base to 1024 (swizzle atom)
 
