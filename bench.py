@@ -310,12 +310,23 @@ def b200_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    if args.config == 2:
-        args.samples, args.variants = 100_000, 697
-    elif args.config == 5:
-        args.samples, args.variants = 50_000, 10_000
-    elif args.config == 4:
-        raise SystemExit("--config 4 is reported under `extra.config4` of the default run (npc_score_resident_multi is a synchronous host call)")
+    if args.config in (2, 4, 5):
+        # the small configs are single launches near or below the L2 size: timed one launch at a time with the L2 flushed
+        # in between (time_resident / extra_configs), N = 1 only
+        if world > 1:
+            raise SystemExit("--config 2 / 4 / 5 are single-GPU configurations")
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        ex = extra_configs(nb, torch, dev, peak)[f"config{args.config}"]
+        line = {"metric": "genotypes scored/sec (variants x samples)", "value": ex["value"], "unit": ex["unit"], "n_gpus": 1,
+                "steps": 20, "warmup": 5, "ms_per_step": ex.get("launch_us", ex.get("call_ms", 0.0) * 1e3) / 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": ex["workload"], "l2": ex.get("l2", "8 GB slab: larger than L2")},
+                "roofline": {"bound": "hbm", "frac": ex.get("roofline_frac"), "peak": peak, "unit": "GB/s"}, "detail": ex}
+        print(json.dumps(line))
+        return
     n, V = args.samples, args.variants
     stride = -(-2 * n // 128) * 128
     fused = os.environ.get("NPC_FUSED", "1") != "0"

@@ -118,7 +118,26 @@ k_count_generic(const uint8_t *__restrict__ gt, int64_t row_stride, const npc_ro
     if (row.kind != NPC_KIND_GT || row.gt_row < 0) return;
     const T *base = reinterpret_cast<const T *>(gt + (int64_t)row.gt_row * row_stride);
     ull nmiss = 0, neff = 0;
-    for (int64_t s = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.y * blockDim.x) {
+    const int64_t step = (int64_t)gridDim.y * blockDim.x;
+    int64_t s = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (ploidy <= 2) {
+        // haploid / diploid: four samples' values in registers before any is decoded (the loop is latency-bound otherwise)
+        constexpr int U = 4;
+        for (; s + (U - 1) * step < n; s += U * step) {
+            T v[U][2];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) v[u][k] = k < ploidy ? base[(s + u * step) * ploidy + k] : (T)Sent<T>::vend;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                int d; bool miss;
+                decode_sample<T>(v[u], 2, row.eaidx, d, miss);
+                if (miss) nmiss++; else neff += d;
+            }
+        }
+    }
+    for (; s < n; s += step) {
         int d; bool miss;
         decode_sample<T>(base + s * ploidy, ploidy, row.eaidx, d, miss);
         if (miss) nmiss++; else neff += d;
@@ -295,7 +314,34 @@ k_accum_generic(const uint8_t *__restrict__ gt, int64_t row_stride, const RowP *
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     double acc = sums[s];
-    for (int64_t r = 0; r < n_rows; r++) {
+    int64_t r = 0;
+    if (ploidy <= 2) {
+        // haploid / diploid: the values of four rows are loaded before the first is added -- the adds stay in row order
+        // (the reference's chain), only the loads run ahead
+        constexpr int U = 4;
+        for (; r + U <= n_rows; r += U) {
+            T v[U][2];
+            int mode[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                mode[u] = rowp[r + u].mode;
+                const T *p = reinterpret_cast<const T *>(gt + (int64_t)rowp[r + u].gt_row * row_stride) + s * ploidy;
+#pragma unroll
+                for (int k = 0; k < 2; k++) v[u][k] = (mode[u] == MODE_DECODE && k < ploidy) ? p[k] : (T)Sent<T>::vend;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const RowP &rp = rowp[r + u];
+                if (mode[u] == MODE_CONST) acc = __dadd_rn(acc, rp.c0);
+                else if (mode[u] == MODE_DECODE) {
+                    int d; bool miss;
+                    decode_sample<T>(v[u], 2, rp.eaidx, d, miss);
+                    acc = __dadd_rn(acc, miss ? rp.cm : __dmul_rn((double)d, rp.beta));
+                }
+            }
+        }
+    }
+    for (; r < n_rows; r++) {
         const RowP rp = rowp[r];
         if (rp.mode == MODE_CONST) acc = __dadd_rn(acc, rp.c0);
         else if (rp.mode == MODE_DECODE) {
