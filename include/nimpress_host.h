@@ -52,7 +52,8 @@ typedef struct {
     int32_t exact_order;    /* 1: npc_set_exact_order(ctx, 1) -- the reference's summation order bit for bit */
     int32_t device_mask;    /* != 0: score on every CUDA device whose bit is set (ascending order): the score rows are split
                                into contiguous ranges, one per device, combined in range order by npc_reduce; `device` is then
-                               ignored.  0: one device, `device`.  (Several score files at once use the first device only.) */
+                               ignored.  0: one device, `device`.  Several score files at once: every file is cut into ranges of its own,
+                               device d scores range d of every file, the host adds each file's partial sums in device order. */
     int64_t mincs;
     double  maxmis;
     double  afmisp;

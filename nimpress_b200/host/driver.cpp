@@ -214,17 +214,21 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
     // Devices: one context per GPU.  With several, the score rows are partitioned into contiguous ranges in
     // score-file order (a contig / region partition for a sorted score file): context d scores range d over all
     // samples, a matched record is uploaded to the device(s) whose ranges name it, and the partial sums are
-    // combined in range order by npc_reduce.  Several score files at once (S > 1) use the first device only.
+    // combined in range order by npc_reduce.  Several score files at once: every file is cut into D ranges of its own,
+    // device d scores range d of every file in one npc_score_resident_multi call (raw partial sums), and the host adds
+    // the partials of each file in device order and normalises once.
     std::vector<int> dev_ids = p.devices.empty() ? std::vector<int>{ p.device } : p.devices;
     if (const char *e = getenv("NIMPRESS_SPLIT")) if (*e && dev_ids.size() == 1 && atoi(e) > 1)      // tests: several contexts on one GPU
         dev_ids.assign((size_t)std::min(atoi(e), 16), dev_ids[0]);
-    if (S > 1) dev_ids.resize(1);
     const int D = (int)dev_ids.size();
-    const int64_t nE0 = (int64_t)scores[0]->entries.size();
-    auto dev_of = [&](int64_t i) -> int { return D == 1 ? 0 : (int)std::min<int64_t>(D - 1, i * D / std::max<int64_t>(nE0, 1)); };
-    std::vector<int64_t> dev_lookup(D, 0);            // rows of each device's range that need a record
+    // entry i of score file k belongs to device i * D / (entries of k): contiguous ranges of EVERY file in its own order
+    auto dev_of = [&](int k, int64_t i) -> int {
+        return D == 1 ? 0 : (int)std::min<int64_t>(D - 1, i * D / std::max<int64_t>((int64_t)scores[k]->entries.size(), 1));
+    };
+    std::vector<int64_t> dev_lookup(D, 0);            // rows of each device's ranges that need a record (an upper bound when files share records)
     if (D == 1) dev_lookup[0] = n_lookup;
-    else for (int64_t i = 0; i < nE0; i++) if (ps[0].M->kind[i] == Matcher::PENDING) dev_lookup[dev_of(i)]++;
+    else for (int k = 0; k < S; k++)
+        for (int64_t i = 0; i < (int64_t)scores[k]->entries.size(); i++) if (ps[k].M->kind[i] == Matcher::PENDING) dev_lookup[dev_of(k, i)]++;
 
     // staging slots of ~8 MB: big enough for efficient H2D copies, small enough that pinning three of them per
     // device does not dominate a short run (pinning costs ~1 ms per MB); scoring launches are sized separately
@@ -281,7 +285,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
         const std::vector<ScoreEntry> &E = scores[k]->entries;
         rows.clear();
         for (int64_t i = 0; i < (int64_t)E.size(); i++) {
-            if (q.done[i] || (S == 1 && dev_of(i) != d)) continue;
+            if (q.done[i] || dev_of(k, i) != d) continue;
             const int32_t kind = q.M->kind[i];
             if (!final_round && !(kind == NPC_KIND_GT && q.slab_row[i] >= 0)) continue;
             npc_row r;
@@ -319,7 +323,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             const std::vector<int64_t> &hits = ps[k].M->match(rec);
             for (int64_t i : hits) {
                 any = true;
-                if (ps[k].M->kind[i] == NPC_KIND_GT) { need_gt = true; need_dev |= 1u << (S == 1 ? dev_of(i) : 0); }
+                if (ps[k].M->kind[i] == NPC_KIND_GT) { need_gt = true; need_dev |= 1u << dev_of(k, i); }
             }
         }
         if (!any) continue;
@@ -365,7 +369,7 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             if (ps[k].M->kind[i] == NPC_KIND_GT) {
                 if (p.use_ds && ps[k].M->eaidx[i] > 1)
                     throw InputError("record " + *rec.contig + ":" + std::to_string(rec.pos) + ": FORMAT/DS rows take the REF or the first ALT as effect allele");
-                ps[k].slab_row[i] = rec_row[S == 1 ? dev_of(i) : 0];
+                ps[k].slab_row[i] = rec_row[dev_of(k, i)];
             }
         for (int d = 0; d < D; d++) if (devs[d].slot >= 0 && devs[d].staged == devs[d].block_rows) flush_stage(devs[d]);
     }
@@ -411,23 +415,43 @@ void run_pass(const std::vector<const ScoreFile *> &scores, VariantSource &vcf, 
             }
         }
     } else {
-        Dev &v = devs[0];
-        flush_stage(v);
-        std::vector<const npc_row *> rows(S);
-        std::vector<int64_t> n_rows(S), nloci(S);
-        std::vector<double> offsets(S);
-        std::vector<double *> sc(S);
-        std::vector<npc_locus *> lg(S);
-        for (int k = 0; k < S; k++) {
-            collect_rows(k, 0, true, ps[k].rows, order[k]);
-            rows[k] = ps[k].rows.data(); n_rows[k] = (int64_t)ps[k].rows.size(); offsets[k] = scores[k]->offset;
-            outs[k].scores.assign(n, 0.0); sc[k] = outs[k].scores.data();
-            logs[k].resize(ps[k].rows.size()); lg[k] = logs[k].data();
-            outs[k].rounds = 1; outs[k].devices = 1;
+        std::vector<int64_t> nloci_tot(S, 0);
+        std::vector<std::vector<double>> part(S);
+        for (int k = 0; k < S; k++) { outs[k].scores.assign(n, 0.0); outs[k].rounds = 1; outs[k].devices = D; if (D > 1) part[k].assign((size_t)n, 0.0); }
+        for (int d = 0; d < D; d++) {
+            Dev &v = devs[d];
+            flush_stage(v);
+            std::vector<std::vector<npc_row>> drows(S);
+            std::vector<std::vector<npc_locus>> dlog(S);
+            std::vector<const npc_row *> rows(S);
+            std::vector<int64_t> n_rows(S), nloci(S);
+            std::vector<double> offsets(S);
+            std::vector<double *> sc(S);
+            std::vector<npc_locus *> lg(S);
+            for (int k = 0; k < S; k++) {
+                collect_rows(k, d, true, drows[k], order[k]);
+                rows[k] = drows[k].data(); n_rows[k] = (int64_t)drows[k].size(); offsets[k] = scores[k]->offset;
+                sc[k] = D == 1 ? outs[k].scores.data() : part[k].data();
+                dlog[k].resize(drows[k].size()); lg[k] = dlog[k].data();
+            }
+            // one device: normalised scores straight away; several: raw partial sums (offsets = NULL), combined below
+            v.ctx.ck(npc_score_resident_multi(v.ctx.h, S, rows.data(), n_rows.data(), D == 1 ? offsets.data() : nullptr, sc.data(), nloci.data(), lg.data()),
+                     "npc_score_resident_multi");
+            for (int k = 0; k < S; k++) {
+                nloci_tot[k] += nloci[k];
+                logs[k].insert(logs[k].end(), dlog[k].begin(), dlog[k].end());
+                if (D > 1) {
+                    double *tot = outs[k].scores.data();
+                    const double *pk = part[k].data();
+                    if (d == 0) memcpy(tot, pk, (size_t)n * sizeof(double));
+                    else for (int64_t i = 0; i < n; i++) tot[i] += pk[i];            // device order = score-file order of the ranges
+                }
+            }
         }
-        v.ctx.ck(npc_score_resident_multi(v.ctx.h, S, rows.data(), n_rows.data(), offsets.data(), sc.data(), nloci.data(), lg.data()),
-                 "npc_score_resident_multi");
-        for (int k = 0; k < S; k++) outs[k].nloci = nloci[k];
+        for (int k = 0; k < S; k++) {
+            outs[k].nloci = nloci_tot[k];
+            if (D > 1) npc_normalise(outs[k].scores.data(), n, nloci_tot[k], scores[k]->offset);
+        }
     }
     timer.mark("score + finish (GPU)");
     for (int k = 0; k < S; k++) {

@@ -125,6 +125,35 @@ def test_host_devices_split(api, tmp_path, monkeypatch, exact):
             assert score_excess(got.scores, want["scores"], want) <= 1.0
 
 
+@pytest.mark.parametrize("n_files", [2, 5])
+def test_several_score_files_over_several_devices(api, tmp_path, monkeypatch, n_files):
+    """nph_compute_polygenic_scores_multi with a device list: every file is cut into ranges of its own, device d scores
+    range d of every file in one call (two files: the fused kernel per file; five: the tensor-core contraction), the
+    host adds each file's partial sums in device order.  Each result == the oracle on that file alone."""
+    from util_files import derive_scores
+    rng = np.random.default_rng(80 + n_files)
+    d = make_dataset(str(tmp_path), rng, n=600, V=180, sorted_scores=False)
+    paths = [d["score"]] + derive_scores(str(tmp_path), rng, d["entries"], n_files - 1)
+    ndev = n_devices()
+    devices = list(range(ndev)) if ndev >= 2 else None
+    if ndev < 2:
+        monkeypatch.setenv("NIMPRESS_SPLIT", "3")
+    L = api.load_host_library()
+    import ctypes as C
+    mask = sum(1 << k for k in devices) if devices else 0
+    p = api._Params(0, 0, 3, 0, 1, 0, 0, mask, 100, 0.05, 0.001, 0, 0)
+    arr = (C.c_char_p * len(paths))(*[os.fsencode(x) for x in paths])
+    hs = (C.c_void_p * len(paths))()
+    rc = L.nph_compute_polygenic_scores_multi(arr, len(paths), os.fsencode(d["bcf"]), os.fsencode(d["bed"]), C.byref(p), hs)
+    assert rc == 0, L.nph_last_error()
+    for k, path in enumerate(paths):
+        got = api._take_result(L, C.c_void_p(hs[k]))
+        want = orc.compute_scores_files(path, d["vcf"], d["bed"])
+        assert got.devices == (ndev if ndev >= 2 else 3) and got.nloci == want["nloci"] and got.warnings == want["warn"]
+        assert_loci_equal(got.loci, want["loci"])
+        assert np.array_equal(np.isnan(got.scores), np.isnan(want["scores"])) and score_excess(got.scores, want["scores"], want) <= 1.0
+
+
 def test_more_contexts_than_score_rows(api, tmp_path, monkeypatch):
     """Five contexts, three score rows (one of them absent from the file): ranges may be empty; the result is the oracle's."""
     rng = np.random.default_rng(79)
