@@ -44,6 +44,8 @@
  *   NPC_MULTI_PARTS=<n>      split of a tile's entry range over work units in the contraction (default: chosen from the tile count)
  *   NPC_TIMING=1             phase wall times of npc_score_resident_multi on stderr
  *   NPC_TRACE=1              keep %globaltimer stamps of the tile kernel's CTA 0 (npc_trace)
+ *   NPC_STAGE_WC=1           write-combined pinned staging slots (measured on B200 / PCIe Gen5: no difference, 55 GB/s either way)
+ *   NPC_WIDE=0               cohorts wider than one resident pass: the round-1 two-kernel sequence instead of decided-mode slabs
  */
 #ifndef NIMPRESS_CUDA_H
 #define NIMPRESS_CUDA_H
