@@ -200,8 +200,12 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     c->num_sms = prop.multiProcessorCount;
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
     const int64_t C = (c->n + 7) / 8;
-    int best_gr = 1; double best = -1.0;
     const int force_gr = env_int("NPC_TILE_GR", 0);
+    // candidates in the order of preference: the score of round 1 (SMs used x warps kept busy), a larger number of row
+    // groups only when it is worth 8 %; the first candidate whose rings fit shared memory is taken (the fuzz of round 2
+    // found cohorts whose best-scoring split did not fit and silently lost the fused path)
+    std::vector<std::pair<double, int>> cand;
+    bool too_wide = true;                              // no split at all keeps a CTA's share of a row within 16 warps x 2 chunks
     for (int gr = 1; gr <= 16; gr++) {
         const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
         if (gs < 1) break;
@@ -209,12 +213,21 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         const int k = nch <= 512 ? 1 : 2;
         const int64_t nc = (nch + 32 * k - 1) / (32 * k);
         if (nc > 16) continue;
+        too_wide = false;
+        if (force_gr && gr != force_gr) continue;
         const double score = (double)gs * gr * std::min<int64_t>(nc * k, 14) * ((double)nch / (double)(nc * 32 * k));
-        if (force_gr ? gr == force_gr : score > best * 1.08) { best = score; best_gr = gr; }
+        cand.emplace_back(score, gr);
     }
-    tile_config(c, best_gr, max_smem, c->fast);
+    {
+        // round 1's rule: walk gr upwards, move on only for an 8 % better score
+        std::vector<int> order;
+        double best = -1.0;
+        for (const auto &sc : cand) if (sc.first > best * 1.08) { best = sc.first; order.insert(order.begin(), sc.second); }
+        for (const auto &sc : cand) if (std::find(order.begin(), order.end(), sc.second) == order.end()) order.push_back(sc.second);
+        for (int gr : order) if (tile_config(c, gr, max_smem, c->fast)) break;
+    }
     tile_config(c, 1, max_smem, c->exact_cfg);
-    if (!c->fast.ok && c->width == 1 && env_int("NPC_TILE_V", 5) != 4) {
+    if (too_wide && !c->fast.ok && c->width == 1 && env_int("NPC_TILE_V", 5) != 4) {
         // too wide: the fewest equal slabs (multiples of 1024 samples) the tile kernel can hold
         for (int S = 2; S <= 64 && !c->wide.ok; S++) {
             const int64_t ns = ((c->n + S - 1) / S + 1023) / 1024 * 1024;
@@ -225,7 +238,9 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     for (int ex = 0; ex < 4; ex++) {
         const npc_ctx::TileCfg &t = ex == 0 ? c->fast : ex == 1 ? c->exact_cfg : ex == 2 ? c->wide : c->wide_exact;
         if (!t.ok) continue;
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, (ex & 1) != 0, c->width), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+        // the device's maximum, not this shape's need: the attribute belongs to the kernel function, which other contexts
+        // of the process (and this context's other shapes) launch with other sizes
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, (ex & 1) != 0, c->width), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     }
     if (c->fast.ok || c->exact_cfg.ok || c->wide.ok) {

@@ -511,3 +511,28 @@ def test_cohort_wider_than_one_resident_pass(nb, mode, n):
         eng.close()
         ok = ~np.isnan(a["scores"])
         assert np.array_equal(bits(a["scores"][ok]), bits(b["scores"][:4096][ok]))
+
+
+def test_kernel_shape_choice_and_contexts_side_by_side(nb):
+    """Two findings of the round-2 fuzz (tools/fuzz_parity.py).  157,929 samples: the best-scoring split of the grid (7 row
+    groups) does not fit shared memory -- the next candidate must be taken, not the slow generic path.  And the
+    dynamic-shared-memory attribute belongs to the kernel function, not to a context: a second context with a smaller
+    shape must not shrink what the first one may launch."""
+    rng = np.random.default_rng(58)
+    n, V = 157_929, 40
+    gt = random_cohort(rng, n, V, miss_rate=0.01, n_alt=2)
+    rows = random_rows(rng, V, n_rows=52, n_alt=2)
+    want = oracle(gt, n, rows)
+    for exact in (True, False):
+        big = nb.Engine(n, max_rows_per_block=64, n_slots=2)
+        big.set_policy(); big.set_exact_order(exact); big.reset()
+        assert big.kernel_shape["fused"] == (1 if exact else 2), big.kernel_shape
+        small_gt = random_cohort(rng, 4000, 8)
+        small_rows = random_rows(rng, 8, n_rows=8)
+        small = nb.Engine(4000, max_rows_per_block=64, n_slots=2)       # created AFTER big: sets its own, smaller shapes
+        small.set_policy(); small.set_exact_order(exact); small.reset()
+        small.score_host(small_gt, small_rows)
+        big.score_host(gt, rows)
+        assert_parity(big.finish(), want, exact=exact)
+        assert_parity(small.finish(), oracle(small_gt, 4000, small_rows), exact=exact)
+        big.close(); small.close()
