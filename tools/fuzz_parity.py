@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--cases", type=int, default=300)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--seconds", type=float, default=240.0)
+    ap.add_argument("--dosage", action="store_true", help="FORMAT/DS rows (fp32 dosages) instead of GT rows")
     args = ap.parse_args()
     import nimpress_b200 as nb
     import orc
@@ -41,22 +42,34 @@ def main():
         pol = dict(imp_locus=str(rng.choice(["ps", "homref", "fail", "ignore"])), imp_missing=str(rng.choice(["homref", "ignore"])),
                    imp_sample=str(rng.choice(["ps", "homref", "fail", "int_ps", "int_fail"])), maxmis=float(rng.choice([0.0, 0.02, 0.05, 1.0])),
                    mincs=int(rng.choice([0, 100, n + 1])))
-        gt = random_cohort(rng, n, V, width=width, miss_rate=miss, n_alt=n_alt, sentinel_rate=sent)
         n_rows = int(V * rng.uniform(0.5, 2.0)) + 1
-        rows = random_rows(rng, V, n_rows=n_rows, n_alt=n_alt)
+        if args.dosage:
+            n_alt, width = 1, 4
+            gt = np.zeros((V, -(-n // 32) * 32), dtype=np.float32)
+            gt[:, :n] = np.round(rng.uniform(0, 2, size=(V, n)) * rng.choice([0.0, 1.0, 1.0], size=(V, 1)), int(rng.integers(1, 7)))
+            b = gt.view(np.uint32)
+            m = rng.random((V, n)) < miss
+            b[:, :n][m] = rng.choice(np.array([0x7F800001, 0x7F800002, 0x7FC00000], dtype=np.uint32), size=int(m.sum()))
+            rows = random_rows(rng, V, n_rows=n_rows)
+            rows["eaidx"] = np.where(rows["ref_is_ea"] == 1, 0, 1)
+        else:
+            gt = random_cohort(rng, n, V, width=width, miss_rate=miss, n_alt=n_alt, sentinel_rate=sent)
+            rows = random_rows(rng, V, n_rows=n_rows, n_alt=n_alt)
         block = int(rng.choice([n_rows, max(1, n_rows // 3), 5]))
         offset = float(rng.choice([0.0, 0.5, -3.25]))
         desc = dict(case=case, n=n, V=V, width=width, n_alt=n_alt, miss=miss, sent=sent, exact=exact, pol=pol, n_rows=n_rows, block=block)
         try:
-            eng = nb.Engine(n, ploidy=2, gt_width=width, max_rows_per_block=max(n_rows, V, 1), n_slots=2)
+            eng = nb.Engine(n, ploidy=1 if args.dosage else 2, gt_width=width, max_rows_per_block=max(n_rows, V, 1), n_slots=2)
+            if args.dosage:
+                eng.set_dosage_rows(True)
             eng.set_policy(**pol); eng.set_exact_order(exact); eng.reset()
             for r0 in range(0, n_rows, block):
                 eng.score_host(gt, rows[r0:r0 + block])
             got = eng.finish(offset=offset)
             shape = eng.kernel_shape
             eng.close()
-            want = orc.score_matrix(gt, n, 2, rows.astype(orc.ROW_DTYPE), offset=offset, **pol)
-            assert_parity(got, want, exact=exact or shape["fused"] == 0)
+            want = orc.score_matrix(gt, n, 1 if args.dosage else 2, rows.astype(orc.ROW_DTYPE), offset=offset, **pol)
+            assert_parity(got, want, exact=exact or shape["fused"] == 0 or args.dosage)
         except Exception as e:               # noqa: BLE001
             print("FAIL", desc, repr(e)[:300], flush=True)
             raise SystemExit(1)
