@@ -18,7 +18,7 @@
  */
 /*
  * Environment (diagnostics and tests; none is needed in normal use):
- *   NIMPRESS_THREADS=<n>     BGZF inflate threads (default min(cores, 16); 1 = one thread, block by block)
+ *   NIMPRESS_THREADS=<n>     BGZF inflate threads (default min(cores - 1, 32); 1 = one thread, block by block)
  *   NIMPRESS_ZLIB_ONLY=1     inflate BGZF blocks with zlib instead of this library's own DEFLATE decoder
  *   NIMPRESS_NO_INDEX=1      never use <genotypes>.tbi / .csi;  NIMPRESS_FORCE_INDEX=1  use it whatever it saves
  *   NIMPRESS_TIMING=1        phase wall times on stderr

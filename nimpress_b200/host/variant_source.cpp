@@ -176,7 +176,9 @@ bool InflateStream::open(const std::string &path, bool seekable) {
     compressed_ = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     const bool bgzf = got == 18 && compressed_ && (magic[3] & 4) && magic[12] == 'B' && magic[13] == 'C';
     bgzf_ = bgzf;
-    int want = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    // all cores but one (the reader's own thread walks the records and copies the GT payloads), at most 32
+    const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+    int want = (int)std::min<unsigned>(hc > 2 ? hc - 1 : hc, 32u);
     if (const char *e = getenv("NIMPRESS_THREADS")) if (*e) want = std::max(1, atoi(e));
     block_mode_ = bgzf && (seekable || want == 1);     // one thread: block by block with this engine's decoder
     if (bgzf && want > 1 && !block_mode_) {

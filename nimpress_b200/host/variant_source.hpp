@@ -26,7 +26,7 @@ struct FastInflateTables;                                      // multi-threaded
 // `BC` extra field giving each member's size) is inflated by a pool of worker threads, blocks
 // delivered in file order; plain gzip falls back to one sequential zlib stream.  This is the
 // replacement for htslib's bgzf reader (which the reference uses single-threaded, hts-nim's
-// default threads = 0).  NIMPRESS_THREADS sets the pool size (default: min(cores, 16); 1 = sequential).
+// default threads = 0).  NIMPRESS_THREADS sets the pool size (default: min(cores - 1, 32); 1 = sequential).
 class InflateStream {
 public:
     InflateStream();
