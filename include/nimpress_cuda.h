@@ -297,7 +297,7 @@ int npc_set_dosage_rows(npc_ctx *ctx, int32_t on);
  * tile kernel in "decided" mode once per slab of the sample axis),
  * 0 for the count/decide/accumulate sequence; then grid (tile kernel: sample slabs * 1000 + row
  * groups), consumer warps, chunks per thread, rows
- * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + decider warps, dynamic
+ * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + tiles per decider pass * 10 + decider warps, dynamic
  * shared-memory bytes. */
 int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
 /* NPC_TRACE=1 at npc_create: %globaltimer stamps (ns) of CTA 0 of the last tile-kernel launch -- launch start, code

@@ -46,7 +46,7 @@ struct npc_ctx {
     // fused tile kernel (int8 diploid): launch shapes fixed per context
     struct TileCfg {
         bool ok = false;
-        int Gs = 1, Gr = 1, K = 1, nc = 1, slab = 0, Sr = 3, Sc = 16, L = 15, A = 2;
+        int Gs = 1, Gr = 1, K = 1, nc = 1, slab = 0, Sr = 3, Sc = 16, L = 15, A = 2, GD = 8;
         int ver = 5;                        // 5: pair-lookup kernel (npc_fused5.cuh); 4: the round-1 kernel (npc_fused4.cuh, NPC_TILE_V=4)
         uint32_t smem = 0;
     };
@@ -140,12 +140,13 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-static const void *tile_kernel(int ver, int K, bool exact, int width = 1) {
+static const void *tile_kernel(int ver, int K, bool exact, int width, int nc) {
     if (ver == 5 && width == 2) {
         if (K == 1) return exact ? (const void *)k_fused_pair<1, true, 2> : (const void *)k_fused_pair<1, false, 2>;
         return exact ? (const void *)k_fused_pair<2, true, 2> : (const void *)k_fused_pair<2, false, 2>;
     }
     if (ver == 5) {
+        if (K == 1 && nc > 16) return exact ? (const void *)k_fused_pair<1, true, 1, F5_NC_WIDE> : (const void *)k_fused_pair<1, false, 1, F5_NC_WIDE>;
         if (K == 1) return exact ? (const void *)k_fused_pair<1, true> : (const void *)k_fused_pair<1, false>;
         return exact ? (const void *)k_fused_pair<2, true> : (const void *)k_fused_pair<2, false>;
     }
@@ -153,36 +154,55 @@ static const void *tile_kernel(int ver, int K, bool exact, int width = 1) {
     return exact ? (const void *)k_fused_tile4<2, true> : (const void *)k_fused_tile4<2, false>;
 }
 
-// Launch shape of the tile kernel for `gr` row groups: Gs sample slabs (one CTA each), K chunks per
-// consumer thread, a raw ring of Sr stages (~110 KB of loads in flight per SM), the rest of shared
-// memory as index-ring slots, lag L = Sc - 1 tiles, A decider warps.
+// Consumer shape for a CTA that owns nch chunks (of 8 samples) of every row: K chunks per thread, nc warps.  One chunk
+// per thread as long as the warps fit the SM's registers (int8 GT: up to 24 warps on the 72-register instance, cohorts
+// up to ~909,000 samples per GPU), two (up to 16 warps) above that.
+static bool tile_shape(int ver, int width, int64_t nch, int &K, int64_t &nc) {
+    const int max1 = ver == 5 && width == 1 ? std::max(1, std::min(F5_NC_WIDE, env_int("NPC_TILE_NC1", F5_NC_WIDE))) : 16;
+    K = env_int("NPC_TILE_K", 0);
+    if (K != 1 && K != 2) K = nch <= 32 * max1 ? 1 : 2;
+    nc = (nch + 32 * K - 1) / (32 * K);
+    return nc <= (K == 1 ? max1 : 16);                // else: cohort too wide for one resident pass
+}
+
+// Launch shape of the tile kernel for `gr` row groups: Gs sample slabs (one CTA each), a raw ring of Sr
+// stages (one chunk set of 4 rows each; ~110 KB of loads in flight per SM), the rest of shared memory as
+// index-ring slots, lag L = Sc - 1 tiles, A decider warps deciding GD tiles per pass.
 static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg &t, int64_t n_samples = -1) {
     const int64_t C = ((n_samples < 0 ? c->n : n_samples) + 7) / 8;
     const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
     if (gs < 1) return false;
     const int64_t nch = (C + gs - 1) / gs;
-    int K = env_int("NPC_TILE_K", 0);
-    if (K != 1 && K != 2) K = nch <= 512 ? 1 : 2;
-    const int64_t nc = (nch + 32 * K - 1) / (32 * K);
-    if (nc > 16) return false;                        // cohort too wide for one resident pass
+    const int ver = env_int("NPC_TILE_V", 5) == 4 ? 4 : 5;
+    int K; int64_t nc;
+    if (!tile_shape(ver, c->width, nch, K, nc)) return false;
     const int W = c->width;                            // 1 or 2 (int16 GT: pair kernel only)
     const int slab = (int)(nc * 32 * K * 16 * W);
     int Sr = env_int("NPC_TILE_SR", 0), Sc = env_int("NPC_TILE_SC", 0), L = env_int("NPC_TILE_L", 0), A = env_int("NPC_TILE_A", 2);
-    const int ver = env_int("NPC_TILE_V", 5) == 4 ? 4 : 5;
+    int GD = env_int("NPC_TILE_GD", 0);
     if (W != 1 && ver != 5) return false;
+    const int stage = F4_R * (ver == 5 ? slab / K : slab);           // bytes of a raw stage
     auto smem_of = [&](int sr, int sc) {
         return ver == 5 ? (int)Fused5Smem::make(sr, sc, slab, (int)nc, K, W).total : (int)Fused4Smem::make(sr, sc, slab).total;
     };
-    if (Sr <= 0) Sr = std::max(2, std::min(8, (112 * 1024) / (F4_R * slab)));
+    // K = 2: one raw stage per chunk set, ~110 KB of them, at least 3
+    if (Sr <= 0) Sr = std::max(ver == 5 && K == 2 ? 3 : 2, std::min(8, (112 * 1024) / stage));
     if (Sc <= 0) {
         Sc = 32;
         while (Sc > 2 && smem_of(Sr, Sc) > max_smem) Sc--;
     }
-    while (Sr > 2 && smem_of(Sr, Sc) > max_smem) Sr--;
-    // deciders work on groups of 8 tiles: the lag must cover a whole group
-    if (smem_of(Sr, Sc) > max_smem || Sc < 10) return false;
-    if (L <= 8 || L > Sc - 1) L = Sc - 1;
-    t.Gs = gs; t.Gr = gr; t.K = K; t.nc = (int)nc; t.slab = slab; t.Sr = Sr; t.Sc = Sc; t.L = L;
+    while (Sr > (ver == 5 && K == 2 ? 3 : 2) && smem_of(Sr, Sc) > max_smem) Sr--;
+    // Deciders work on groups of GD tiles and the first tile of a group waits for the last: the lag must cover a
+    // whole group plus the grid-wide round trip of the tally word (~6 us under load; a tile streams in
+    // 4 * slab bytes / 42 GB/s per SM).  8 tiles per pass where the rings leave that much lag, else 4.
+    if (ver != 5) GD = 8;
+    else if (GD != 4 && GD != 8) {
+        const double tile_us = 4.0 * slab / 41.9e3;
+        GD = Sc - 1 >= 8 + 1 + (int)std::ceil(6.0 / tile_us) ? 8 : 4;
+    }
+    if (smem_of(Sr, Sc) > max_smem || Sc < GD + 2) return false;
+    if (L <= GD || L > Sc - 1) L = Sc - 1;
+    t.Gs = gs; t.Gr = gr; t.K = K; t.nc = (int)nc; t.slab = slab; t.Sr = Sr; t.Sc = Sc; t.L = L; t.GD = GD;
     t.A = std::max(1, std::min(2, A));
     t.smem = (uint32_t)smem_of(Sr, Sc);
     t.ver = ver;
@@ -205,15 +225,12 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     // groups only when it is worth 8 %; the first candidate whose rings fit shared memory is taken (the fuzz of round 2
     // found cohorts whose best-scoring split did not fit and silently lost the fused path)
     std::vector<std::pair<double, int>> cand;
-    bool too_wide = true;                              // no split at all keeps a CTA's share of a row within 16 warps x 2 chunks
     for (int gr = 1; gr <= 16; gr++) {
         const int gs = (int)std::min<int64_t>(c->num_sms / gr, std::max<int64_t>(1, C / 32));
         if (gs < 1) break;
         const int64_t nch = (C + gs - 1) / gs;
-        const int k = nch <= 512 ? 1 : 2;
-        const int64_t nc = (nch + 32 * k - 1) / (32 * k);
-        if (nc > 16) continue;
-        too_wide = false;
+        int k; int64_t nc;
+        if (!tile_shape(env_int("NPC_TILE_V", 5) == 4 ? 4 : 5, c->width, nch, k, nc)) continue;
         if (force_gr && gr != force_gr) continue;
         const double score = (double)gs * gr * std::min<int64_t>(nc * k, 14) * ((double)nch / (double)(nc * 32 * k));
         cand.emplace_back(score, gr);
@@ -227,8 +244,8 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         for (int gr : order) if (tile_config(c, gr, max_smem, c->fast)) break;
     }
     tile_config(c, 1, max_smem, c->exact_cfg);
-    if (too_wide && !c->fast.ok && c->width == 1 && env_int("NPC_TILE_V", 5) != 4) {
-        // too wide: the fewest equal slabs (multiples of 1024 samples) the tile kernel can hold
+    if (!c->fast.ok && c->width == 1 && env_int("NPC_TILE_V", 5) != 4) {
+        // no shape holds a whole row's share in one CTA: the fewest equal slabs (multiples of 1024 samples) the tile kernel can hold
         for (int S = 2; S <= 64 && !c->wide.ok; S++) {
             const int64_t ns = ((c->n + S - 1) / S + 1023) / 1024 * 1024;
             if (tile_config(c, 1, max_smem, c->wide, ns) && tile_config(c, 1, max_smem, c->wide_exact, ns)) { c->wide_n = ns; c->wide_slabs = (int)((c->n + ns - 1) / ns); }
@@ -240,7 +257,7 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         if (!t.ok) continue;
         // the device's maximum, not this shape's need: the attribute belongs to the kernel function, which other contexts
         // of the process (and this context's other shapes) launch with other sizes
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, (ex & 1) != 0, c->width), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel(t.ver, t.K, (ex & 1) != 0, c->width, t.nc), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return NPC_ECUDA; }
     }
     if (c->fast.ok || c->exact_cfg.ok || c->wide.ok) {
@@ -375,7 +392,7 @@ extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
     memset(shape, 0, 8 * sizeof(int32_t));
     if (!t.ok) return NPC_OK;
     shape[0] = wide ? 3 : ctx->exact ? 1 : 2; shape[1] = t.Gs * 1000 + (ctx->exact ? 1 : t.Gr); shape[2] = t.nc; shape[3] = t.K;
-    shape[4] = F4_R; shape[5] = t.Sr * 1000 + t.Sc; shape[6] = t.L * 100 + t.A; shape[7] = (int32_t)t.smem;
+    shape[4] = F4_R; shape[5] = t.Sr * 1000 + t.Sc; shape[6] = t.L * 100 + t.GD * 10 + t.A; shape[7] = (int32_t)t.smem;
     return NPC_OK;
 }
 
@@ -500,12 +517,12 @@ static int launch_fused(npc_ctx *c, const npc_ctx::TileCfg &t, bool exact, const
     P.gt = gt; P.row_stride = row_stride; P.n = c->n; P.rows = d_rows; P.n_rows = n_rows; P.pol = c->pol;
     P.sums = c->d_sums; P.counts = counts; P.log = c->d_log + c->log_len; P.nloci = c->d_nloci;
     P.counts_next = counts_next; P.n_zero = n_zero; P.trace = c->d_trace;
-    P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab;
+    P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = t.A; P.nc = t.nc; P.slab_stride = t.slab; P.GD = t.GD;
     P.Gs = t.Gs; P.Gr = gr; P.partials = c->d_partials;
     P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
     P.decided = nullptr;
     void *args[] = { &P };
-    NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
+    NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width, t.nc), dim3(t.Gs * gr), dim3((t.nc + 2 + t.A) * 32), args, t.smem, c->stream));
     c->launches++;
     // Row groups > 1: a second, wide kernel adds the groups' partial sums in group order.  (Folding this into the tile
     // kernel -- the last group of a slab to finish adds them -- was measured in round 2: one CTA per slab doing
@@ -545,12 +562,12 @@ static int launch_wide(npc_ctx *c, bool exact, const uint8_t *gt, int64_t row_st
         // takes every A-th group of 8 tiles would wait on a ring slot's barrier 8*A tiles apart -- with 8*A > Sc it
         // skips a phase of that slot and the parity test passes a whole ring turn early (in the normal mode the poll
         // of the grid-wide tally word is the real gate, so the early pass is harmless there)
-        P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = 1; P.nc = t.nc; P.slab_stride = t.slab;
+        P.Sr = t.Sr; P.Sc = t.Sc; P.L = t.L; P.A = 1; P.nc = t.nc; P.slab_stride = t.slab; P.GD = t.GD;
         P.Gs = t.Gs; P.Gr = 1; P.partials = nullptr;
         P.aux_sleep_ns = (uint32_t)env_int("NPC_TILE_SLEEP", 0);
         P.decided = c->d_rowp;
         void *args[] = { &P };
-        NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width), dim3(t.Gs), dim3((t.nc + 2 + 1) * 32), args, t.smem, c->stream));
+        NPC_CUDA(c, cudaLaunchCooperativeKernel(tile_kernel(t.ver, t.K, exact, c->width, t.nc), dim3(t.Gs), dim3((t.nc + 2 + 1) * 32), args, t.smem, c->stream));
         c->launches++;
     }
     return NPC_OK;

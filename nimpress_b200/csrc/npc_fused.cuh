@@ -19,6 +19,7 @@ struct FusedParams {
     ull *nloci;
     int32_t Sr, Sc, L, A;      // raw stages, index-ring tiles, count->accumulate lag (tiles), decider warps
     int32_t nc;                // consumer warps
+    int32_t GD;                // pair kernel: tiles a decider pass covers (8 = one row per lane; 4 when the lag is short)
     int32_t slab_stride;       // bytes per row in a raw stage = nc*32*K*16 (every consumer thread has a cell)
     // tile kernel only: the grid is Gs sample slabs x Gr row groups (Gr = 1: every CTA sees every row).
     // Group g > 0 accumulates into partials[(g-1)*n ..]; k_add_partials folds them in group order.

@@ -33,6 +33,7 @@
 
 namespace npc {
 
+constexpr int F5_NC_WIDE = 24;                // consumer warps of the K = 1 "wide" instance (72 registers); all others: 16
 constexpr int F5_R = 4;                       // rows per tile
 constexpr uint32_t F5_NT = 4;                 // tables per parity: T = 1, 2, 3 and "no allele matches" (T >= 4)
 constexpr uint32_t F5_TAB_BYTES = 1152;       // 262 four-byte entries (index <= 3 * 87), padded to a multiple of 128
@@ -54,7 +55,7 @@ struct Fused5Smem {
         m.rtb = o;    o += (uint32_t)Sr * 16u;                  o = (o + 127u) & ~127u;
         m.reaidx = o; o += (uint32_t)Sr * 16u;                  o = (o + 127u) & ~127u;
         m.idx = o;    o += (uint32_t)Sc * (uint32_t)(slab_stride / (2 * W));  o = (o + 127u) & ~127u;   // one byte per sample per tile
-        m.data = o;   o += (uint32_t)Sr * F5_R * (uint32_t)slab_stride;
+        m.data = o;   o += (uint32_t)Sr * F5_R * (uint32_t)(slab_stride / K);    // a raw stage: one chunk set (1/K of the slab) of R rows
         m.total = o;
         return m;
     }
@@ -99,8 +100,11 @@ __device__ __forceinline__ uint32_t f5_slow_code16(uint32_t word, int eaidx) {
 }
 
 // W = bytes per stored allele value: 1 (int8, the usual BCF GT) or 2 (int16: records with more than 63 alleles)
-template <int K, bool EXACT, int W = 1>
-__global__ void __launch_bounds__(640, 1)         // <= 16 consumer warps + producer + publisher + <= 2 deciders
+// NCMAX = most consumer warps the instance is launched with (+ producer + publisher + <= 2 deciders): 16 keeps ~96
+// registers per thread; the K = 1 instance for 17-24 warps is held to 72 (measured: 3 % slower than the 16-warp instance on
+// 14 warps, but 0.95-0.99 of the roofline at 800-900 k samples where two chunks per thread on 11-12 warps reach 0.81-0.88)
+template <int K, bool EXACT, int W = 1, int NCMAX = 16>
+__global__ void __launch_bounds__((NCMAX + 4) * 32, 1)
 k_fused_pair(const FusedParams P) {
     constexpr int R = F5_R;
     constexpr uint32_t CELL = 16u * W;                 // bytes of a chunk (8 diploid samples) in a raw row
@@ -129,6 +133,7 @@ k_fused_pair(const FusedParams P) {
     const int64_t c0 = (int64_t)slab_id * q_ + min((int64_t)slab_id, rem);
     const int nch = (int)(q_ + ((int64_t)slab_id < rem ? 1 : 0));
     const uint32_t slab_bytes = (uint32_t)nch * CELL;
+    const uint32_t hslab = (uint32_t)P.slab_stride / K;             // bytes per row of a raw stage (one chunk set)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Sr; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_rempty + 8u * s, NC); }
@@ -137,13 +142,17 @@ k_fused_pair(const FusedParams P) {
     }
     for (uint32_t i = threadIdx.x; i < (uint32_t)Sc * cnt_slot / 4u; i += blockDim.x)
         reinterpret_cast<uint32_t *>(smem + M.cnt)[i] = 0u;
-    // Raw ring: the TMA copies write bytes [0, slab_bytes) of a stage row; only the cells past them -- read by the
-    // lanes that own no chunk -- must hold something harmless (zero = "missing", and those lanes' tallies are not
-    // published).  Zeroing just that tail instead of the whole ring takes ~1 us off every launch.
-    {
-        const uint32_t tail16 = ((uint32_t)P.slab_stride - slab_bytes) / 16u;
+    // Lanes past the slab's last chunk.  K = 1: they run along on the cells past the bytes the TMA copies write, which
+    // nothing ever writes -- zero ("missing": every lane looks up the same entry, a broadcast) just that tail of the
+    // ring, not the whole ring: ~1 us off every launch.  Their tallies are not published, their sums not stored.
+    // K = 2: a stage alternates between the two chunk sets, its tail would hold an older set's genotypes and the idle
+    // lanes' lookups would collide with the others' -- there they sit the loop bodies out.
+    // (Measured both ways: predicating costs the K = 1 shapes with a partly filled warp 5 %, running along costs the
+    // K = 2 shapes 3 %.)
+    if (K == 1) {
+        const uint32_t tail16 = (hslab - slab_bytes) / 16u;
         for (uint32_t i = threadIdx.x; i < (uint32_t)Sr * R * tail16; i += blockDim.x)
-            reinterpret_cast<uint4 *>(smem + M.data + (i / tail16) * (uint32_t)P.slab_stride + slab_bytes)[i % tail16] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4 *>(smem + M.data + (i / tail16) * hslab + slab_bytes)[i % tail16] = make_uint4(0, 0, 0, 0);
     }
     if (P.counts_next)
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_zero; i += (int64_t)gridDim.x * blockDim.x) P.counts_next[i] = 0ull;
@@ -180,18 +189,23 @@ k_fused_pair(const FusedParams P) {
             const int T = is_gt ? cur.eaidx + 1 : 99;
             const uint32_t my_tb = sb + M.code + (uint32_t)((T >= 1 && T <= 3 ? T - 1 : 3) * 2 + (lane & 1)) * F5_TAB_BYTES;
             for (int j = 0; j < ng; j++) {
-                mbar_wait_sleep(bar_rempty + 8u * s, ph ^ 1u, P.aux_sleep_ns);
                 const uint32_t gt_mask = (gt_all >> (R * j)) & ((1u << R) - 1u);
                 const bool mine = (lane / R) == j;                   // lanes R*j .. R*j+R-1 own this tile's rows
-                if (mine) { s_reaidx[s * R + (lane % R)] = is_gt ? cur.eaidx : 0; s_rtb[s * R + (lane % R)] = my_tb; }
-                if (lane == 0) s_rflags[s] = gt_mask | (((odd_all >> (R * j)) & ((1u << R) - 1u)) << 4);
-                __syncwarp();
-                if (lane == 0) mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)__popc(gt_mask) * slab_bytes);
-                __syncwarp();
-                if (mine && is_gt)
-                    tma_load_1d(sb + M.data + (uint32_t)(s * R + (lane % R)) * (uint32_t)P.slab_stride,
-                                P.gt + (int64_t)cur.gt_row * P.row_stride + c0 * CELL, slab_bytes, bar_full + 8u * s, pol);
-                if (++s == Sr) { s = 0; ph ^= 1u; }
+#pragma unroll
+                for (int k = 0; k < K; k++) {                        // one raw stage per chunk set of the tile
+                    const uint32_t lo = (uint32_t)k * hslab;
+                    const uint32_t bytes = slab_bytes > lo ? min(slab_bytes - lo, hslab) : 0u;
+                    mbar_wait_sleep(bar_rempty + 8u * s, ph ^ 1u, P.aux_sleep_ns);
+                    if (mine) { s_reaidx[s * R + (lane % R)] = is_gt ? cur.eaidx : 0; s_rtb[s * R + (lane % R)] = my_tb; }
+                    if (lane == 0) s_rflags[s] = gt_mask | (((odd_all >> (R * j)) & ((1u << R) - 1u)) << 4);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)__popc(gt_mask) * bytes);
+                    __syncwarp();
+                    if (mine && is_gt && bytes)
+                        tma_load_1d(sb + M.data + (uint32_t)(s * R + (lane % R)) * hslab,
+                                    P.gt + (int64_t)cur.gt_row * P.row_stride + c0 * CELL + lo, bytes, bar_full + 8u * s, pol);
+                    if (++s == Sr) { s = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == NC + 1) {
@@ -222,11 +236,14 @@ k_fused_pair(const FusedParams P) {
         }
     } else if (warp > NC + 1) {
         // ================= deciders ============================================================
-        // One pass decides a GROUP of 8 tiles = 32 rows, one row per lane: the global round trip of
-        // the tally word (microseconds under load) is paid once per 8 tiles, not once per tile.
+        // One pass decides a GROUP of GD tiles, one row per lane (GD = 8: 32 rows): the global round trip
+        // of the tally word (microseconds under load) is paid once per group, not once per tile.  The
+        // first tile of a group waits for the last one to be counted everywhere, so the lag L must cover
+        // GD tiles plus that round trip: shapes whose rings leave a short lag (wide cohorts: a tile of
+        // 1M samples is 1.4 us of streaming and 11 KB of ring) run with GD = 4.
         // Groups rotate over the A decider warps.
         const int a = warp - NC - 2;
-        constexpr int GD = 32 / R;                                   // tiles per group
+        const int GD = P.GD;                                         // tiles per group
         double *vrow = reinterpret_cast<double *>(smem + M.vrow) + a * 128;      // [row in group][code]
         const int64_t n_groups = (n_tiles + GD - 1) / GD;
         for (int64_t g = a; g < n_groups; g += A) {
@@ -298,7 +315,7 @@ k_fused_pair(const FusedParams P) {
         asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");
         if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1] = globaltimer_ns();
         uint32_t cell[K], tailor[K], cnt_off[K];
-        bool own[K];
+        bool own[K];                           // lanes past the slab's last chunk sit the loop bodies out
         int valid[K];
         double acc[K][8];                      // natural sample order: acc[2w + s] = sample s of word w
 #pragma unroll
@@ -308,7 +325,7 @@ k_fused_pair(const FusedParams P) {
             const int64_t g = c0 + jc;
             valid[k] = jc < nch ? (int)min((int64_t)8, P.n - g * 8) : 0;
             own[k] = jc < nch;
-            tailor[k] = (jc < nch && valid[k] < 8) ? 0xF8u : 0u;          // a set bit of HI_MASK: the cohort's last, partial chunk decodes exactly
+            tailor[k] = (jc < nch && valid[k] < 8) ? 0xF8u : 0u;                        // a set bit of HI_MASK: the cohort's last, partial chunk decodes exactly
             cnt_off[k] = (uint32_t)((warp * K + k) / F5_GROUP) * 256u + (uint32_t)lane * 4u;
 #pragma unroll
             for (int e = 0; e < 8; e++) acc[k][e] = (e < valid[k] && grp == 0) ? P.sums[g * 8 + e] : 0.0;
@@ -320,21 +337,22 @@ k_fused_pair(const FusedParams P) {
         uint32_t ph_r = 0, ph_a = 0;
         for (int i = 0; i < nt + L; i++) {
             if (i < nt) {
-                mbar_wait(bar_full + 8u * sr, ph_r);
-                const uint32_t flags = s_rflags[sr];                 // bits 0-3: row has genotypes; bits 4-7: row needs the exact decode
-                const uint32_t d0 = sb + M.data + (uint32_t)(sr * R) * slab;
-                const uint4 tb4 = lds_v4(sb + M.rtb + (uint32_t)sr * 16u);
-                const uint32_t tb[R] = { tb4.x, tb4.y, tb4.z, tb4.w };
                 const uint32_t cnt_base = sb + M.cnt + (uint32_t)sc * cnt_slot;
 #pragma unroll
-                for (int k = 0; k < K; k++) {
+                for (int k = 0; k < K; k++) {                    // one raw stage per chunk set: wait, count, release
+                  mbar_wait(bar_full + 8u * sr, ph_r);
+                  if (K == 1 || own[k]) {
+                    const uint32_t flags = s_rflags[sr];             // bits 0-3: row has genotypes; bits 4-7: row needs the exact decode
+                    const uint32_t d0 = sb + M.data + (uint32_t)(sr * R) * hslab + (uint32_t)(lane + 32 * warp) * CELL;
+                    const uint4 tb4 = lds_v4(sb + M.rtb + (uint32_t)sr * 16u);
+                    const uint32_t tb[R] = { tb4.x, tb4.y, tb4.z, tb4.w };
                     uint32_t ww[R][4 * W];                       // the chunk's raw words, row by row
                     uint32_t hi_bits = tailor[k];
 #pragma unroll
                     for (int r = 0; r < R; r++)                  // all loads of the tile first: independent LDS.128
 #pragma unroll
                         for (int h = 0; h < W; h++) {
-                            const uint4 v = lds_v4(d0 + r * slab + cell[k] * CELL + 16u * h);
+                            const uint4 v = lds_v4(d0 + r * hslab + 16u * h);
                             ww[r][4 * h] = v.x; ww[r][4 * h + 1] = v.y; ww[r][4 * h + 2] = v.z; ww[r][4 * h + 3] = v.w;
                             hi_bits |= (v.x | v.y) | (v.z | v.w);
                         }
@@ -391,11 +409,14 @@ k_fused_pair(const FusedParams P) {
                     const uint32_t x = __byte_perm(__byte_perm(A4[0], A4[1], 0x0073), __byte_perm(A4[2], A4[3], 0x0073), 0x5410);
                     const uint32_t y = __byte_perm(__byte_perm(B4[0], B4[1], 0x0073), __byte_perm(B4[2], B4[3], 0x0073), 0x5410);
                     sts_v2(sb + M.idx + (uint32_t)sc * islab + cell[k] * 8u, x, y);
+                  }
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bar_rempty + 8u * sr);
+                  if (++sr == Sr) { sr = 0; ph_r ^= 1u; }
                 }
-                // raw stage fully read, tallies and index bytes written
+                // tallies and index bytes of the tile written
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(bar_rempty + 8u * sr); mbar_arrive(bar_cnt + 8u * sc); }
-                if (++sr == Sr) { sr = 0; ph_r ^= 1u; }
+                if (lane == 0) mbar_arrive(bar_cnt + 8u * sc);
                 if (++sc == Sc) sc = 0;
                 if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (i == 0 || i == nt - 1)) P.trace[i == 0 ? 2 : 3] = globaltimer_ns();
             }
@@ -404,6 +425,7 @@ k_fused_pair(const FusedParams P) {
                 const uint32_t thi = (sb + M.vtab + (uint32_t)sa * 256u) >> 8;     // bits 8.. of the slot's table block
 #pragma unroll
                 for (int k = 0; k < K; k++) {
+                    if (K != 1 && !own[k]) continue;
                     const uint2 v = lds_v2(sb + M.idx + (uint32_t)sa * islab + cell[k] * 8u);
                     if (EXACT) {
                         // the reference's chain: one rounded add per row, rows in order.  Row r's table holds

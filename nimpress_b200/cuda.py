@@ -323,7 +323,7 @@ class Engine:
         self._ck(self.L.npc_kernel_shape(self.h, C.byref(a)))
         keys = ("fused", "grid", "consumer_warps", "chunks_per_thread", "rows_per_tile", "stages", "lag", "smem_bytes")
         d = dict(zip(keys, list(a)))
-        d["decider_warps"], d["lag"] = d["lag"] % 100, d["lag"] // 100
+        d["decider_warps"], d["decider_tiles"], d["lag"] = d["lag"] % 10, d["lag"] % 100 // 10, d["lag"] // 100
         d["raw_stages"], d["index_tiles"] = d["stages"] // 1000, d["stages"] % 1000
         del d["stages"]
         if d["fused"] in (1, 2, 3):              # tile kernel: grid = sample slabs x (max) row groups

@@ -473,10 +473,12 @@ def test_pair_table_every_code_combination(nb, mode):
     assert_parity(got, oracle(gt, n, rows, policy=dict(maxmis=1.0)), exact=mode == "exact")
 
 
-@pytest.mark.parametrize("n", [1_300_000, 2_000_000])
+@pytest.mark.parametrize("n", [850_000, 1_150_000, 1_300_000, 2_000_000])
 @pytest.mark.parametrize("mode", MODES)
-def test_cohort_wider_than_one_resident_pass(nb, mode, n):
-    """1,300,000 / 2,000,000 samples on one GPU: more than the tile kernel keeps resident (~1.2 M).  The rows are tallied and
+def test_wide_cohorts(nb, mode, n):
+    """850,000 samples: one chunk per thread on 23 consumer warps (the 72-register instance of the kernel).  1,150,000: two
+    chunk sets per tile on 16 warps, each its own raw stage, deciders on groups of 4 tiles (the rings leave a short lag).  1,300,000 / 2,000,000 samples on one GPU:
+    more than the tile kernel keeps resident (~1.2 M) -- the rows are tallied and
     decided over all samples first, then the tile kernel runs in "decided" mode once per slab of the sample axis
     (kernel_shape fused = 3): per-locus records equal, scores bit-equal in exact-order mode."""
     import torch
@@ -497,7 +499,9 @@ def test_cohort_wider_than_one_resident_pass(nb, mode, n):
     got = eng.finish(offset=0.25)
     shape = eng.kernel_shape
     eng.close()
-    assert shape["fused"] == 3, shape
+    assert shape["fused"] == (3 if n > 1_200_000 else 1 if mode == "exact" else 2), shape
+    if n == 850_000: assert (shape["chunks_per_thread"], shape["consumer_warps"]) == (1, 23), shape
+    if n == 1_150_000: assert (shape["chunks_per_thread"], shape["consumer_warps"], shape["decider_tiles"]) == (2, 16, 4), shape
     # threads=8 in the oracle adds per-thread partial sums: compare the scores at the re-association tolerance, the records exactly
     assert_parity(got, want, exact=False)
     if mode == "exact":
