@@ -10,7 +10,11 @@ from util_cohort import random_cohort, random_rows, assert_parity
 rng = np.random.default_rng(1)
 for (n, V, width, ploidy, exact, env) in [(20011, 150, 1, 2, False, {}), (20011, 150, 1, 2, True, {}), (3001, 40, 2, 2, True, {}),
                                            (9001, 60, 2, 2, False, {}), (3001, 40, 1, 3, True, {}), (20011, 90, 1, 2, True, {"NPC_FUSED": "0"}),
-                                           (20011, 90, 1, 2, False, {"NPC_TILE_V": "4"})]:
+                                           (20011, 90, 1, 2, False, {"NPC_TILE_V": "4"}),
+                                           # two chunk sets per thread (a raw stage each, idle lanes predicated), 4-tile decider passes
+                                           (20011, 90, 1, 2, False, {"NPC_TILE_K": "2", "NPC_TILE_GD": "4"}), (20011, 90, 1, 2, True, {"NPC_TILE_K": "2"}),
+                                           # 18 consumer warps: the 72-register instance of the K = 1 kernel
+                                           (40003, 70, 1, 2, False, {"NPC_TILE_GR": "16"})]:
     for k, v in env.items(): os.environ[k] = v
     gt = random_cohort(rng, n, V, width=width, ploidy=ploidy, miss_rate=0.03, n_alt=5, sentinel_rate=0.01)
     rows = random_rows(rng, V, n_rows=V + 20, n_alt=5)
@@ -19,7 +23,7 @@ for (n, V, width, ploidy, exact, env) in [(20011, 150, 1, 2, False, {}), (20011,
     for r0 in range(0, len(rows), 97): eng.score_host(gt, rows[r0:r0 + 97])
     got = eng.finish(offset=0.5); shape = eng.kernel_shape; eng.close()
     assert_parity(got, orc.score_matrix(gt, n, ploidy, rows, offset=0.5), exact=exact or shape["fused"] != 2)
-    print("ok", n, V, width, ploidy, exact, env, shape["fused"], flush=True)
+    print("ok", n, V, width, ploidy, exact, env, shape["fused"], shape["consumer_warps"], shape["chunks_per_thread"], shape["decider_tiles"], flush=True)
     for k in env: os.environ.pop(k)
 # FORMAT/DS rows and the multi-context combine
 n, V = 5003, 30
