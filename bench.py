@@ -238,7 +238,7 @@ def time_resident(nb, torch, dev, n, V, miss_lo, miss_hi, steps=20, warmup=5, po
         if i >= warmup:
             ms.append(e0.elapsed_time(e1))
     out = eng.finish(want_loci=True)
-    shape = eng.kernel_shape
+    shape = eng.kernel_shape_for(V)
     eng.close()
     t = float(np.median(ms)) * 1e-3
     return t, out, shape, 2.0 * n * V + 32.0 * V + 16.0 * n
@@ -338,7 +338,7 @@ def b200_arm(args):
     rows = make_rows(nb.ROW_DTYPE, V, af, beta, ref_is_ea)
 
     eng = nb.Engine(n, max_rows_per_block=max(block_rows, 1), n_slots=0, device=local)
-    shape = eng.kernel_shape
+    shape = eng.kernel_shape_for(min(block_rows, V))
     # a real (non-default) stream: the default stream's handle is 0, which npc_set_stream reads as
     # "use the context's own stream" and the timing events below would then miss the kernels
     stream = torch.cuda.Stream(device=dev)

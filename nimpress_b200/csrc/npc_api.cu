@@ -51,6 +51,7 @@ struct npc_ctx {
         uint32_t smem = 0;
     };
     TileCfg fast;                           // default: sample slabs x row groups, tile-wise summation
+    TileCfg fast_long;                      // default mode, launches of >= 2 GB of genotypes: the best-filled split, however many row groups
     TileCfg exact_cfg;                      // npc_set_exact_order: 1-D grid, reference summation order
     // cohorts too wide for one resident pass (> ~1.2 M samples): tally + decide over all samples first, then the tile
     // kernel in "decided" mode over wide_slabs slabs of wide_n samples each (both shapes: default / exact order)
@@ -146,6 +147,7 @@ static const void *tile_kernel(int ver, int K, bool exact, int width, int nc) {
         return exact ? (const void *)k_fused_pair<2, true, 2> : (const void *)k_fused_pair<2, false, 2>;
     }
     if (ver == 5) {
+        if (K == 1 && nc > F5_NC_WIDE) return exact ? (const void *)k_fused_pair<1, true, 1, F5_NC_MAX> : (const void *)k_fused_pair<1, false, 1, F5_NC_MAX>;
         if (K == 1 && nc > 16) return exact ? (const void *)k_fused_pair<1, true, 1, F5_NC_WIDE> : (const void *)k_fused_pair<1, false, 1, F5_NC_WIDE>;
         if (K == 1) return exact ? (const void *)k_fused_pair<1, true> : (const void *)k_fused_pair<1, false>;
         return exact ? (const void *)k_fused_pair<2, true> : (const void *)k_fused_pair<2, false>;
@@ -158,7 +160,7 @@ static const void *tile_kernel(int ver, int K, bool exact, int width, int nc) {
 // per thread as long as the warps fit the SM's registers (int8 GT: up to 24 warps on the 72-register instance, cohorts
 // up to ~909,000 samples per GPU), two (up to 16 warps) above that.
 static bool tile_shape(int ver, int width, int64_t nch, int &K, int64_t &nc) {
-    const int max1 = ver == 5 && width == 1 ? std::max(1, std::min(F5_NC_WIDE, env_int("NPC_TILE_NC1", F5_NC_WIDE))) : 16;
+    const int max1 = ver == 5 && width == 1 ? std::max(1, std::min(F5_NC_MAX, env_int("NPC_TILE_NC1", F5_NC_MAX))) : 16;
     K = env_int("NPC_TILE_K", 0);
     if (K != 1 && K != 2) K = nch <= 32 * max1 ? 1 : 2;
     nc = (nch + 32 * K - 1) / (32 * K);
@@ -244,6 +246,16 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         for (const auto &sc : cand) if (std::find(order.begin(), order.end(), sc.second) == order.end()) order.push_back(sc.second);
         for (int gr : order) if (tile_config(c, gr, max_smem, c->fast)) break;
     }
+    // Long launches take the split with the best-filled warps even for a few per cent (bench shard, 500,000 samples: 74 slabs x
+    // 2 row groups on 27 warps fill 97.8 % of the lanes, 148 x 1 on 14 warps 94.3 %: 0.938 against 0.920 of the
+    // roofline); short ones keep round 1's rule -- more row groups leave a CTA fewer tiles to hide ramp-up and
+    // drain behind, and k_add_partials grows with them.
+    c->fast_long.ok = false;
+    if (c->fast.ok && !force_gr && env_int("NPC_TILE_LONG", 1)) {
+        double have = 0.0, best = 0.0; int best_gr = 0;
+        for (const auto &sc : cand) { if (sc.second == c->fast.Gr) have = sc.first; if (sc.first > best) { best = sc.first; best_gr = sc.second; } }
+        if (best_gr && best_gr != c->fast.Gr && best > have * 1.02) tile_config(c, best_gr, max_smem, c->fast_long);
+    }
     tile_config(c, 1, max_smem, c->exact_cfg);
     if (!c->fast.ok && c->width == 1 && env_int("NPC_TILE_V", 5) != 4) {
         // no shape holds a whole row's share in one CTA: the fewest equal slabs (multiples of 1024 samples) the tile kernel can hold
@@ -253,8 +265,8 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
             else c->wide.ok = c->wide_exact.ok = false;
         }
     }
-    for (int ex = 0; ex < 4; ex++) {
-        const npc_ctx::TileCfg &t = ex == 0 ? c->fast : ex == 1 ? c->exact_cfg : ex == 2 ? c->wide : c->wide_exact;
+    for (int ex = 0; ex < 5; ex++) {
+        const npc_ctx::TileCfg &t = ex == 0 ? c->fast : ex == 1 ? c->exact_cfg : ex == 2 ? c->wide : ex == 3 ? c->wide_exact : c->fast_long;
         if (!t.ok) continue;
         // the device's maximum, not this shape's need: the attribute belongs to the kernel function, which other contexts
         // of the process (and this context's other shapes) launch with other sizes
@@ -267,7 +279,8 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
         NPC_CUDA(c, cudaMemset(c->d_fcounts, 0, words * sizeof(ull)));
         if (env_int("NPC_TRACE", 0)) { NPC_CUDA(c, cudaMalloc(&c->d_trace, 8 * sizeof(ull))); NPC_CUDA(c, cudaMemset(c->d_trace, 0, 8 * sizeof(ull))); }
     }
-    if (c->fast.ok && c->fast.Gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(c->fast.Gr - 1) * (size_t)c->n * sizeof(double)));
+    const int max_gr = std::max(c->fast.ok ? c->fast.Gr : 1, c->fast_long.ok ? c->fast_long.Gr : 1);
+    if (max_gr > 1) NPC_CUDA(c, cudaMalloc(&c->d_partials, (size_t)(max_gr - 1) * (size_t)c->n * sizeof(double)));
     c->exact = env_int("NPC_EXACT", 0) != 0;
     return NPC_OK;
 }
@@ -386,16 +399,24 @@ extern "C" int npc_trace(npc_ctx *ctx, uint64_t out[8]) {
     return NPC_OK;
 }
 
-extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) {
-    if (!ctx || !shape) return NPC_EINVAL;
+// a launch of at least this many genotype bytes counts as long (fast_long): 2 GB = ~330 us of streaming; NPC_TILE_LONG_MB overrides
+static const npc_ctx::TileCfg &fast_config(const npc_ctx *c, int64_t n_rows) {
+    if (!c->fast_long.ok) return c->fast;
+    const int64_t long_bytes = (int64_t)env_int("NPC_TILE_LONG_MB", 2048) << 20;
+    return n_rows * c->row_stride >= long_bytes ? c->fast_long : c->fast;
+}
+
+extern "C" int npc_kernel_shape2(const npc_ctx *ctx, int64_t n_rows, int32_t shape[8]) {
+    if (!ctx || !shape || n_rows < 0) return NPC_EINVAL;
     const bool wide = !(ctx->exact ? ctx->exact_cfg.ok : ctx->fast.ok) && ctx->wide.ok;
-    const npc_ctx::TileCfg &t = wide ? (ctx->exact ? ctx->wide_exact : ctx->wide) : ctx->exact ? ctx->exact_cfg : ctx->fast;
+    const npc_ctx::TileCfg &t = wide ? (ctx->exact ? ctx->wide_exact : ctx->wide) : ctx->exact ? ctx->exact_cfg : fast_config(ctx, n_rows);
     memset(shape, 0, 8 * sizeof(int32_t));
     if (!t.ok) return NPC_OK;
     shape[0] = wide ? 3 : ctx->exact ? 1 : 2; shape[1] = t.Gs * 1000 + (ctx->exact ? 1 : t.Gr); shape[2] = t.nc; shape[3] = t.K;
     shape[4] = F4_R; shape[5] = t.Sr * 1000 + t.Sc; shape[6] = t.L * 100 + t.GD * 10 + t.A; shape[7] = (int32_t)t.smem;
     return NPC_OK;
 }
+extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) { return npc_kernel_shape2(ctx, 0, shape); }
 
 extern "C" int npc_set_dosage_rows(npc_ctx *ctx, int32_t on) {
     if (!ctx) return NPC_EINVAL;
@@ -604,7 +625,7 @@ static int launch_dosage(npc_ctx *c, const uint8_t *gt, int64_t row_stride, cons
 
 static int launch_block(npc_ctx *c, const uint8_t *gt, int64_t row_stride, const npc_row *d_rows, int64_t n_rows) {
     if (c->ds) return launch_dosage(c, gt, row_stride, d_rows, n_rows);
-    if (c->exact ? c->exact_cfg.ok : c->fast.ok) return launch_fused(c, c->exact ? c->exact_cfg : c->fast, c->exact, gt, row_stride, d_rows, n_rows);
+    if (c->exact ? c->exact_cfg.ok : c->fast.ok) return launch_fused(c, c->exact ? c->exact_cfg : fast_config(c, n_rows), c->exact, gt, row_stride, d_rows, n_rows);
     if (c->wide.ok && env_int("NPC_WIDE", 1)) return launch_wide(c, c->exact, gt, row_stride, d_rows, n_rows);
     int rc = launch_count(c, gt, row_stride, d_rows, n_rows, c->d_counts);
     if (rc) return rc;

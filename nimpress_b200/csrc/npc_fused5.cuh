@@ -34,6 +34,7 @@
 namespace npc {
 
 constexpr int F5_NC_WIDE = 24;                // consumer warps of the K = 1 "wide" instance (72 registers); all others: 16
+constexpr int F5_NC_MAX = 28;                 // ... and of the widest one: 32 warps per CTA, 64 registers (24 bytes of spills)
 constexpr int F5_R = 4;                       // rows per tile
 constexpr uint32_t F5_NT = 4;                 // tables per parity: T = 1, 2, 3 and "no allele matches" (T >= 4)
 constexpr uint32_t F5_TAB_BYTES = 1152;       // 262 four-byte entries (index <= 3 * 87), padded to a multiple of 128

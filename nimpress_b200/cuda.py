@@ -81,6 +81,7 @@ def load_library():
         "npc_comm_sum_counts": (C.c_int, [vp, vp, i64]),
         "npc_launch_count": (i64, [vp]),
         "npc_kernel_shape": (C.c_int, [vp, C.POINTER(i32 * 8)]),
+        "npc_kernel_shape2": (C.c_int, [vp, i64, C.POINTER(i32 * 8)]),
         "npc_trace": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "npc_set_exact_order": (C.c_int, [vp, i32]),
         "npc_set_dosage_rows": (C.c_int, [vp, i32]),
@@ -319,8 +320,12 @@ class Engine:
 
     @property
     def kernel_shape(self):
+        return self.kernel_shape_for(0)
+
+    def kernel_shape_for(self, n_rows):
+        """Launch shape of a block of n_rows score rows (long launches may split the grid differently)."""
         a = (C.c_int32 * 8)()
-        self._ck(self.L.npc_kernel_shape(self.h, C.byref(a)))
+        self._ck(self.L.npc_kernel_shape2(self.h, int(n_rows), C.byref(a)))
         keys = ("fused", "grid", "consumer_warps", "chunks_per_thread", "rows_per_tile", "stages", "lag", "smem_bytes")
         d = dict(zip(keys, list(a)))
         d["decider_warps"], d["decider_tiles"], d["lag"] = d["lag"] % 10, d["lag"] % 100 // 10, d["lag"] // 100

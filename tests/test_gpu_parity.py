@@ -517,6 +517,26 @@ def test_wide_cohorts(nb, mode, n):
         assert np.array_equal(bits(a["scores"][ok]), bits(b["scores"][:4096][ok]))
 
 
+def test_long_launch_split(nb, monkeypatch):
+    """A launch of >= 2 GB of genotypes may split the grid differently from a short one (more row groups, better-filled warps:
+    250,000 samples run 74 slabs x 2 row groups on 14 warps when short, 49 x 3 on 20 warps when long).  With the threshold
+    lowered to 1 MB the same context serves a short and a "long" launch; both match the oracle, the records exactly."""
+    rng = np.random.default_rng(77)
+    n, V = 250_000, 256
+    gt = random_cohort(rng, n, V, miss_rate=0.01, n_alt=2)
+    rows = random_rows(rng, V, n_rows=V + 40, n_alt=2)
+    want = oracle(gt, n, rows)
+    eng = nb.Engine(n, max_rows_per_block=512, n_slots=2)
+    short, long_ = eng.kernel_shape_for(16), eng.kernel_shape_for(1 << 20)
+    assert short["fused"] == long_["fused"] == 2 and long_["row_groups"] > short["row_groups"], (short, long_)
+    for mb in ("1", "1000000"):
+        monkeypatch.setenv("NPC_TILE_LONG_MB", mb)
+        eng.set_policy(); eng.reset()
+        eng.score_host(gt, rows)
+        assert_parity(eng.finish(), want, exact=False)
+    eng.close()
+
+
 def test_kernel_shape_choice_and_contexts_side_by_side(nb):
     """Two findings of the round-2 fuzz (tools/fuzz_parity.py).  157,929 samples: the best-scoring split of the grid (7 row
     groups) does not fit shared memory -- the next candidate must be taken, not the slow generic path.  And the
