@@ -474,7 +474,8 @@ def b200_arm(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")          # dram bytes of one ncu --set full capture of this launch shape
     if os.path.exists(tpath):
         for t in json.load(open(tpath)):
-            if t["samples"] == n and t["rows"] == launch_rows and t["fused"] == shape["fused"] and t.get("ver", 5) == tile_ver:
+            if (t["samples"] == n and t["rows"] == launch_rows and t["fused"] == shape["fused"] and t.get("ver", 5) == tile_ver
+                    and t.get("row_groups", 1) == shape.get("row_groups", 1)):
                 traffic, traffic_src = t["dram_bytes"], t["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
