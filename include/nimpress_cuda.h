@@ -38,7 +38,7 @@
  *   NPC_EXACT=1              exact-order mode for every context (as npc_set_exact_order)
  *   NPC_TILE_K / _SR / _SC / _L / _A / _GR / _GD / _NC1   launch shape of the fused tile kernel (chunks per thread, raw
  *                            stages, index tiles, lag, decider warps, row groups, tiles per decider pass, most warps at K = 1)
- *   NPC_TILE_LONG=0          no separate grid split for long launches; NPC_TILE_LONG_MB=<MB>: what counts as long (default 2048)
+ *   NPC_TILE_LONG=0          no separate grid split for long launches; NPC_TILE_LONG_MB=<MB>: what counts as long (default 1536, or 192 when short launches split the rows too)
  *   NPC_TILE_V=4             the round-1 tile kernel (npc_fused4.cuh) instead of the pair-lookup kernel (npc_fused5.cuh)
  *   NPC_TILE_SLEEP=<ns>      auxiliary warps of the tile kernel poll + nanosleep instead of a suspended try_wait
  *   NPC_MULTI=0 | 1          npc_score_resident_multi: never / always the tensor-core contraction (default: >= 3 definitions)
@@ -301,7 +301,7 @@ int npc_set_dosage_rows(npc_ctx *ctx, int32_t on);
  * per tile, raw stages * 1000 + index-ring tiles, lag * 100 + tiles per decider pass * 10 + decider warps, dynamic
  * shared-memory bytes. */
 int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
-/* The same for a launch of n_rows score rows: in the default mode a launch of >= 2 GB of genotypes may use another
+/* The same for a launch of n_rows score rows: in the default mode a launch of >= 1.5 GB of genotypes (192 MB for cohorts whose short launches split the rows too) may use another
  * split of the grid (more row groups, better-filled warps) than a short one; npc_kernel_shape = npc_kernel_shape2(ctx, 0, ..). */
 int npc_kernel_shape2(const npc_ctx *ctx, int64_t n_rows, int32_t shape[8]);
 /* NPC_TRACE=1 at npc_create: %globaltimer stamps (ns) of CTA 0 of the last tile-kernel launch -- launch start, code

@@ -51,7 +51,7 @@ struct npc_ctx {
         uint32_t smem = 0;
     };
     TileCfg fast;                           // default: sample slabs x row groups, tile-wise summation
-    TileCfg fast_long;                      // default mode, launches of >= 2 GB of genotypes: the best-filled split, however many row groups
+    TileCfg fast_long;                      // default mode, long launches (fast_config): the best-filled split, however many row groups
     TileCfg exact_cfg;                      // npc_set_exact_order: 1-D grid, reference summation order
     // cohorts too wide for one resident pass (> ~1.2 M samples): tally + decide over all samples first, then the tile
     // kernel in "decided" mode over wide_slabs slabs of wide_n samples each (both shapes: default / exact order)
@@ -399,10 +399,14 @@ extern "C" int npc_trace(npc_ctx *ctx, uint64_t out[8]) {
     return NPC_OK;
 }
 
-// a launch of at least this many genotype bytes counts as long (fast_long): 2 GB = ~330 us of streaming; NPC_TILE_LONG_MB overrides
+// A launch of at least this many genotype bytes counts as long (fast_long).  Measured crossover (500,000 samples, 148 x 1
+// against 74 x 2): the extra k_add_partials launch and the shorter per-CTA tile runs cost more than the fuller warps gain
+// below ~1.5 GB.  When the short split has row groups of its own the partial sums are added anyway and the better-filled
+// split wins from ~200 MB on (250,000 samples, 74 x 2 against 49 x 3: +3.5 % at 256 MB, +5.5 % at 1 GB).
+// NPC_TILE_LONG_MB overrides.
 static const npc_ctx::TileCfg &fast_config(const npc_ctx *c, int64_t n_rows) {
     if (!c->fast_long.ok) return c->fast;
-    const int64_t long_bytes = (int64_t)env_int("NPC_TILE_LONG_MB", 2048) << 20;
+    const int64_t long_bytes = (int64_t)env_int("NPC_TILE_LONG_MB", c->fast.Gr > 1 ? 192 : 1536) << 20;
     return n_rows * c->row_stride >= long_bytes ? c->fast_long : c->fast;
 }
 

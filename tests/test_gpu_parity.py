@@ -518,8 +518,8 @@ def test_wide_cohorts(nb, mode, n):
 
 
 def test_long_launch_split(nb, monkeypatch):
-    """A launch of >= 2 GB of genotypes may split the grid differently from a short one (more row groups, better-filled warps:
-    250,000 samples run 74 slabs x 2 row groups on 14 warps when short, 49 x 3 on 20 warps when long).  With the threshold
+    """A long launch (>= 1.5 GB of genotypes, or >= 192 MB where short launches split the rows too) may split the grid
+    differently from a short one (more row groups, better-filled warps: 250,000 samples run 74 slabs x 2 row groups on 14 warps when short, 49 x 3 on 20 warps when long).  With the threshold
     lowered to 1 MB the same context serves a short and a "long" launch; both match the oracle, the records exactly."""
     rng = np.random.default_rng(77)
     n, V = 250_000, 256

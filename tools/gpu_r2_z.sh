@@ -1,5 +1,8 @@
 #!/bin/bash
-# round 2: ncu --set full of the bench launch shape after the long-launch split (74 slabs x 2 row groups, 27 warps), and the launch list
-mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fused_pair -s 2 -c 1 -o gpurun_out/pair_long -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extra > gpurun_out/ncu_long.log 2>&1; tail -2 gpurun_out/ncu_long.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_long.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extra > gpurun_out/launches_long.log 2>&1; tail -1 gpurun_out/launches_long.log | cut -c1-200
+# round 2: where is the crossover between the short-launch and the long-launch grid split?
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --brief"
+for nv in "100000 697" "200000 730" "250000 512" "250000 2048" "500000 128" "500000 256" "500000 512" "500000 1024" "500000 2048"; do
+  set -- $nv
+  echo "n=$1 V=$2 ($(( $1 * $2 * 2 / 1000000 )) MB): short $(NPC_TILE_LONG_MB=100000 timeout 200 $B --samples $1 --variants $2 2>&1 | tail -1 | cut -c1-62)"
+  echo "                                   long  $(NPC_TILE_LONG_MB=1 timeout 200 $B --samples $1 --variants $2 2>&1 | tail -1 | cut -c1-62)"
+done
