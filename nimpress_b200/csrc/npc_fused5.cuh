@@ -25,6 +25,12 @@
 //    LDS.64 and two DADD per sample per four genotypes); the index-ring byte of a sample pair is
 //    [sample 0: rows a,b | sample 1: rows a,b], one byte for rows (0,1) and one for rows (2,3).
 //
+//  * Wide cohorts.  One chunk (8 samples) per consumer thread up to 28 warps (~1.06 M samples on 148 CTAs); above that
+//    two chunk SETS per tile (K = 2), each set a raw stage of its own, so the ring holds 3-4 half-tile stages where two
+//    whole tiles would leave no room for the index ring.  Where the index ring is short (a tile of 1 M samples is 11 KB
+//    of ring and 1.4 us of streaming) the deciders take 4 tiles per pass instead of 8: the first tile of a pass waits
+//    for its last to be counted by the whole grid, and that wait must fit the lag.
+//
 // Rounding and the EXACT mode are as in npc_fused4.cuh: every addend is the reference's rounded
 // product fl(dosage*beta) (src/nimpress.nim:640); the default mode adds rows (0,1) and (2,3) of a
 // tile to each other first, EXACT adds row by row in score-file order, bit for bit the reference.
@@ -101,9 +107,10 @@ __device__ __forceinline__ uint32_t f5_slow_code16(uint32_t word, int eaidx) {
 }
 
 // W = bytes per stored allele value: 1 (int8, the usual BCF GT) or 2 (int16: records with more than 63 alleles)
-// NCMAX = most consumer warps the instance is launched with (+ producer + publisher + <= 2 deciders): 16 keeps ~96
-// registers per thread; the K = 1 instance for 17-24 warps is held to 72 (measured: 3 % slower than the 16-warp instance on
-// 14 warps, but 0.95-0.99 of the roofline at 800-900 k samples where two chunks per thread on 11-12 warps reach 0.81-0.88)
+// NCMAX = most consumer warps the instance is launched with (+ producer + publisher + <= 2 deciders): 16 keeps up to 96
+// registers per thread; the K = 1 instances for 17-24 and 25-28 warps are held to 72 and 64 (measured: each ~3 % slower than
+// the next one up at equal warp count, but 0.95-0.99 of the roofline at 800-950 k samples where two chunks per thread on
+// 11-13 warps reach 0.81-0.88, and 27 warps on half as many sample slabs beat 14 at 500 k because their lanes are fuller)
 template <int K, bool EXACT, int W = 1, int NCMAX = 16>
 __global__ void __launch_bounds__((NCMAX + 4) * 32, 1)
 k_fused_pair(const FusedParams P) {
