@@ -304,6 +304,14 @@ int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]);
 /* The same for a launch of n_rows score rows: in the default mode a launch of >= 1.5 GB of genotypes (192 MB for cohorts whose short launches split the rows too) may use another
  * split of the grid (more row groups, better-filled warps) than a short one; npc_kernel_shape = npc_kernel_shape2(ctx, 0, ..). */
 int npc_kernel_shape2(const npc_ctx *ctx, int64_t n_rows, int32_t shape[8]);
+/* The launch-shape choice alone, no device needed (host arithmetic; used by the CPU tests to check every cohort size):
+ * what a context of n_samples diploid samples of gt_width bytes on a GPU with num_sms SMs and max_smem bytes of
+ * shared memory per CTA would launch for a block of n_rows rows.  plan = { mode (0: generic kernels, 2: tile kernel,
+ * 1: exact order, 3: decided-mode slabs), sample slabs, row groups, chunks per thread K, consumer warps, cells * 16 W bytes,
+ * raw stages, index-ring tiles, lag, decider warps, tiles per decider pass, shared-memory bytes, threads per CTA, most
+ * consumer warps of the kernel instance, sample slabs of the wide mode, samples per such slab }. */
+int npc_plan_shape(int64_t n_samples, int32_t gt_width, int32_t num_sms, int32_t max_smem, int64_t n_rows, int32_t exact,
+                   int32_t plan[16]);
 /* NPC_TRACE=1 at npc_create: %globaltimer stamps (ns) of CTA 0 of the last tile-kernel launch -- launch start, code
  * tables ready, first tile counted, last tile counted, last tile accumulated, sums stored -- for the launch-floor
  * analysis of short launches (profiles/). */

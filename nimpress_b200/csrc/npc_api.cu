@@ -217,11 +217,13 @@ static bool tile_config(const npc_ctx *c, int gr, int max_smem, npc_ctx::TileCfg
 // small to give every SM ~14 consumer warps from the sample axis alone (< ~500k samples) also splits
 // the rows into contiguous groups whose partial sums are added in group order afterwards.  Exact
 // order: Gr = 1.  NPC_TILE_{K,SR,SC,L,A,GR} override for tuning; NPC_FUSED=0 forces the two-kernel path.
-static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
-    c->fast.ok = c->exact_cfg.ok = false;
-    if ((c->width != 1 && c->width != 2) || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return NPC_OK;
-    c->num_sms = prop.multiProcessorCount;
-    const int max_smem = (int)prop.sharedMemPerBlockOptin;
+// Pure host arithmetic (no CUDA call): fills c->fast, fast_long, exact_cfg, wide, wide_exact from n, width, ploidy, the SM
+// count and the shared memory a CTA may take.  npc_plan_shape exposes it so that the choice can be tested for every
+// cohort size without a device (tests/test_shape_plan.py).
+static void plan_shapes(npc_ctx *c, int num_sms, int max_smem) {
+    c->fast.ok = c->fast_long.ok = c->exact_cfg.ok = c->wide.ok = c->wide_exact.ok = false;
+    if ((c->width != 1 && c->width != 2) || c->ploidy != 2 || c->n == 0 || c->n >= (1ll << 27) || env_int("NPC_FUSED", 1) == 0) return;
+    c->num_sms = num_sms;
     const int64_t C = (c->n + 7) / 8;
     const int force_gr = env_int("NPC_TILE_GR", 0);
     // candidates in the order of preference: the score of round 1 (SMs used x warps kept busy), a larger number of row
@@ -250,7 +252,6 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
     // 2 row groups on 27 warps fill 97.8 % of the lanes, 148 x 1 on 14 warps 94.3 %: 0.938 against 0.920 of the
     // roofline); short ones keep round 1's rule -- more row groups leave a CTA fewer tiles to hide ramp-up and
     // drain behind, and k_add_partials grows with them.
-    c->fast_long.ok = false;
     if (c->fast.ok && !force_gr && env_int("NPC_TILE_LONG", 1)) {
         double have = 0.0, best = 0.0; int best_gr = 0;
         for (const auto &sc : cand) { if (sc.second == c->fast.Gr) have = sc.first; if (sc.first > best) { best = sc.first; best_gr = sc.second; } }
@@ -265,6 +266,12 @@ static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
             else c->wide.ok = c->wide_exact.ok = false;
         }
     }
+}
+
+static int fused_configure(npc_ctx *c, const cudaDeviceProp &prop) {
+    const int max_smem = (int)prop.sharedMemPerBlockOptin;
+    plan_shapes(c, prop.multiProcessorCount, max_smem);
+    if (!c->fast.ok && !c->exact_cfg.ok && !c->wide.ok) return NPC_OK;
     for (int ex = 0; ex < 5; ex++) {
         const npc_ctx::TileCfg &t = ex == 0 ? c->fast : ex == 1 ? c->exact_cfg : ex == 2 ? c->wide : ex == 3 ? c->wide_exact : c->fast_long;
         if (!t.ok) continue;
@@ -421,6 +428,27 @@ extern "C" int npc_kernel_shape2(const npc_ctx *ctx, int64_t n_rows, int32_t sha
     return NPC_OK;
 }
 extern "C" int npc_kernel_shape(const npc_ctx *ctx, int32_t shape[8]) { return npc_kernel_shape2(ctx, 0, shape); }
+
+extern "C" int npc_plan_shape(int64_t n_samples, int32_t gt_width, int32_t num_sms, int32_t max_smem, int64_t n_rows, int32_t exact,
+                              int32_t plan[16]) {
+    if (!plan || n_samples < 0 || num_sms < 1 || max_smem < 1 || n_rows < 0) return NPC_EINVAL;
+    npc_ctx *c = new npc_ctx;
+    c->n = n_samples; c->ploidy = 2; c->width = gt_width;
+    c->row_stride = ((c->n * c->ploidy * c->width + 127) / 128) * 128;
+    plan_shapes(c, num_sms, max_smem);
+    const bool wide = !(exact ? c->exact_cfg.ok : c->fast.ok) && c->wide.ok;
+    const npc_ctx::TileCfg &t = wide ? (exact ? c->wide_exact : c->wide) : exact ? c->exact_cfg : fast_config(c, n_rows);
+    memset(plan, 0, 16 * sizeof(int32_t));
+    if (t.ok) {
+        const int A = wide ? 1 : t.A;
+        const int32_t v[16] = { wide ? 3 : exact ? 1 : 2, t.Gs, exact || wide ? 1 : t.Gr, t.K, t.nc, t.slab, t.Sr, t.Sc, t.L, A, t.GD, (int32_t)t.smem,
+                                (t.nc + 2 + A) * 32, t.K == 1 && c->width == 1 ? (t.nc > F5_NC_WIDE ? F5_NC_MAX : t.nc > 16 ? F5_NC_WIDE : 16) : 16,
+                                wide ? c->wide_slabs : 1, wide ? (int32_t)c->wide_n : (int32_t)std::min<int64_t>(c->n, INT32_MAX) };
+        memcpy(plan, v, sizeof(v));
+    }
+    delete c;
+    return NPC_OK;
+}
 
 extern "C" int npc_set_dosage_rows(npc_ctx *ctx, int32_t on) {
     if (!ctx) return NPC_EINVAL;

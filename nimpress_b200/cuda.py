@@ -82,6 +82,7 @@ def load_library():
         "npc_launch_count": (i64, [vp]),
         "npc_kernel_shape": (C.c_int, [vp, C.POINTER(i32 * 8)]),
         "npc_kernel_shape2": (C.c_int, [vp, i64, C.POINTER(i32 * 8)]),
+        "npc_plan_shape": (C.c_int, [i64, i32, i32, i32, i64, i32, C.POINTER(i32 * 16)]),
         "npc_trace": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "npc_set_exact_order": (C.c_int, [vp, i32]),
         "npc_set_dosage_rows": (C.c_int, [vp, i32]),
@@ -106,6 +107,19 @@ def _ptr(x):
     if isinstance(x, np.ndarray):
         return x.ctypes.data
     return x.data_ptr()
+
+
+PLAN_KEYS = ("mode", "sample_slabs", "row_groups", "chunks_per_thread", "consumer_warps", "slab_bytes", "raw_stages", "index_tiles",
+             "lag", "decider_warps", "decider_tiles", "smem_bytes", "threads", "instance_warps", "wide_slabs", "wide_samples")
+
+
+def plan_shape(n_samples, gt_width=1, num_sms=148, max_smem=232448, n_rows=0, exact=False):
+    """npc_plan_shape: the launch shape a context of this size would choose on such a GPU -- host arithmetic, no device."""
+    a = (C.c_int32 * 16)()
+    rc = load_library().npc_plan_shape(int(n_samples), int(gt_width), int(num_sms), int(max_smem), int(n_rows), int(bool(exact)), C.byref(a))
+    if rc != 0:
+        raise NpcError(f"npc_plan_shape: error {rc}")
+    return dict(zip(PLAN_KEYS, list(a)))
 
 
 def reduce_contexts(engines, offset=None):

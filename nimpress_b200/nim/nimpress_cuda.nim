@@ -74,6 +74,7 @@ proc npc_launch_count*(ctx: NpcCtx): int64
 proc npc_multi_contractions*(ctx: NpcCtx): int64
 proc npc_kernel_shape*(ctx: NpcCtx; shape: ptr array[8, int32]): cint
 proc npc_kernel_shape2*(ctx: NpcCtx; n_rows: int64; shape: ptr array[8, int32]): cint
+proc npc_plan_shape*(n_samples: int64; gt_width, num_sms, max_smem: int32; n_rows: int64; exact: int32; plan: ptr array[16, int32]): cint
 proc npc_synth_fill_device*(ctx: NpcCtx; gtDev: pointer; rowStride, v0, nRows: int64; seed: uint64;
                             afThr16Dev, missThr24Dev: ptr uint32; altCodeDev: ptr int32): cint
 proc npc_version*(): cint
