@@ -3,8 +3,9 @@
 # Builds an instrumented libnimpress_host.so in place, runs tests/test_host_cpu.py, restores the normal build.
 set -e
 cd "$(dirname "$0")/../nimpress_b200/host"
-cp ../lib/libnimpress_host.so /tmp/libnimpress_host.orig.so
-trap 'cp /tmp/libnimpress_host.orig.so ../lib/libnimpress_host.so' EXIT
+LIB="$(pwd)/../lib/libnimpress_host.so"
+cp "$LIB" /tmp/libnimpress_host.orig.so
+trap 'cp /tmp/libnimpress_host.orig.so "$LIB"' EXIT
 g++ -std=c++17 -O1 -g -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -ffp-contract=off -shared -o ../lib/libnimpress_host.so \
     inputs.cpp variant_source.cpp region_index.cpp fast_inflate.cpp stats.cpp driver.cpp host_api.cpp -L../lib -lnimpress_cuda -lz -lpthread -Wl,-rpath,'$ORIGIN'
 cd ../..
