@@ -155,9 +155,11 @@ bool fast_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len
                 if (!build(lens + hlit, (int)hdist, DIST_P, true, t.dist, (int)(sizeof t.dist / 4))) return false;
             }
             // ---- symbols ----
+            // >= 56 bits after a refill: a literal/length code (15 + 5) and a distance code (15 + 13) fit.  The entry of the
+            // NEXT symbol is looked up before a match is copied, so that the table load overlaps the copy.
+            REFILL();
+            uint32_t e = t.lit[bb & ((1u << LIT_P) - 1u)];
             for (;;) {
-                REFILL();                                               // >= 56 bits: a literal/length code (15 + 5) and a distance code (15 + 13) fit
-                uint32_t e = t.lit[bb & ((1u << LIT_P) - 1u)];
                 if (e_kind(e) == K_LINK) {
                     if (e == INVALID) return false;
                     TAKE(LIT_P);
@@ -176,6 +178,8 @@ bool fast_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len
                         TAKE(e_bits(e2));
                         *op++ = (uint8_t)e_payload(e2);
                     }
+                    REFILL();
+                    e = t.lit[bb & ((1u << LIT_P) - 1u)];
                     continue;
                 }
                 if (e_kind(e) == K_EOB) break;
@@ -193,10 +197,13 @@ bool fast_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len
                 const uint32_t dist = e_payload(d) + ((uint32_t)bb & ((1u << e_extra(d)) - 1u));
                 TAKE(e_extra(d));
                 if (dist > (size_t)(op - out) || len > (size_t)(out_end - op)) return false;
+                REFILL();
+                e = t.lit[bb & ((1u << LIT_P) - 1u)];
                 const uint8_t *src = op - dist;
                 uint8_t *const stop = op + len;
-                if (dist >= 8) {                                        // word copies; the last one may run up to 7 bytes past `stop` (caller's slack)
-                    do { store64(op, load64(src)); op += 8; src += 8; } while (op < stop);
+                if (dist >= 8) {                                        // word copies; they may run up to 13 bytes past `stop` (caller's slack: 16)
+                    store64(op, load64(src)); store64(op + 8, load64(src + 8));        // most matches are short: no loop, no loop-exit misprediction
+                    if (len > 16) { op += 16; src += 16; do { store64(op, load64(src)); op += 8; src += 8; } while (op < stop); }
                 } else if (dist == 1) {                                 // a run of one byte
                     const uint64_t v = 0x0101010101010101ull * *src;
                     do { store64(op, v); op += 8; } while (op < stop);
