@@ -18,7 +18,7 @@ def sizes():
     return sorted(set(fixed + dense + [int(x) for x in rng.integers(1, 3_000_000, size=400)]))
 
 
-def check(n, width, plan, exact):
+def check(n, width, plan, exact, sms=SMS):
     mode = plan["mode"]
     if mode == 0:
         return
@@ -28,7 +28,7 @@ def check(n, width, plan, exact):
     assert width == 1 or plan["instance_warps"] == 16, plan                       # int16 GT: the 16-warp instances only
     assert plan["threads"] == (nc + 2 + A) * 32 <= (plan["instance_warps"] + 4) * 32 <= 1024, plan
     assert plan["threads"] * REGS[plan["instance_warps"]] <= 65536, plan          # one CTA's registers fit the SM
-    assert plan["sample_slabs"] * plan["row_groups"] <= SMS, plan                 # cooperative launch: one CTA per SM
+    assert plan["sample_slabs"] * plan["row_groups"] <= sms, plan                 # cooperative launch: one CTA per SM
     assert plan["smem_bytes"] <= SMEM, plan
     assert gd in (4, 8) and plan["index_tiles"] >= gd + 2 and gd <= plan["lag"] <= plan["index_tiles"] - 1, plan
     assert plan["raw_stages"] >= (3 if K == 2 else 2), plan
@@ -55,6 +55,16 @@ def test_every_cohort_size_gets_a_feasible_shape(width):
         for exact in (False, True):
             for n_rows in (64, 1 << 20):
                 check(n, width, cuda.plan_shape(n, width, SMS, SMEM, n_rows, exact), exact)
+
+
+@pytest.mark.parametrize("sms", [144, 132, 74, 16])
+def test_other_sm_counts(sms):
+    """A part with fewer SMs (another sm_100 SKU, a MIG slice): the same invariants, and still no cohort on the generic path."""
+    for n in sizes()[::3]:
+        for exact in (False, True):
+            p = cuda.plan_shape(n, 1, sms, SMEM, 1 << 20, exact)
+            assert p["mode"] != 0, (sms, n, p)
+            check(n, 1, p, exact, sms)
 
 
 def test_no_holes_in_the_fused_range():
